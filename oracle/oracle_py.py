@@ -1,0 +1,188 @@
+"""ctypes binding of oracle/liboracle.so -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  PARITY UNPINNED: see oracle/adv_oracle.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+HOR = {"UPW1": 0, "MUSCL": 1, "MFCT": 2}
+VER = {"UPW1": 0, "QR4C": 1, "PPM": 2, "CDIFF": 3}
+LIM = {"NON": 0, "NONE": 0, "FCT": 1}
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+
+
+class OraMesh(C.Structure):
+    _fields_ = [("nl", C.c_int), ("myDim_nod2D", C.c_int), ("eDim_nod2D", C.c_int),
+                ("myDim_elem2D", C.c_int), ("eDim_elem2D", C.c_int), ("myDim_edge2D", C.c_int),
+                ("nod_in_elem_ld", C.c_int),
+                ("edges", c_ip), ("edge_tri", c_ip), ("elem2D_nodes", c_ip), ("nod_in_elem2D", c_ip),
+                ("nod_in_elem2D_num", c_ip), ("nlevels", c_ip), ("ulevels", c_ip),
+                ("nlevels_nod2D", c_ip), ("ulevels_nod2D", c_ip),
+                ("edge_cross_dxdy", c_dp), ("edge_dxdy", c_dp), ("elem_cos", c_dp),
+                ("area", c_dp), ("areasvol", c_dp),
+                ("helem", c_dp), ("hnode", c_dp), ("hnode_new", c_dp), ("zbar_3d_n", c_dp),
+                ("Z_3d_n", c_dp), ("zbar_n_bot", c_dp)]
+
+
+class OraWork(C.Structure):
+    _fields_ = [("fct_LO", c_dp), ("adv_flux_hor", c_dp), ("adv_flux_ver", c_dp),
+                ("fct_ttf_min", c_dp), ("fct_ttf_max", c_dp), ("fct_plus", c_dp), ("fct_minus", c_dp),
+                ("tvert_max", c_dp), ("tvert_min", c_dp), ("AUX", c_dp), ("nboundary_lay", c_ip)]
+
+
+class OraRank(C.Structure):
+    _fields_ = [("mesh", OraMesh), ("work", OraWork),
+                ("vel", c_dp), ("w", c_dp), ("wi", c_dp), ("we", c_dp),
+                ("use_wsplit", C.c_int), ("ntr", C.c_int),
+                ("values", C.POINTER(c_dp)), ("valuesAB", C.POINTER(c_dp)),
+                ("edge_up_dn_grad", C.POINTER(c_dp)), ("dttf_h", C.POINTER(c_dp)), ("dttf_v", C.POINTER(c_dp)),
+                ("hor", c_ip), ("ver", c_ip), ("lim", c_ip), ("opth", c_dp), ("optv", c_dp),
+                ("halo_owner", c_ip), ("halo_owner_idx", c_ip)]
+
+
+def build(fast: bool = False, force: bool = False) -> str:
+    """Compile the restatement with gcc (Makefile recipe).  ``fast`` = -O3 -march=native flavour
+    for timing on the machine it is built on."""
+    name = "liboracle_fast.so" if fast else "liboracle.so"
+    path = os.path.join(_HERE, name)
+    src = os.path.join(_HERE, "adv_oracle.c")
+    if force or not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, name], stdout=subprocess.DEVNULL)
+    return path
+
+
+_libs = {}
+
+
+def lib(fast: bool = False):
+    if fast not in _libs:
+        L = C.CDLL(build(fast))
+        L.ora_run_ranks.restype = C.c_double
+        L.ora_run_ranks.argtypes = [C.c_int, C.POINTER(OraRank), C.c_double, C.c_int, C.c_int]
+        L.ora_do_oce_adv_tra.restype = C.c_int
+        _libs[fast] = L
+    return _libs[fast]
+
+
+def _dp(a: np.ndarray):
+    assert a.dtype == np.float64 and a.flags.c_contiguous
+    return a.ctypes.data_as(c_dp)
+
+
+def _ip(a: np.ndarray):
+    assert a.dtype == np.int32 and a.flags.c_contiguous
+    return a.ctypes.data_as(c_ip)
+
+
+def _np(t) -> np.ndarray:
+    if isinstance(t, np.ndarray):
+        return np.ascontiguousarray(t)
+    return np.ascontiguousarray(t.detach().cpu().numpy())
+
+
+class OracleRank:
+    """All arrays of one rank, kept alive on the Python side, plus the C structs pointing at them."""
+
+    def __init__(self, mesh, state, tracers, nboundary_lay, alias_aux: bool = False):
+        m = mesh
+        self.mesh_py = m
+        L, nl, Nh, N, T, E = m.L, m.nl, m.Nh, m.N, m.T, m.E
+        k = self.keep = {}
+        for name in ("edges", "edge_tri", "elem2D_nodes", "nod_in_elem2D", "nod_in_elem2D_num",
+                     "nlevels", "ulevels", "nlevels_nod2D", "ulevels_nod2D"):
+            k[name] = np.ascontiguousarray(getattr(m, name), dtype=np.int32)
+        for name in ("edge_cross_dxdy", "edge_dxdy", "elem_cos", "area", "areasvol"):
+            k[name] = np.ascontiguousarray(getattr(m, name), dtype=np.float64)
+        for name in ("helem", "hnode", "hnode_new", "zbar_3d_n", "Z_3d_n", "zbar_n_bot", "uv", "w", "w_e", "w_i"):
+            k[name] = _np(getattr(state, name)).astype(np.float64)
+        k["nboundary_lay"] = np.ascontiguousarray(nboundary_lay, dtype=np.int32)
+        om = OraMesh(nl=nl, myDim_nod2D=N, eDim_nod2D=m.eDim_nod2D, myDim_elem2D=T, eDim_elem2D=m.eDim_elem2D,
+                     myDim_edge2D=E, nod_in_elem_ld=k["nod_in_elem2D"].shape[1])
+        for name in ("edges", "edge_tri", "elem2D_nodes", "nod_in_elem2D", "nod_in_elem2D_num",
+                     "nlevels", "ulevels", "nlevels_nod2D", "ulevels_nod2D"):
+            setattr(om, name, _ip(k[name]))
+        for name in ("edge_cross_dxdy", "edge_dxdy", "elem_cos", "area", "areasvol",
+                     "helem", "hnode", "hnode_new", "zbar_3d_n", "Z_3d_n", "zbar_n_bot"):
+            setattr(om, name, _dp(k[name]))
+        self.cmesh = om
+        # work arrays (oce_adv_tra_fct_init, oce_adv_tra_fct.F90:35-67)
+        for name, shape in (("fct_LO", (Nh, L)), ("adv_flux_hor", (E, L)), ("adv_flux_ver", (N, nl)),
+                            ("fct_ttf_min", (Nh, L)), ("fct_ttf_max", (Nh, L)), ("fct_plus", (Nh, L)),
+                            ("fct_minus", (Nh, L)), ("tvert_max", (Nh, L)), ("tvert_min", (Nh, L))):
+            k[name] = np.zeros(shape)
+        self.ntr = len(tracers)
+        self.values = [_np(t.values).copy() for t in tracers]
+        self.valuesAB = [_np(t.valuesAB).copy() for t in tracers]
+        self.grad = [_np(t.edge_up_dn_grad).copy() for t in tracers]
+        self.dttf_h = [np.zeros((Nh, L)) for _ in tracers]
+        self.dttf_v = [np.zeros((Nh, L)) for _ in tracers]
+        self.hor = np.array([HOR[t.tra_adv_hor] for t in tracers], np.int32)
+        self.ver = np.array([VER[t.tra_adv_ver] for t in tracers], np.int32)
+        self.lim = np.array([LIM[t.tra_adv_lim] for t in tracers], np.int32)
+        self.opth = np.array([t.tra_adv_ph for t in tracers], np.float64)
+        self.optv = np.array([t.tra_adv_pv for t in tracers], np.float64)
+        self.alias_aux = alias_aux
+        k["AUX"] = np.zeros((E, L, 4))
+        wk = OraWork()
+        for name in ("fct_LO", "adv_flux_hor", "adv_flux_ver", "fct_ttf_min", "fct_ttf_max", "fct_plus",
+                     "fct_minus", "tvert_max", "tvert_min", "AUX"):
+            setattr(wk, name, _dp(k[name]))
+        wk.nboundary_lay = _ip(k["nboundary_lay"])
+        self.cwork = wk
+        self.use_wsplit = int(bool(state.use_wsplit))
+        self.halo_owner = np.zeros(max(m.eDim_nod2D, 1), np.int32)
+        self.halo_owner_idx = np.zeros(max(m.eDim_nod2D, 1), np.int32)
+
+    def fill(self, rk: OraRank):
+        k = self.keep
+        rk.mesh = self.cmesh
+        rk.work = self.cwork
+        rk.vel, rk.w, rk.wi, rk.we = _dp(k["uv"]), _dp(k["w"]), _dp(k["w_i"]), _dp(k["w_e"])
+        rk.use_wsplit = self.use_wsplit
+        rk.ntr = self.ntr
+        PA = c_dp * self.ntr
+        self._pa = [PA(*[_dp(a) for a in lst]) for lst in (self.values, self.valuesAB, self.grad, self.dttf_h, self.dttf_v)]
+        rk.values, rk.valuesAB, rk.edge_up_dn_grad, rk.dttf_h, rk.dttf_v = [C.cast(p, C.POINTER(c_dp)) for p in self._pa]
+        rk.hor, rk.ver, rk.lim = _ip(self.hor), _ip(self.ver), _ip(self.lim)
+        rk.opth, rk.optv = _dp(self.opth), _dp(self.optv)
+        rk.halo_owner, rk.halo_owner_idx = _ip(self.halo_owner), _ip(self.halo_owner_idx)
+
+
+def link_halos(ranks: Sequence[OracleRank]):
+    """Pair every rank's recv segment from p with p's send segment to it (same order: ascending
+    global id), i.e. what the MPI datatypes of init_mpi_types encode
+    (gen_modules_partitioning.F90:416-514)."""
+    for r, rk in enumerate(ranks):
+        com = rk.mesh_py.com_nod2D
+        N = rk.mesh_py.N
+        for i, p in enumerate(com.rPE):
+            seg = com.rlist[com.rptr[i] - 1:com.rptr[i + 1] - 1]
+            pc = ranks[int(p)].mesh_py.com_nod2D
+            j = int(np.flatnonzero(pc.sPE == r)[0])
+            sseg = pc.slist[pc.sptr[j] - 1:pc.sptr[j + 1] - 1]
+            assert seg.size == sseg.size
+            rk.halo_owner[seg - N - 1] = int(p)
+            rk.halo_owner_idx[seg - N - 1] = sseg
+
+
+def run(ranks: Sequence[OracleRank], dt: float, nsteps: int = 1, mode: int = 0, fast: bool = False) -> float:
+    """Run ``nsteps`` of the path on all ranks (one thread each). mode 0: do_oce_adv_tra only
+    (del_ttf_adv* accumulate); mode 1: dwarf iteration with value update + exchange."""
+    n = len(ranks)
+    if n > 1:
+        link_halos(ranks)
+    arr = (OraRank * n)()
+    for r, rk in enumerate(ranks):
+        rk.fill(arr[r])
+    return lib(fast).ora_run_ranks(n, arr, float(dt), int(nsteps), int(mode))
