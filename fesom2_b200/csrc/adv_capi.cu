@@ -1,0 +1,731 @@
+// fesom2_b200/csrc/adv_capi.cu -- C ABI (include/fesom_adv_b200.h): context, gather-list
+// construction, launch sequencing with halo/compute overlap, packed-halo NCCL exchange.
+//
+// There is deliberately no CPU path in this file: every entry point needs a CUDA device.
+#include "../../include/fesom_adv_b200.h"
+#include "adv_kernels.cuh"
+
+#include <nccl.h>   // types only: the library is resolved at run time (see NcclApi)
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace adv;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(ADV_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+    } while (0)
+#define NC(call)                                                                              \
+    do {                                                                                      \
+        ncclResult_t r_ = (call);                                                             \
+        if (r_ != ncclSuccess)                                                                \
+            return fail(ADV_ENCCL, std::string(#call) + ": " + g_nccl.GetErrorString(r_));    \
+    } while (0)
+
+static const double R_EARTH = 6367500.0;  // src/oce_modules.F90:29
+
+// NCCL is bound with dlopen at the first communicator call instead of at link time: inside a
+// Python process torch has already loaded its own libnccl.so.2 (same SONAME) and that copy must be
+// the one in use; a Fortran host gets the system library.
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+static NcclApi g_nccl;
+static int nccl_load()
+{
+    if (g_nccl.ok) return ADV_OK;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(ADV_ENCCL, std::string("cannot load libnccl.so.2: ") + dlerror());
+#define SYM(field, name) *(void**)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) return fail(ADV_ENCCL, "missing NCCL symbol " name);
+    SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+    SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.ok = true;
+    return ADV_OK;
+}
+
+namespace {
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count, bool zero = true)
+    {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        if (zero) e = cudaMemset(p, 0, count * sizeof(T));
+        return e;
+    }
+    cudaError_t upload(const std::vector<T>& h)
+    {
+        cudaError_t e = alloc(h.size(), false);
+        if (e != cudaSuccess || h.empty()) return e;
+        return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { release(); }
+};
+
+struct Slot {  // per-tracer work arrays (t_tracer_work, allocated by oce_adv_tra_fct_init) + host staging
+    DevBuf<double> lo, plus, minus, adf_h, adf_v;
+    DevBuf<double> ttf, ttfAB, grad, dh, dv;  // only used with ADV_HOST pointers
+    DevBuf<double> sendbuf;                   // 2 x (send columns x L)
+};
+
+struct Peer { int pe; int off, cnt; };  // segment of slist / halo tail, in columns
+
+}  // namespace
+
+struct adv_ctx {
+    int device = 0;
+    int max_tr = 0;
+    MeshDev m{};
+    int mype = 0, npes = 1;
+    // topology
+    DevBuf<int> ne_ptr, cl_ptr, nboundary_lay, list_S, list_I, list_SH, slist;
+    DevBuf<int4> ne_ent;
+    DevBuf<int2> cl_ent, edge_el;
+    DevBuf<uchar4> node_lev, edge_lev;
+    DevBuf<double4> edge_cross;
+    DevBuf<double2> edge_c;
+    DevBuf<double> area, areasvol, Q;
+    int nS = 0, nI = 0, nSH = 0;
+    std::vector<Peer> rpeers, speers;
+    int send_cols = 0;
+    // state (ADV_HOST staging)
+    DevBuf<double> uv, helem, w, we, wi, hnode, hnode_new, zbar3d, Z3d, zbar_n_bot;
+    bool state_set = false, q_valid = false;
+    DevBuf<double> impl_cp, impl_tp;
+    std::vector<Slot> slots;
+    DevBuf<double> xbuf;  // adv_exchange_nod pack buffer
+    cudaStream_t s_comp = nullptr, s_comm = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_ph[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool profiling = false, ph_valid = false;
+    ncclComm_t comm = nullptr;
+    int64_t launches = 0;
+    bool timed = false;
+};
+
+const char* adv_last_error(void) { return g_err.c_str(); }
+
+// ------------------------------------------------------------------------------------------------
+static int parse_scheme(const char* s, const char* const* names, const int* codes, int n)
+{
+    if (!s) return -1;
+    char buf[16];
+    int k = 0;
+    while (k < 15 && s[k] && s[k] != ' ') { buf[k] = s[k]; ++k; }   // Fortran strings are blank padded
+    buf[k] = 0;
+    for (int i = 0; i < n; ++i)
+        if (strcmp(buf, names[i]) == 0) return codes[i];
+    return -1;
+}
+
+int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int max_tracers)
+{
+    if (!out || !d || max_tracers < 1) return fail(ADV_EINVAL, "adv_ctx_create: null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(ADV_ECUDA, "no CUDA device: this library has no CPU fallback");
+    CU(cudaSetDevice(device));
+    const int nl = d->nl, L = nl - 1;
+    const int N = d->myDim_nod2D, Nh = N + d->eDim_nod2D, T = d->myDim_elem2D, E = d->myDim_edge2D;
+    if (L < 1 || L > kBlock || nl > 255) return fail(ADV_EINVAL, "nl out of the supported range (2..255)");
+    if (N < 1 || T < 1 || E < 1) return fail(ADV_EINVAL, "empty mesh");
+
+    // ---- host-side gather lists ----------------------------------------------------------------
+    std::vector<int2> edge_el(E);
+    std::vector<uchar4> edge_lev(E);
+    std::vector<double4> edge_cross(E);
+    std::vector<double2> edge_c(E);
+    std::vector<int> deg(Nh + 1, 0);
+    for (int e = 0; e < E; ++e) {
+        const int n1 = d->edges[2 * e] - 1, n2 = d->edges[2 * e + 1] - 1;
+        const int el1 = d->edge_tri[2 * e] - 1, el2 = d->edge_tri[2 * e + 1] > 0 ? d->edge_tri[2 * e + 1] - 1 : -1;
+        if (n1 < 0 || n1 >= Nh || n2 < 0 || n2 >= Nh || el1 < 0 || el1 >= T || el2 >= T)
+            return fail(ADV_EINVAL, "edge " + std::to_string(e + 1) + ": index out of range");
+        const int nu1 = d->ulevels[el1], nl1 = d->nlevels[el1] - 1;
+        int nu2 = 0, nl2 = 0;
+        double a = R_EARTH * d->elem_cos[el1];                       // oce_adv_tra_hor.F90:325,338
+        if (el2 >= 0) {
+            nu2 = d->ulevels[el2]; nl2 = d->nlevels[el2] - 1;
+            a = 0.5 * (a + R_EARTH * d->elem_cos[el2]);
+            if (std::max(nu1, nu2) > std::min(nl1, nl2) + 1)
+                return fail(ADV_EINVAL, "edge " + std::to_string(e + 1) + ": adjacent elements have disjoint level ranges");
+        }
+        if (nu1 < 1 || nl1 > L || nl2 > L || nu1 > nl1) return fail(ADV_EINVAL, "element levels out of range");
+        edge_el[e] = make_int2(el1, el2);
+        edge_lev[e] = make_uchar4((unsigned char)nu1, (unsigned char)nl1, (unsigned char)nu2, (unsigned char)nl2);
+        edge_cross[e] = make_double4(d->edge_cross_dxdy[4 * e], d->edge_cross_dxdy[4 * e + 1],
+                                     d->edge_cross_dxdy[4 * e + 2], d->edge_cross_dxdy[4 * e + 3]);
+        edge_c[e] = make_double2(d->edge_dxdy[2 * e] * a, d->edge_dxdy[2 * e + 1] * R_EARTH);
+        ++deg[n1 + 1]; ++deg[n2 + 1];
+    }
+    std::vector<int> ne_ptr(Nh + 1, 0);
+    for (int n = 0; n < Nh; ++n) ne_ptr[n + 1] = ne_ptr[n] + deg[n + 1];
+    std::vector<int4> ne_ent(ne_ptr[Nh]);
+    {
+        std::vector<int> fill(ne_ptr.begin(), ne_ptr.end() - 1);
+        for (int e = 0; e < E; ++e) {   // ascending e => every node's list is ascending (serial scatter order)
+            const int n1 = d->edges[2 * e] - 1, n2 = d->edges[2 * e + 1] - 1;
+            const uchar4 lv = edge_lev[e];
+            // scatter range of oce_adv_tra_driver.F90:154-156: [min(nu1, nu2>0), max(nl1, nl2)]
+            const int lo = lv.z > 0 ? std::min<int>(lv.x, lv.z) : lv.x;
+            const int hi = std::max<int>(lv.y, lv.w);
+            const bool w1 = n1 < N;   // designated writer of adf_h(:,e): edges(1,e) if owned, else edges(2,e)
+            ne_ent[fill[n1]++] = make_int4(e, n2, lo | (hi << 8) | (0 << 16) | ((w1 ? 1 : 0) << 17), 0);
+            ne_ent[fill[n2]++] = make_int4(e, n1, lo | (hi << 8) | (1 << 16) | ((w1 ? 0 : 1) << 17), 0);
+        }
+    }
+    // FCT clusters (oce_adv_tra_fct.F90:148-215 collapsed): for owned node n the distinct nodes of
+    // its elements, each with the union of the level ranges of the elements that contain it.
+    std::vector<uchar4> node_lev(Nh);
+    std::vector<int> cl_ptr(N + 1, 0);
+    std::vector<int2> cl_ent;
+    cl_ent.reserve((size_t)N * 8);
+    const int ld = d->nod_in_elem2D_ld;
+    struct Iv { int node, lo, hi; };
+    std::vector<Iv> iv;
+    for (int n = 0; n < Nh; ++n) {
+        int pad_lo = 0, pad_hi = 255;
+        if (n < N) {
+            iv.clear();
+            const int num = d->nod_in_elem2D_num[n];
+            if (num < 1 || num > ld) return fail(ADV_EINVAL, "nod_in_elem2D_num out of range");
+            pad_lo = 0; pad_hi = 255;
+            for (int k = 0; k < num; ++k) {
+                const int el = d->nod_in_elem2D[(size_t)n * ld + k] - 1;
+                if (el < 0 || el >= T) return fail(ADV_EINVAL, "nod_in_elem2D out of range");
+                const int lo = d->ulevels[el], hi = d->nlevels[el] - 1;
+                pad_lo = std::max(pad_lo, lo); pad_hi = std::min(pad_hi, hi);
+                for (int j = 0; j < 3; ++j) iv.push_back({d->elem2D_nodes[3 * el + j] - 1, lo, hi});
+            }
+            std::sort(iv.begin(), iv.end(), [](const Iv& a, const Iv& b) { return a.node != b.node ? a.node < b.node : a.lo < b.lo; });
+            for (size_t i = 0; i < iv.size();) {
+                Iv cur = iv[i];
+                size_t j = i + 1;
+                for (; j < iv.size() && iv[j].node == cur.node && iv[j].lo <= cur.hi + 1; ++j) cur.hi = std::max(cur.hi, iv[j].hi);
+                cl_ent.push_back(make_int2(cur.node, cur.lo | (cur.hi << 8)));
+                i = j;
+            }
+            cl_ptr[n + 1] = (int)cl_ent.size();
+        }
+        node_lev[n] = make_uchar4((unsigned char)d->ulevels_nod2D[n], (unsigned char)d->nlevels_nod2D[n],
+                                  (unsigned char)pad_lo, (unsigned char)pad_hi);
+        if (d->nlevels_nod2D[n] > nl || d->ulevels_nod2D[n] < 1) return fail(ADV_EINVAL, "node levels out of range");
+    }
+
+    adv_ctx* c = new adv_ctx();
+    c->device = device; c->max_tr = max_tracers; c->mype = d->mype; c->npes = std::max(1, d->npes);
+#define CUF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { delete c; return fail(ADV_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+    CUF(c->ne_ptr.upload(ne_ptr)); CUF(c->ne_ent.upload(ne_ent));
+    CUF(c->cl_ptr.upload(cl_ptr)); CUF(c->cl_ent.upload(cl_ent));
+    CUF(c->node_lev.upload(node_lev)); CUF(c->edge_el.upload(edge_el)); CUF(c->edge_lev.upload(edge_lev));
+    CUF(c->edge_cross.upload(edge_cross)); CUF(c->edge_c.upload(edge_c));
+    {
+        std::vector<int> nb(Nh, L);
+        if (d->nboundary_lay) nb.assign(d->nboundary_lay, d->nboundary_lay + Nh);
+        CUF(c->nboundary_lay.upload(nb));
+        std::vector<double> tmp(d->area, d->area + (size_t)nl * Nh);
+        CUF(c->area.upload(tmp));
+        tmp.assign(d->areasvol, d->areasvol + (size_t)nl * Nh);
+        CUF(c->areasvol.upload(tmp));
+    }
+    CUF(c->Q.alloc((size_t)L * E));
+
+    // ---- halo bookkeeping (com_nod2D) ------------------------------------------------------------
+    if (c->npes > 1) {
+        std::vector<char> isS(N, 0);
+        std::vector<int> sl;
+        for (int i = 0; i < d->sPEnum; ++i) {
+            Peer p{d->sPE[i], d->sptr[i] - 1, d->sptr[i + 1] - d->sptr[i]};
+            c->speers.push_back(p);
+            for (int k = 0; k < p.cnt; ++k) {
+                const int n = d->slist[p.off + k] - 1;
+                if (n < 0 || n >= N) { delete c; return fail(ADV_EINVAL, "slist entry is not an owned node"); }
+                isS[n] = 1; sl.push_back(n);
+            }
+        }
+        c->send_cols = (int)sl.size();
+        for (int i = 0; i < d->rPEnum; ++i) {
+            Peer p{d->rPE[i], d->rptr[i] - 1, d->rptr[i + 1] - d->rptr[i]};
+            // the halo tail must be contiguous per source rank: rlist(k) = myDim_nod2D + k (oce_local.F90:41)
+            for (int k = 0; k < p.cnt; ++k)
+                if (d->rlist[p.off + k] != N + p.off + k + 1) { delete c; return fail(ADV_EINVAL, "rlist is not the identity on the halo tail"); }
+            c->rpeers.push_back(p);
+        }
+        // a node also belongs to the boundary set when one of its edge neighbours is a halo node
+        for (int e = 0; e < E; ++e) {
+            const int n1 = d->edges[2 * e] - 1, n2 = d->edges[2 * e + 1] - 1;
+            if (n1 < N && n2 >= N) isS[n1] = 1;
+            if (n2 < N && n1 >= N) isS[n2] = 1;
+        }
+        std::vector<int> S, I, SH;
+        for (int n = 0; n < N; ++n) (isS[n] ? S : I).push_back(n);
+        SH = S;
+        for (int n = N; n < Nh; ++n) SH.push_back(n);
+        c->nS = (int)S.size(); c->nI = (int)I.size(); c->nSH = (int)SH.size();
+        CUF(c->list_S.upload(S)); CUF(c->list_I.upload(I)); CUF(c->list_SH.upload(SH)); CUF(c->slist.upload(sl));
+    }
+    c->slots.resize(max_tracers);
+    for (auto& s : c->slots) {
+        CUF(s.lo.alloc((size_t)L * Nh)); CUF(s.plus.alloc((size_t)L * Nh)); CUF(s.minus.alloc((size_t)L * Nh));
+        CUF(s.adf_h.alloc((size_t)L * E)); CUF(s.adf_v.alloc((size_t)nl * N));
+        if (c->npes > 1) CUF(s.sendbuf.alloc((size_t)2 * c->send_cols * L));
+    }
+    CUF(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+    CUF(cudaStreamCreateWithFlags(&c->s_comm, cudaStreamNonBlocking));
+    for (cudaEvent_t* ev : {&c->ev_a, &c->ev_b, &c->ev_c, &c->ev_d}) CUF(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+    CUF(cudaEventCreate(&c->ev_t0)); CUF(cudaEventCreate(&c->ev_t1));
+    for (auto& ev : c->ev_ph) CUF(cudaEventCreate(&ev));
+#undef CUF
+    MeshDev& m = c->m;
+    m.L = L; m.nl = nl; m.N = N; m.Nh = Nh; m.T = T; m.E = E;
+    m.ne_ptr = c->ne_ptr.p; m.ne_ent = c->ne_ent.p; m.cl_ptr = c->cl_ptr.p; m.cl_ent = c->cl_ent.p;
+    m.node_lev = c->node_lev.p; m.edge_el = c->edge_el.p; m.edge_lev = c->edge_lev.p;
+    m.edge_cross = c->edge_cross.p; m.edge_c = c->edge_c.p; m.nboundary_lay = c->nboundary_lay.p;
+    m.area = c->area.p; m.areasvol = c->areasvol.p; m.Q = c->Q.p;
+    *out = c;
+    return ADV_OK;
+}
+
+int adv_ctx_destroy(adv_ctx_t* c)
+{
+    if (!c) return ADV_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
+    for (cudaEvent_t ev : {c->ev_a, c->ev_b, c->ev_c, c->ev_d, c->ev_t0, c->ev_t1}) if (ev) cudaEventDestroy(ev);
+    for (auto ev : c->ev_ph) if (ev) cudaEventDestroy(ev);
+    if (c->s_comp) cudaStreamDestroy(c->s_comp);
+    if (c->s_comm) cudaStreamDestroy(c->s_comm);
+    delete c;
+    return ADV_OK;
+}
+
+int adv_comm_unique_id(char id[128])
+{
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    if (int rc = nccl_load()) return rc;
+    ncclUniqueId u;
+    NC(g_nccl.GetUniqueId(&u));
+    memcpy(id, &u, 128);
+    return ADV_OK;
+}
+
+int adv_ctx_comm_init(adv_ctx_t* c, const char id[128])
+{
+    if (!c) return fail(ADV_EINVAL, "null ctx");
+    if (c->npes == 1) return ADV_OK;
+    CU(cudaSetDevice(c->device));
+    if (int rc = nccl_load()) return rc;
+    ncclUniqueId u;
+    memcpy(&u, id, 128);
+    NC(g_nccl.CommInitRank(&c->comm, c->npes, u, c->mype));
+    return ADV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int adv_ctx_set_state(adv_ctx_t* c, const adv_state_desc_t* st, int where)
+{
+    if (!c || !st) return fail(ADV_EINVAL, "null argument");
+    CU(cudaSetDevice(c->device));
+    MeshDev& m = c->m;
+    const size_t L = m.L, nl = m.nl, Nh = m.Nh, T = m.T;
+    if (!st->uv || !st->w || !st->w_e || !st->helem || !st->hnode || !st->hnode_new || !st->zbar_3d_n || !st->Z_3d_n)
+        return fail(ADV_EINVAL, "adv_ctx_set_state: null field");
+    if (st->use_wsplit && !st->w_i) return fail(ADV_EINVAL, "use_wsplit needs w_i");
+    if (where == ADV_DEVICE) {
+        m.uv = st->uv; m.helem = st->helem; m.w = st->w; m.we = st->w_e; m.wi = st->w_i;
+        m.hnode = st->hnode; m.hnode_new = st->hnode_new; m.zbar3d = st->zbar_3d_n; m.Z3d = st->Z_3d_n;
+    } else {
+        struct { DevBuf<double>* b; const double* src; size_t n; const double** dst; } cp[] = {
+            {&c->uv, st->uv, 2 * L * T, &m.uv}, {&c->helem, st->helem, L * T, &m.helem},
+            {&c->w, st->w, nl * Nh, &m.w}, {&c->we, st->w_e, nl * Nh, &m.we},
+            {&c->wi, st->w_i, st->w_i ? nl * Nh : 0, &m.wi},
+            {&c->hnode, st->hnode, L * Nh, &m.hnode}, {&c->hnode_new, st->hnode_new, L * Nh, &m.hnode_new},
+            {&c->zbar3d, st->zbar_3d_n, nl * Nh, &m.zbar3d}, {&c->Z3d, st->Z_3d_n, L * Nh, &m.Z3d}};
+        for (auto& x : cp) {
+            if (x.n == 0) { *x.dst = nullptr; continue; }
+            if (x.b->n != x.n) CU(x.b->alloc(x.n, false));
+            CU(cudaMemcpyAsync(x.b->p, x.src, x.n * sizeof(double), cudaMemcpyHostToDevice, c->s_comp));
+            *x.dst = x.b->p;
+        }
+    }
+    m.use_wsplit = st->use_wsplit ? 1 : 0;
+    if (m.use_wsplit && c->impl_cp.n == 0) { CU(c->impl_cp.alloc(L * m.N)); CU(c->impl_tp.alloc(L * m.N)); }
+    c->state_set = true;
+    c->q_valid = false;
+    return ADV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Group { int fct, hor, ver; std::vector<int> idx; };
+
+inline int cols_per_block(int L) { return kBlock / L; }
+inline int nblocks(int count, int cpb) { return (count + cpb - 1) / cpb; }
+
+template <int TB>
+TrBatch<TB> make_batch(adv_ctx* c, const std::vector<const double*>& ttf, const std::vector<const double*>& ttfAB,
+                       const std::vector<const double*>& grad, const std::vector<double*>& dh,
+                       const std::vector<double*>& dv, const adv_tracer_desc_t* tr, const int* idx)
+{
+    TrBatch<TB> b;
+    for (int t = 0; t < TB; ++t) {
+        const int i = idx[t];
+        Slot& s = c->slots[i];
+        b.ttf[t] = ttf[i]; b.ttfAB[t] = ttfAB[i]; b.grad[t] = grad[i];
+        b.lo[t] = s.lo.p; b.adf_h[t] = s.adf_h.p; b.adf_v[t] = s.adf_v.p; b.plus[t] = s.plus.p; b.minus[t] = s.minus.p;
+        b.dttf_h[t] = dh[i]; b.dttf_v[t] = dv[i];
+        b.ph[t] = tr[i].tra_adv_ph; b.pv[t] = tr[i].tra_adv_pv;
+    }
+    return b;
+}
+
+enum Phase { PH_K1, PH_K2, PH_K3, PH_NOFCT };
+
+template <int HOR, int VER, int TB>
+void launch_hv(adv_ctx* c, Phase ph, const TrBatch<TB>& b, const NodeRange& r, double dt)
+{
+    if (r.count <= 0) return;
+    const int grid = nblocks(r.count, r.cpb);
+    const size_t sm2 = (size_t)2 * TB * kBlock * sizeof(double), sm1 = (size_t)TB * kBlock * sizeof(double);
+    if (ph == PH_K1) k_fct_lo_adf<HOR, VER, TB><<<grid, kBlock, sm2, c->s_comp>>>(c->m, b, r, dt);
+    else k_nofct<HOR, VER, TB><<<grid, kBlock, sm1, c->s_comp>>>(c->m, b, r, dt);
+    ++c->launches;
+}
+
+template <int TB>
+void launch_phase(adv_ctx* c, Phase ph, int hor, int ver, const TrBatch<TB>& b, const NodeRange& r, double dt)
+{
+    if (r.count <= 0) return;
+    if (ph == PH_K2 || ph == PH_K3) {
+        const int grid = nblocks(r.count, r.cpb);
+        if (ph == PH_K2) k_fct_bounds<TB><<<grid, kBlock, (size_t)2 * TB * kBlock * sizeof(double), c->s_comp>>>(c->m, b, r, dt);
+        else k_fct_update<TB><<<grid, kBlock, (size_t)TB * kBlock * sizeof(double), c->s_comp>>>(c->m, b, r, dt);
+        ++c->launches;
+        return;
+    }
+#define HV(H, V) if (hor == H && ver == V) { launch_hv<H, V, TB>(c, ph, b, r, dt); return; }
+    HV(HOR_UPW1, VER_UPW1) HV(HOR_UPW1, VER_QR4C) HV(HOR_UPW1, VER_PPM) HV(HOR_UPW1, VER_CDIFF)
+    HV(HOR_MUSCL, VER_UPW1) HV(HOR_MUSCL, VER_QR4C) HV(HOR_MUSCL, VER_PPM) HV(HOR_MUSCL, VER_CDIFF)
+    HV(HOR_MFCT, VER_UPW1) HV(HOR_MFCT, VER_QR4C) HV(HOR_MFCT, VER_PPM) HV(HOR_MFCT, VER_CDIFF)
+#undef HV
+}
+
+// one exchange_nod over NCCL for `nf` fields of nlev levels each: pack the send columns per field,
+// then one grouped send/recv per (peer, field); receives land directly in the halo tail.
+int halo_exchange(adv_ctx* c, cudaStream_t s, int nf, double* const* fields, double* const* sendbufs, int nlev)
+{
+    const int cols = c->send_cols;
+    for (int f = 0; f < nf; ++f) {
+        const long long tot = (long long)cols * nlev;
+        if (tot > 0) {
+            k_pack_halo<<<(unsigned)((tot + kBlock - 1) / kBlock), kBlock, 0, s>>>(fields[f], c->slist.p, cols, nlev, sendbufs[f]);
+            ++c->launches;
+        }
+    }
+    NC(g_nccl.GroupStart());
+    for (int f = 0; f < nf; ++f) {
+        for (const Peer& p : c->rpeers)
+            NC(g_nccl.Recv(fields[f] + ((size_t)c->m.N + p.off) * nlev, (size_t)p.cnt * nlev, ncclDouble, p.pe, c->comm, s));
+        for (const Peer& p : c->speers)
+            NC(g_nccl.Send(sendbufs[f] + (size_t)p.off * nlev, (size_t)p.cnt * nlev, ncclDouble, p.pe, c->comm, s));
+    }
+    NC(g_nccl.GroupEnd());
+    return ADV_OK;
+}
+
+}  // namespace
+
+static int run_batch(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr,
+                     const std::vector<const double*>& ttf, const std::vector<const double*>& ttfAB,
+                     const std::vector<const double*>& grad, const std::vector<double*>& dh,
+                     const std::vector<double*>& dv)
+{
+    static const char* hn[] = {"MUSCL", "MFCT", "UPW1"};
+    static const int hc[] = {HOR_MUSCL, HOR_MFCT, HOR_UPW1};
+    static const char* vn[] = {"QR4C", "CDIFF", "PPM", "UPW1"};
+    static const int vc[] = {VER_QR4C, VER_CDIFF, VER_PPM, VER_UPW1};
+    MeshDev& m = c->m;
+    std::vector<Group> groups;
+    for (int i = 0; i < ntr; ++i) {
+        const int hor = parse_scheme(tr[i].tra_adv_hor, hn, hc, 3);
+        const int ver = parse_scheme(tr[i].tra_adv_ver, vn, vc, 4);
+        if (hor < 0) return fail(ADV_ESCHEME, std::string("Unknown horizontal advection type ") + (tr[i].tra_adv_hor ? tr[i].tra_adv_hor : "(null)"));
+        if (ver < 0) return fail(ADV_ESCHEME, std::string("Unknown vertical advection type ") + (tr[i].tra_adv_ver ? tr[i].tra_adv_ver : "(null)"));
+        static const char* ln[] = {"FCT"};
+        static const int lc[] = {1};
+        const int fct = parse_scheme(tr[i].tra_adv_lim, ln, lc, 1) == 1 ? 1 : 0;   // driver :111: anything else = no limiter
+        if (hor != HOR_UPW1 && !grad[i]) return fail(ADV_EINVAL, "edge_up_dn_grad is NULL for a gradient-based scheme");
+        bool found = false;
+        for (auto& g : groups)
+            if (g.fct == fct && g.hor == hor && g.ver == ver) { g.idx.push_back(i); found = true; break; }
+        if (!found) groups.push_back(Group{fct, hor, ver, {i}});
+    }
+    struct Chunk { int fct, hor, ver, tb; int idx[2]; };
+    std::vector<Chunk> chunks;
+    for (auto& g : groups) {
+        size_t i = 0;
+        for (; i + 2 <= g.idx.size(); i += 2) chunks.push_back(Chunk{g.fct, g.hor, g.ver, 2, {g.idx[i], g.idx[i + 1]}});
+        if (i < g.idx.size()) chunks.push_back(Chunk{g.fct, g.hor, g.ver, 1, {g.idx[i], 0}});
+    }
+    cudaStream_t sc = c->s_comp, sx = c->s_comm;
+    const int cpb = cols_per_block(m.L);
+    const bool multi = c->npes > 1;
+    if (multi && !c->comm) return fail(ADV_ESTATE, "npes > 1 but adv_ctx_comm_init was not called");
+    const bool prof = c->profiling && !multi;
+    auto mark = [&](int i) { if (prof) cudaEventRecord(c->ev_ph[i], sc); };
+
+    mark(0);
+    if (!c->q_valid) {
+        const long long tot = (long long)m.E * m.L;
+        k_edge_volflux<<<(unsigned)((tot + kBlock - 1) / kBlock), kBlock, 0, sc>>>(m);
+        ++c->launches;
+        c->q_valid = true;
+    }
+    mark(1);
+    const NodeRange rAll{nullptr, 0, m.N, cpb}, rS{c->list_S.p, 0, c->nS, cpb}, rI{c->list_I.p, 0, c->nI, cpb},
+        rSH{c->list_SH.p, 0, c->nSH, cpb}, rAllH{nullptr, 0, m.Nh, cpb};
+    auto run = [&](Phase ph, const Chunk& ch, const NodeRange& r) {
+        if (ch.tb == 2) launch_phase<2>(c, ph, ch.hor, ch.ver, make_batch<2>(c, ttf, ttfAB, grad, dh, dv, tr, ch.idx), r, dt);
+        else launch_phase<1>(c, ph, ch.hor, ch.ver, make_batch<1>(c, ttf, ttfAB, grad, dh, dv, tr, ch.idx), r, dt);
+    };
+    std::vector<double*> f1, s1, f2, s2;   // exchange field / send buffer lists over all FCT tracers
+    bool any_fct = false;
+    for (auto& ch : chunks)
+        if (ch.fct) {
+            any_fct = true;
+            for (int t = 0; t < ch.tb; ++t) {
+                Slot& s = c->slots[ch.idx[t]];
+                f1.push_back(s.lo.p); s1.push_back(s.sendbuf.p);
+                f2.push_back(s.plus.p); s2.push_back(s.sendbuf.p);
+                f2.push_back(s.minus.p); s2.push_back(s.sendbuf.p + (size_t)c->send_cols * m.L);
+            }
+        }
+    // non-FCT tracers: one sweep, no exchange inside the path
+    for (auto& ch : chunks)
+        if (!ch.fct) run(PH_NOFCT, ch, multi ? rAllH : rAll);
+    if (any_fct) {
+        const bool overlap = multi && !m.use_wsplit;
+        // ---- phase 1: LO + antidiffusive fluxes (boundary set first, then start exchange 1)
+        if (overlap) {
+            for (auto& ch : chunks) if (ch.fct) run(PH_K1, ch, rS);
+            CU(cudaEventRecord(c->ev_a, sc));
+            CU(cudaStreamWaitEvent(sx, c->ev_a, 0));
+            if (int rc = halo_exchange(c, sx, (int)f1.size(), f1.data(), s1.data(), m.L)) return rc;   // driver :335
+            CU(cudaEventRecord(c->ev_b, sx));
+            for (auto& ch : chunks) if (ch.fct) run(PH_K1, ch, rI);
+            CU(cudaStreamWaitEvent(sc, c->ev_b, 0));
+        } else {
+            for (auto& ch : chunks) if (ch.fct) run(PH_K1, ch, rAll);
+            if (m.use_wsplit) {
+                for (auto& ch : chunks)
+                    if (ch.fct)
+                        for (int t = 0; t < ch.tb; ++t) {
+                            k_vert_impl<<<(m.N + 127) / 128, 128, 0, sc>>>(m, c->slots[ch.idx[t]].lo.p, c->impl_cp.p, c->impl_tp.p, dt);
+                            ++c->launches;
+                        }
+            }
+            if (multi) if (int rc = halo_exchange(c, sc, (int)f1.size(), f1.data(), s1.data(), m.L)) return rc;
+        }
+        mark(2);
+        // ---- phase 2: bounds + R+/R- (boundary set first, then start exchange 2)
+        if (multi) {
+            for (auto& ch : chunks) if (ch.fct) run(PH_K2, ch, rS);
+            CU(cudaEventRecord(c->ev_c, sc));
+            CU(cudaStreamWaitEvent(sx, c->ev_c, 0));
+            if (int rc = halo_exchange(c, sx, (int)f2.size(), f2.data(), s2.data(), m.L)) return rc;   // fct :413
+            CU(cudaEventRecord(c->ev_d, sx));
+            for (auto& ch : chunks) if (ch.fct) run(PH_K2, ch, rI);
+            // ---- phase 3: interior update overlaps exchange 2
+            for (auto& ch : chunks) if (ch.fct) run(PH_K3, ch, rI);
+            CU(cudaStreamWaitEvent(sc, c->ev_d, 0));
+            for (auto& ch : chunks) if (ch.fct) run(PH_K3, ch, rSH);
+        } else {
+            for (auto& ch : chunks) if (ch.fct) run(PH_K2, ch, rAll);
+            mark(3);
+            for (auto& ch : chunks) if (ch.fct) run(PH_K3, ch, rAll);
+        }
+    } else { mark(2); mark(3); }
+    mark(4);
+    c->ph_valid = prof;
+    CU(cudaGetLastError());
+    return ADV_OK;
+}
+
+static int do_adv(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr, int where, bool blocking)
+{
+    if (!c || !tr || ntr < 1) return fail(ADV_EINVAL, "null argument");
+    if (ntr > c->max_tr) return fail(ADV_EINVAL, "ntr exceeds max_tracers of the context");
+    if (!c->state_set) return fail(ADV_ESTATE, "adv_ctx_set_state has not been called");
+    CU(cudaSetDevice(c->device));
+    MeshDev& m = c->m;
+    const size_t nLN = (size_t)m.L * m.Nh, nLE = (size_t)m.L * m.E;
+    std::vector<const double*> ttf(ntr), ttfAB(ntr), grad(ntr);
+    std::vector<double*> dh(ntr), dv(ntr);
+    for (int i = 0; i < ntr; ++i) {
+        if (!tr[i].values || !tr[i].valuesAB || !tr[i].del_ttf_advhoriz || !tr[i].del_ttf_advvert)
+            return fail(ADV_EINVAL, "tracer " + std::to_string(i + 1) + ": null field");
+        if (where == ADV_DEVICE) {
+            ttf[i] = tr[i].values; ttfAB[i] = tr[i].valuesAB; grad[i] = tr[i].edge_up_dn_grad;
+            dh[i] = tr[i].del_ttf_advhoriz; dv[i] = tr[i].del_ttf_advvert;
+        } else {
+            Slot& s = c->slots[i];
+            if (s.ttf.n != nLN) { CU(s.ttf.alloc(nLN, false)); CU(s.ttfAB.alloc(nLN, false)); CU(s.dh.alloc(nLN, false)); CU(s.dv.alloc(nLN, false)); }
+            CU(cudaMemcpyAsync(s.ttf.p, tr[i].values, nLN * 8, cudaMemcpyHostToDevice, c->s_comp));
+            CU(cudaMemcpyAsync(s.ttfAB.p, tr[i].valuesAB, nLN * 8, cudaMemcpyHostToDevice, c->s_comp));
+            CU(cudaMemcpyAsync(s.dh.p, tr[i].del_ttf_advhoriz, nLN * 8, cudaMemcpyHostToDevice, c->s_comp));
+            CU(cudaMemcpyAsync(s.dv.p, tr[i].del_ttf_advvert, nLN * 8, cudaMemcpyHostToDevice, c->s_comp));
+            grad[i] = nullptr;
+            if (tr[i].edge_up_dn_grad) {
+                if (s.grad.n != 4 * nLE) CU(s.grad.alloc(4 * nLE, false));
+                CU(cudaMemcpyAsync(s.grad.p, tr[i].edge_up_dn_grad, 4 * nLE * 8, cudaMemcpyHostToDevice, c->s_comp));
+                grad[i] = s.grad.p;
+            }
+            ttf[i] = s.ttf.p; ttfAB[i] = s.ttfAB.p; dh[i] = s.dh.p; dv[i] = s.dv.p;
+        }
+    }
+    CU(cudaEventRecord(c->ev_t0, c->s_comp));
+    if (int rc = run_batch(c, dt, ntr, tr, ttf, ttfAB, grad, dh, dv)) return rc;
+    CU(cudaEventRecord(c->ev_t1, c->s_comp));
+    c->timed = true;
+    if (where == ADV_HOST) {
+        for (int i = 0; i < ntr; ++i) {
+            CU(cudaMemcpyAsync(tr[i].del_ttf_advhoriz, dh[i], nLN * 8, cudaMemcpyDeviceToHost, c->s_comp));
+            CU(cudaMemcpyAsync(tr[i].del_ttf_advvert, dv[i], nLN * 8, cudaMemcpyDeviceToHost, c->s_comp));
+        }
+    }
+    if (blocking) CU(cudaStreamSynchronize(c->s_comp));
+    return ADV_OK;
+}
+
+int adv_do_oce_adv_tra(adv_ctx_t* c, double dt, int ntr, const adv_tracer_desc_t* tr, int where)
+{
+    return do_adv(c, dt, ntr, tr, where, true);
+}
+
+int adv_do_oce_adv_tra_async(adv_ctx_t* c, double dt, int ntr, const adv_tracer_desc_t* tr)
+{
+    return do_adv(c, dt, ntr, tr, ADV_DEVICE, false);
+}
+
+int adv_ctx_synchronize(adv_ctx_t* c)
+{
+    if (!c) return fail(ADV_EINVAL, "null ctx");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->s_comp));
+    CU(cudaStreamSynchronize(c->s_comm));
+    return ADV_OK;
+}
+
+int adv_exchange_nod(adv_ctx_t* c, int nfields, double* const* fields, int nlev)
+{
+    if (!c || !fields || nfields < 1 || nlev < 1) return fail(ADV_EINVAL, "bad argument");
+    if (c->npes == 1) return ADV_OK;
+    if (!c->comm) return fail(ADV_ESTATE, "adv_ctx_comm_init was not called");
+    CU(cudaSetDevice(c->device));
+    const size_t need = (size_t)nfields * c->send_cols * nlev;
+    if (c->xbuf.n < need) { CU(cudaStreamSynchronize(c->s_comp)); CU(c->xbuf.alloc(need, false)); }
+    std::vector<double*> sb(nfields);
+    for (int f = 0; f < nfields; ++f) sb[f] = c->xbuf.p + (size_t)f * c->send_cols * nlev;
+    return halo_exchange(c, c->s_comp, nfields, fields, sb.data(), nlev);
+}
+
+int adv_update_values(adv_ctx_t* c, int ntr, double* const* values, const double* const* dh, const double* const* dv)
+{
+    if (!c || !values || !dh || !dv || ntr < 1) return fail(ADV_EINVAL, "bad argument");
+    if (!c->state_set) return fail(ADV_ESTATE, "adv_ctx_set_state has not been called");
+    CU(cudaSetDevice(c->device));
+    const long long tot = (long long)c->m.N * c->m.L;
+    for (int i = 0; i < ntr; ++i) {
+        k_update_values<<<(unsigned)((tot + kBlock - 1) / kBlock), kBlock, 0, c->s_comp>>>(c->m, values[i], dh[i], dv[i]);
+        ++c->launches;
+    }
+    CU(cudaGetLastError());
+    if (c->npes > 1) return adv_exchange_nod(c, ntr, values, c->m.L);
+    return ADV_OK;
+}
+
+int adv_ctx_get_work(adv_ctx_t* c, const char* name, int slot, double* out)
+{
+    if (!c || !name || !out) return fail(ADV_EINVAL, "null argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->s_comp));
+    CU(cudaStreamSynchronize(c->s_comm));
+    const MeshDev& m = c->m;
+    const double* src = nullptr;
+    size_t n = 0;
+    const std::string s(name);
+    if (s == "edge_volflux") { src = c->Q.p; n = (size_t)m.L * m.E; }
+    else {
+        if (slot < 0 || slot >= c->max_tr) return fail(ADV_EINVAL, "slot out of range");
+        Slot& sl = c->slots[slot];
+        if (s == "fct_LO") { src = sl.lo.p; n = (size_t)m.L * m.Nh; }
+        else if (s == "fct_plus") { src = sl.plus.p; n = (size_t)m.L * m.Nh; }
+        else if (s == "fct_minus") { src = sl.minus.p; n = (size_t)m.L * m.Nh; }
+        else if (s == "adv_flux_hor") { src = sl.adf_h.p; n = (size_t)m.L * m.E; }
+        else if (s == "adv_flux_ver") { src = sl.adf_v.p; n = (size_t)m.nl * m.N; }
+        else return fail(ADV_EINVAL, "unknown work array " + s);
+    }
+    CU(cudaMemcpy(out, src, n * sizeof(double), cudaMemcpyDeviceToHost));
+    return ADV_OK;
+}
+
+int64_t adv_ctx_launch_count(const adv_ctx_t* c) { return c ? c->launches : 0; }
+void* adv_ctx_stream(adv_ctx_t* c) { return c ? (void*)c->s_comp : nullptr; }
+
+int adv_ctx_last_elapsed_ms(adv_ctx_t* c, float* ms)
+{
+    if (!c || !ms || !c->timed) return fail(ADV_ESTATE, "no timed call yet");
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventSynchronize(c->ev_t1));
+    CU(cudaEventElapsedTime(ms, c->ev_t0, c->ev_t1));
+    return ADV_OK;
+}
+
+int adv_ctx_set_profiling(adv_ctx_t* c, int on)
+{
+    if (!c) return fail(ADV_EINVAL, "null ctx");
+    c->profiling = on != 0;
+    c->ph_valid = false;
+    return ADV_OK;
+}
+
+int adv_ctx_phase_ms(adv_ctx_t* c, float ms[8])
+{
+    if (!c || !ms || !c->ph_valid) return fail(ADV_ESTATE, "no profiled call yet");
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventSynchronize(c->ev_ph[4]));
+    for (int i = 0; i < 8; ++i) ms[i] = 0.f;
+    for (int i = 0; i < 4; ++i) CU(cudaEventElapsedTime(&ms[i], c->ev_ph[i], c->ev_ph[i + 1]));
+    return ADV_OK;
+}

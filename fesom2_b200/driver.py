@@ -1,0 +1,253 @@
+"""Host-side mirror of the reference's interface for the tracer-advection path, on top of the
+C ABI (include/fesom_adv_b200.h, libfesom_adv_b200.so).
+
+The reference's seam is the Fortran procedure ``do_oce_adv_tra(dt, vel, w, wi, we, tr_num, dynamics,
+tracers, partit, mesh)`` (src/oce_adv_tra_driver.F90:46).  ``AdvB200`` keeps that shape: a mesh
+(+partit) object creates the context once (``oce_adv_tra_fct_init``), the per-step state carries
+``uv,w,w_i,w_e`` and the ALE thicknesses, and ``do_oce_adv_tra`` takes the tracer batch and
+accumulates into ``del_ttf_advhoriz/del_ttf_advvert``.  torch is used only to own device memory
+and streams; all arithmetic happens in the CUDA library.  There is no CPU fallback: if the
+library is missing or no GPU is present the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfesom_adv_b200.so")
+
+ADV_HOST, ADV_DEVICE = 0, 1
+ADV_ESCHEME = -3
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int32)
+
+
+class AdvError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"fesom_adv_b200 error {code}: {msg}")
+        self.code = code
+
+
+class MeshDesc(C.Structure):
+    _fields_ = [("nl", C.c_int32), ("myDim_nod2D", C.c_int32), ("eDim_nod2D", C.c_int32),
+                ("myDim_elem2D", C.c_int32), ("eDim_elem2D", C.c_int32), ("myDim_edge2D", C.c_int32),
+                ("nod_in_elem2D_ld", C.c_int32),
+                ("edges", c_ip), ("edge_tri", c_ip), ("elem2D_nodes", c_ip), ("nod_in_elem2D", c_ip),
+                ("nod_in_elem2D_num", c_ip), ("nlevels", c_ip), ("ulevels", c_ip),
+                ("nlevels_nod2D", c_ip), ("ulevels_nod2D", c_ip),
+                ("edge_cross_dxdy", c_dp), ("edge_dxdy", c_dp), ("elem_cos", c_dp),
+                ("area", c_dp), ("areasvol", c_dp), ("nboundary_lay", c_ip),
+                ("mype", C.c_int32), ("npes", C.c_int32),
+                ("rPEnum", C.c_int32), ("rPE", c_ip), ("rptr", c_ip), ("rlist", c_ip),
+                ("sPEnum", C.c_int32), ("sPE", c_ip), ("sptr", c_ip), ("slist", c_ip)]
+
+
+class StateDesc(C.Structure):
+    _fields_ = [("uv", c_dp), ("w", c_dp), ("w_e", c_dp), ("w_i", c_dp), ("helem", c_dp),
+                ("hnode", c_dp), ("hnode_new", c_dp), ("zbar_3d_n", c_dp), ("Z_3d_n", c_dp),
+                ("zbar_n_bot", c_dp), ("use_wsplit", C.c_int32)]
+
+
+class TracerDesc(C.Structure):
+    _fields_ = [("values", c_dp), ("valuesAB", c_dp), ("edge_up_dn_grad", c_dp),
+                ("del_ttf_advhoriz", c_dp), ("del_ttf_advvert", c_dp),
+                ("tra_adv_hor", C.c_char_p), ("tra_adv_ver", C.c_char_p), ("tra_adv_lim", C.c_char_p),
+                ("tra_adv_ph", C.c_double), ("tra_adv_pv", C.c_double)]
+
+
+EXPORTS = ["adv_ctx_create", "adv_ctx_destroy", "adv_last_error", "adv_comm_unique_id",
+           "adv_ctx_comm_init", "adv_ctx_set_state", "adv_do_oce_adv_tra", "adv_do_oce_adv_tra_async",
+           "adv_ctx_synchronize", "adv_exchange_nod", "adv_update_values", "adv_ctx_get_work",
+           "adv_ctx_launch_count", "adv_ctx_stream", "adv_ctx_last_elapsed_ms",
+           "adv_ctx_set_profiling", "adv_ctx_phase_ms"]
+
+_lib = None
+
+
+def load_library():
+    """dlopen the CUDA library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(f"{LIB_PATH} is missing: run __graft_entry__.build() (nvcc, sm_100a). "
+                                    "There is no CPU fallback for this path.")
+        L = C.CDLL(LIB_PATH)
+        L.adv_last_error.restype = C.c_char_p
+        L.adv_ctx_launch_count.restype = C.c_int64
+        L.adv_ctx_launch_count.argtypes = [C.c_void_p]
+        L.adv_ctx_stream.restype = C.c_void_p
+        L.adv_ctx_stream.argtypes = [C.c_void_p]
+        L.adv_ctx_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(MeshDesc), C.c_int, C.c_int]
+        L.adv_ctx_destroy.argtypes = [C.c_void_p]
+        L.adv_comm_unique_id.argtypes = [C.c_char_p]
+        L.adv_ctx_comm_init.argtypes = [C.c_void_p, C.c_char_p]
+        L.adv_ctx_set_state.argtypes = [C.c_void_p, C.POINTER(StateDesc), C.c_int]
+        L.adv_do_oce_adv_tra.argtypes = [C.c_void_p, C.c_double, C.c_int, C.POINTER(TracerDesc), C.c_int]
+        L.adv_do_oce_adv_tra_async.argtypes = [C.c_void_p, C.c_double, C.c_int, C.POINTER(TracerDesc)]
+        L.adv_ctx_synchronize.argtypes = [C.c_void_p]
+        L.adv_exchange_nod.argtypes = [C.c_void_p, C.c_int, C.POINTER(c_dp), C.c_int]
+        L.adv_update_values.argtypes = [C.c_void_p, C.c_int, C.POINTER(c_dp), C.POINTER(c_dp), C.POINTER(c_dp)]
+        L.adv_ctx_get_work.argtypes = [C.c_void_p, C.c_char_p, C.c_int, c_dp]
+        L.adv_ctx_last_elapsed_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.adv_ctx_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.adv_ctx_phase_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        _lib = L
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise AdvError(rc, load_library().adv_last_error().decode())
+
+
+def unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _check(load_library().adv_comm_unique_id(buf))
+    return buf.raw
+
+
+def _ptr(t) -> c_dp:
+    """Raw pointer of a float64 contiguous torch tensor (cpu or cuda) or numpy array."""
+    if t is None:
+        return c_dp()
+    if isinstance(t, np.ndarray):
+        assert t.dtype == np.float64 and t.flags.c_contiguous
+        return t.ctypes.data_as(c_dp)
+    assert t.dtype.is_floating_point and t.element_size() == 8 and t.is_contiguous()
+    return C.cast(t.data_ptr(), c_dp)
+
+
+def _where(t) -> int:
+    if isinstance(t, np.ndarray):
+        return ADV_HOST
+    return ADV_DEVICE if t.is_cuda else ADV_HOST
+
+
+class AdvB200:
+    """One rank's advection context (mesh + partit resident on one GPU)."""
+
+    def __init__(self, mesh, nboundary_lay: Optional[np.ndarray] = None, device: int = 0, max_tracers: int = 2):
+        self.lib = load_library()
+        self.mesh = mesh
+        m = mesh
+        k = self._keep = {}
+        d = MeshDesc(nl=m.nl, myDim_nod2D=m.N, eDim_nod2D=m.eDim_nod2D, myDim_elem2D=m.T,
+                     eDim_elem2D=m.eDim_elem2D, myDim_edge2D=m.E)
+        for name in ("edges", "edge_tri", "elem2D_nodes", "nod_in_elem2D", "nod_in_elem2D_num",
+                     "nlevels", "ulevels", "nlevels_nod2D", "ulevels_nod2D"):
+            k[name] = np.ascontiguousarray(getattr(m, name), dtype=np.int32)
+            setattr(d, name, k[name].ctypes.data_as(c_ip))
+        d.nod_in_elem2D_ld = k["nod_in_elem2D"].shape[1]
+        for name in ("edge_cross_dxdy", "edge_dxdy", "elem_cos", "area", "areasvol"):
+            k[name] = np.ascontiguousarray(getattr(m, name), dtype=np.float64)
+            setattr(d, name, k[name].ctypes.data_as(c_dp))
+        if nboundary_lay is not None:
+            k["nb"] = np.ascontiguousarray(nboundary_lay, dtype=np.int32)
+            d.nboundary_lay = k["nb"].ctypes.data_as(c_ip)
+        com = m.com_nod2D
+        d.mype, d.npes = m.mype, m.npes
+        for name in ("rPE", "rptr", "rlist", "sPE", "sptr", "slist"):
+            k[name] = np.ascontiguousarray(getattr(com, name), dtype=np.int32)
+            setattr(d, name, k[name].ctypes.data_as(c_ip))
+        d.rPEnum, d.sPEnum = com.rPEnum, com.sPEnum
+        self.max_tracers = max_tracers
+        self.device = device
+        h = C.c_void_p()
+        _check(self.lib.adv_ctx_create(C.byref(h), C.byref(d), device, max_tracers))
+        self.h = h
+        self._state = None
+
+    # -- life cycle ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.adv_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def comm_init(self, uid: bytes):
+        _check(self.lib.adv_ctx_comm_init(self.h, uid))
+
+    # -- per step -----------------------------------------------------------------------------
+    def set_state(self, st):
+        """``st``: fields.OceanState with torch tensors (all cpu or all cuda)."""
+        self._state = st   # keep alive: device pointers are used in place
+        sd = StateDesc(uv=_ptr(st.uv), w=_ptr(st.w), w_e=_ptr(st.w_e), w_i=_ptr(st.w_i), helem=_ptr(st.helem),
+                       hnode=_ptr(st.hnode), hnode_new=_ptr(st.hnode_new), zbar_3d_n=_ptr(st.zbar_3d_n),
+                       Z_3d_n=_ptr(st.Z_3d_n), zbar_n_bot=_ptr(st.zbar_n_bot), use_wsplit=int(bool(st.use_wsplit)))
+        _check(self.lib.adv_ctx_set_state(self.h, C.byref(sd), _where(st.uv)))
+
+    def _descs(self, tracers, dttf_h, dttf_v):
+        n = len(tracers)
+        arr = (TracerDesc * n)()
+        keep = []
+        for i, t in enumerate(tracers):
+            hs, vs, ls = t.tra_adv_hor.encode(), t.tra_adv_ver.encode(), t.tra_adv_lim.encode()
+            keep += [hs, vs, ls]
+            arr[i] = TracerDesc(values=_ptr(t.values), valuesAB=_ptr(t.valuesAB), edge_up_dn_grad=_ptr(t.edge_up_dn_grad),
+                                del_ttf_advhoriz=_ptr(dttf_h[i]), del_ttf_advvert=_ptr(dttf_v[i]),
+                                tra_adv_hor=hs, tra_adv_ver=vs, tra_adv_lim=ls,
+                                tra_adv_ph=float(t.tra_adv_ph), tra_adv_pv=float(t.tra_adv_pv))
+        return arr, keep
+
+    def do_oce_adv_tra(self, dt: float, tracers: Sequence, dttf_h: Sequence, dttf_v: Sequence, sync: bool = True):
+        """Batched ``do_oce_adv_tra``.  Tensors on cuda are used in place; cpu tensors / numpy arrays
+        are copied to the device and the tendencies copied back (blocking)."""
+        arr, keep = self._descs(tracers, dttf_h, dttf_v)
+        where = _where(tracers[0].values)
+        if where == ADV_DEVICE and not sync:
+            _check(self.lib.adv_do_oce_adv_tra_async(self.h, float(dt), len(tracers), arr))
+        else:
+            _check(self.lib.adv_do_oce_adv_tra(self.h, float(dt), len(tracers), arr, where))
+
+    def synchronize(self):
+        _check(self.lib.adv_ctx_synchronize(self.h))
+
+    def exchange_nod(self, fields: Sequence, nlev: int):
+        PA = c_dp * len(fields)
+        _check(self.lib.adv_exchange_nod(self.h, len(fields), PA(*[_ptr(f) for f in fields]), int(nlev)))
+
+    def update_values(self, values: Sequence, dttf_h: Sequence, dttf_v: Sequence):
+        n = len(values)
+        PA = c_dp * n
+        _check(self.lib.adv_update_values(self.h, n, PA(*[_ptr(v) for v in values]),
+                                          PA(*[_ptr(v) for v in dttf_h]), PA(*[_ptr(v) for v in dttf_v])))
+
+    # -- introspection ------------------------------------------------------------------------
+    def get_work(self, name: str, slot: int = 0) -> np.ndarray:
+        m = self.mesh
+        shape = {"fct_LO": (m.Nh, m.L), "fct_plus": (m.Nh, m.L), "fct_minus": (m.Nh, m.L),
+                 "adv_flux_hor": (m.E, m.L), "adv_flux_ver": (m.N, m.nl), "edge_volflux": (m.E, m.L)}[name]
+        out = np.empty(shape, np.float64)
+        _check(self.lib.adv_ctx_get_work(self.h, name.encode(), slot, out.ctypes.data_as(c_dp)))
+        return out
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.adv_ctx_launch_count(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.adv_ctx_stream(self.h) or 0)
+
+    def last_elapsed_ms(self) -> float:
+        ms = C.c_float()
+        _check(self.lib.adv_ctx_last_elapsed_ms(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def set_profiling(self, on: bool):
+        _check(self.lib.adv_ctx_set_profiling(self.h, int(on)))
+
+    def phase_ms(self) -> List[float]:
+        arr = (C.c_float * 8)()
+        _check(self.lib.adv_ctx_phase_ms(self.h, arr))
+        return [float(x) for x in arr]

@@ -588,3 +588,24 @@ def simple_partition(g: Mesh, npes: int) -> np.ndarray:
 
     rec(np.arange(g.Nh), 0, npes)
     return part
+
+
+def load_npz_mesh(path: str) -> Mesh:
+    """Load a mesh fixture written by tests/golden/make_mesh_fixtures.py (raw mesh data of the
+    reference's test/meshes/*); returns the derived global mesh.  Partition vectors stored in the
+    file are attached as ``mesh.parts = {npes: part}``."""
+    z = np.load(path)
+    coord = np.ascontiguousarray(z["coord_deg"], dtype=np.float64) * RAD
+    N, T, E = coord.shape[0], z["elem2D_nodes"].shape[0], z["edges"].shape[0]
+    m = Mesh(nl=int(z["nl"]), myDim_nod2D=N, eDim_nod2D=0, myDim_elem2D=T, eDim_elem2D=0, myDim_edge2D=E,
+             cyclic_length=float(z["cyclic_length_deg"]) * RAD, cartesian=False, coord_nod2D=coord,
+             elem2D_nodes=z["elem2D_nodes"].astype(np.int32), edges=z["edges"].astype(np.int32),
+             edge_tri=z["edge_tri"].astype(np.int32), nlevels=z["nlevels"].astype(np.int32),
+             ulevels=np.ones(T, np.int32), nlevels_nod2D=z["nlevels_nod2D"].astype(np.int32),
+             ulevels_nod2D=np.ones(N, np.int32), zbar=z["zbar"].astype(np.float64))
+    m.myList_nod2D = np.arange(1, N + 1, dtype=np.int32)
+    m.myList_elem2D = np.arange(1, T + 1, dtype=np.int32)
+    m.myList_edge2D = np.arange(1, E + 1, dtype=np.int32)
+    derive_geometry(m)
+    m.parts = {int(k[4:]): z[k].astype(np.int32) for k in z.files if k.startswith("part")}
+    return m

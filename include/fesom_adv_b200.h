@@ -1,0 +1,161 @@
+/* include/fesom_adv_b200.h -- C ABI of the B200 tracer-advection library (libfesom_adv_b200.so).
+ *
+ * Drop-in boundary for the reference's Fortran procedures (FESOM/fesom2 @ e3c3d9d); every entry
+ * point names the reference interface it replaces.  The reference has no FFI for this path: the
+ * seam is the external-procedure interface `do_oce_adv_tra` (src/oce_adv_tra_driver.F90:1-21) and
+ * `exchange_nod` (src/gen_halo_exchange.F90:2731-2768).  A Fortran host binds these functions with
+ * ISO_C_BINDING, passing c_loc() of the allocatable components of t_mesh / t_partit / t_tracer /
+ * t_dyn plus scalar dimensions (see INTEGRATION.md and fesom2_b200/fortran/oce_adv_tra_b200.F90).
+ *
+ * Conventions
+ *   - All arrays keep the reference's memory layout: column-major, level index fastest,
+ *     e.g. values(nl-1, myDim_nod2D+eDim_nod2D), edge_up_dn_grad(4, nl-1, myDim_edge2D).
+ *   - All index VALUES are 1-based local indices, as stored by the Fortran host.
+ *   - Reals are IEEE binary64 (WP = real64, src/oce_modules.F90:17); integers are 32 bit.
+ *   - Every function returns 0 on success, a negative ADV_E* code otherwise (the reference has no
+ *     status codes: an unknown scheme ends in par_ex -> MPI_ABORT, oce_adv_tra_driver.F90:351-353;
+ *     the Fortran shim calls par_ex when it sees ADV_ESCHEME).
+ *   - `where` tells whether the data pointers of a call are HOST or DEVICE pointers.  Host
+ *     pointers are copied H2D / D2H inside the call; device pointers are used in place (the
+ *     OpenACC `!$ACC HOST_DATA USE_DEVICE` convention of the reference's GPU build).
+ *   - No CPU fallback exists: without a CUDA device every call fails with ADV_ECUDA.
+ */
+#ifndef FESOM_ADV_B200_H
+#define FESOM_ADV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADV_OK        0
+#define ADV_EINVAL   -1   /* bad argument / inconsistent mesh */
+#define ADV_ECUDA    -2   /* CUDA runtime error (adv_last_error() has the text) */
+#define ADV_ESCHEME  -3   /* unknown tra_adv_hor / tra_adv_ver / tra_adv_lim string */
+#define ADV_ENCCL    -4   /* NCCL error */
+#define ADV_ESTATE   -5   /* call order violated (e.g. no state set) */
+
+#define ADV_HOST      0
+#define ADV_DEVICE    1
+
+typedef struct adv_ctx adv_ctx_t;
+
+/* Static mesh + partition description: the slice of t_mesh (src/MOD_MESH.F90:22-175, views in
+ * src/associate_mesh_ass.h:9-79) and t_partit (src/MOD_PARTIT.F90:35-120) that the path reads.
+ * All pointers are HOST pointers; the arrays are copied and may be released after the call. */
+typedef struct {
+    int32_t nl;                 /* mesh%nl: number of interfaces, layers = nl-1 */
+    int32_t myDim_nod2D, eDim_nod2D;
+    int32_t myDim_elem2D, eDim_elem2D; /* vel/helem/nlevels/... carry myDim+eDim element columns */
+    int32_t myDim_edge2D;
+    int32_t nod_in_elem2D_ld;   /* leading dimension of nod_in_elem2D */
+    const int32_t *edges;             /* (2, myDim_edge2D)                          */
+    const int32_t *edge_tri;          /* (2, myDim_edge2D), <= 0: no element        */
+    const int32_t *elem2D_nodes;      /* (3, myDim_elem2D)                          */
+    const int32_t *nod_in_elem2D;     /* (ld, myDim_nod2D)                          */
+    const int32_t *nod_in_elem2D_num; /* (myDim_nod2D)                              */
+    const int32_t *nlevels, *ulevels;             /* (myDim_elem2D [+eDim])         */
+    const int32_t *nlevels_nod2D, *ulevels_nod2D; /* (myDim_nod2D+eDim_nod2D)       */
+    const double  *edge_cross_dxdy;   /* (4, myDim_edge2D)                          */
+    const double  *edge_dxdy;         /* (2, myDim_edge2D)                          */
+    const double  *elem_cos;          /* (myDim_elem2D [+eDim])                     */
+    const double  *area;              /* (nl, myDim_nod2D+eDim_nod2D)               */
+    const double  *areasvol;          /* (nl, myDim_nod2D+eDim_nod2D)               */
+    const int32_t *nboundary_lay;     /* (myDim_nod2D+eDim_nod2D) t_tracer_work, may be NULL if MUSCL unused */
+    /* com_nod2D (src/MOD_PARTIT.F90:18-33); all NULL / 0 on a single rank */
+    int32_t mype, npes;
+    int32_t rPEnum; const int32_t *rPE, *rptr, *rlist;
+    int32_t sPEnum; const int32_t *sPE, *sptr, *slist;
+} adv_mesh_desc_t;
+
+/* Per-step ocean state: what the reference refreshes with `!$ACC UPDATE DEVICE` every step
+ * (src/oce_ale_tracer.F90:260-262): dynamics%uv,w,w_e,w_i and mesh%helem,hnode,hnode_new,
+ * zbar_3d_n,Z_3d_n.  zbar_n_bot may be NULL unless use_wsplit. */
+typedef struct {
+    const double *uv;         /* (2, nl-1, myDim_elem2D+eDim_elem2D) */
+    const double *w, *w_e, *w_i; /* (nl, Nh) */
+    const double *helem;      /* (nl-1, myDim_elem2D+eDim_elem2D)    */
+    const double *hnode, *hnode_new; /* (nl-1, Nh) */
+    const double *zbar_3d_n;  /* (nl, Nh)   */
+    const double *Z_3d_n;     /* (nl-1, Nh) */
+    const double *zbar_n_bot; /* (Nh)       */
+    int32_t use_wsplit;       /* dynamics%use_wsplit (src/MOD_DYN.F90:156) */
+} adv_state_desc_t;
+
+/* One tracer of the batch: t_tracer_data (src/MOD_TRACER.F90:10-45) + its work slices. */
+typedef struct {
+    const double *values;          /* ttf   (nl-1, Nh) in    */
+    const double *valuesAB;        /* ttfAB (nl-1, Nh) in    */
+    const double *edge_up_dn_grad; /* (4, nl-1, myDim_edge2D) in (NOT clobbered, unlike the
+                                      reference which reuses it as FCT scratch,
+                                      oce_adv_tra_driver.F90:383-384); may be NULL for UPW1 */
+    double *del_ttf_advhoriz;      /* (nl-1, Nh) inout, accumulated */
+    double *del_ttf_advvert;       /* (nl-1, Nh) inout, accumulated */
+    const char *tra_adv_hor;       /* "MUSCL" | "MFCT" | "UPW1"          (blank padded or NUL terminated) */
+    const char *tra_adv_ver;       /* "QR4C" | "CDIFF" | "PPM" | "UPW1"  */
+    const char *tra_adv_lim;       /* "FCT" or anything else = no limiter */
+    double tra_adv_ph, tra_adv_pv; /* num_ord of the horizontal / vertical scheme */
+} adv_tracer_desc_t;
+
+/* --- life cycle ------------------------------------------------------------------------------ */
+/* Replaces oce_adv_tra_fct_init (src/oce_adv_tra_fct.F90:35-67) and the `!$ACC ENTER DATA` of the
+ * static mesh (src/fesom_module.F90:759-805): uploads the mesh, builds the node->edge gather
+ * lists, FCT cluster lists and halo pack lists, allocates all work arrays for `max_tracers`
+ * tracers per batched call. */
+int adv_ctx_create(adv_ctx_t **ctx, const adv_mesh_desc_t *mesh, int device, int max_tracers);
+int adv_ctx_destroy(adv_ctx_t *ctx);
+const char *adv_last_error(void);
+
+/* Replaces par_init/init_mpi_types for this path (src/gen_modules_partitioning.F90:41-85,
+ * :416-514): one NCCL communicator over the npes ranks.  Rank 0 calls adv_comm_unique_id and the
+ * host broadcasts the 128 bytes (MPI_Bcast in the Fortran host, torch.distributed in the tests). */
+int adv_comm_unique_id(char id[128]);
+int adv_ctx_comm_init(adv_ctx_t *ctx, const char id[128]);
+
+/* --- per step ------------------------------------------------------------------------------- */
+int adv_ctx_set_state(adv_ctx_t *ctx, const adv_state_desc_t *st, int where);
+
+/* Replaces `do_oce_adv_tra(dt, vel, w, wi, we, tr_num, dynamics, tracers, partit, mesh)`
+ * (src/oce_adv_tra_driver.F90:46-490) for a BATCH of ntr tracers (ntr = 1 reproduces one Fortran
+ * call), including its two internal halo exchanges (:335 and src/oce_adv_tra_fct.F90:413).
+ * vel/w/wi/we are those of the last adv_ctx_set_state.  Accumulates into del_ttf_advhoriz /
+ * del_ttf_advvert.  Blocking: results are complete on return. */
+int adv_do_oce_adv_tra(adv_ctx_t *ctx, double dt, int ntr, const adv_tracer_desc_t *tr, int where);
+
+/* Same, asynchronous on the context's stream, DEVICE pointers only (dwarf convention: operands
+ * stay resident in one `!$ACC DATA` region, dwarf/dwarf_tracer/dwarf_ini/fesom.F90:71-130). */
+int adv_do_oce_adv_tra_async(adv_ctx_t *ctx, double dt, int ntr, const adv_tracer_desc_t *tr);
+int adv_ctx_synchronize(adv_ctx_t *ctx);
+
+/* Replaces `exchange_nod(field, partit)` for nfields 3-D node fields with nlev levels
+ * (src/gen_halo_exchange.F90:432-633): packed-halo NCCL send/recv.  DEVICE pointers. */
+int adv_exchange_nod(adv_ctx_t *ctx, int nfields, double *const *fields, int nlev);
+
+/* The dwarf's epilogue (dwarf/dwarf_tracer/dwarf_ini/fesom.F90:105-127) with del_ttf reset per
+ * step as in the model (src/oce_tracer_mod.F90:28-34): values += (advhoriz+advvert)/hnode_new on
+ * owned nodes, then exchange_nod(values).  DEVICE pointers. */
+int adv_update_values(adv_ctx_t *ctx, int ntr, double *const *values,
+                      const double *const *del_ttf_advhoriz, const double *const *del_ttf_advvert);
+
+/* --- introspection (tests, profiling) -------------------------------------------------------- */
+/* Copies an internal work array of tracer slot `slot` to a HOST buffer.  name is one of
+ * "fct_LO" (nl-1,Nh), "adv_flux_hor" (nl-1,E), "adv_flux_ver" (nl,N), "fct_plus", "fct_minus"
+ * (nl-1,Nh), "edge_volflux" (nl-1,E; slot ignored). */
+int adv_ctx_get_work(adv_ctx_t *ctx, const char *name, int slot, double *out);
+/* number of kernels launched by this context since creation */
+int64_t adv_ctx_launch_count(const adv_ctx_t *ctx);
+/* raw CUDA stream (cudaStream_t) the context computes on */
+void *adv_ctx_stream(adv_ctx_t *ctx);
+/* device-side duration [ms] of the last adv_do_oce_adv_tra[_async] call, measured with CUDA
+ * events on the context's compute stream (valid after synchronisation) */
+int adv_ctx_last_elapsed_ms(adv_ctx_t *ctx, float *ms);
+/* per-phase kernel time of the last call [ms]: 0 volflux, 1 lo+adf, 2 bounds/R, 3 update, 4 halo
+ * wait; valid only when profiling was switched on with adv_ctx_set_profiling(ctx, 1) */
+int adv_ctx_set_profiling(adv_ctx_t *ctx, int on);
+int adv_ctx_phase_ms(adv_ctx_t *ctx, float ms[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FESOM_ADV_B200_H */

@@ -1,0 +1,145 @@
+"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerance: north_star demands 1e-12 relative per step (SURVEY Appendix C metric); the gather
+formulation reproduces the serial summation order, so in practice the results are bit-identical
+and the strictest tests assert exactly that."""
+import itertools
+
+import numpy as np
+import pytest
+import torch
+
+from common import TOL_STEP, make_case, rel_err, run_cuda, run_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(mesh, ctx, dh, dv, ora, ntr, fct=True, exact=False):
+    worst = 0.0
+    for k in range(ntr):
+        for name, got, ref in (("del_ttf_advhoriz", dh[k], ora.dttf_h[k]), ("del_ttf_advvert", dv[k], ora.dttf_v[k])):
+            assert np.isfinite(got).all(), name
+            e = rel_err(got, ref)
+            worst = max(worst, e)
+            assert e <= TOL_STEP, (k, name, e)
+            if exact:
+                assert np.array_equal(got, ref), (k, name, "not bit-identical", e)
+    if fct:
+        # the last tracer of the batch is what the oracle's shared work arrays hold
+        k = ntr - 1
+        N = mesh.N
+        lo = ctx.get_work("fct_LO", k)
+        assert rel_err(lo[:N], ora.keep["fct_LO"][:N]) <= TOL_STEP
+        assert rel_err(ctx.get_work("fct_plus", k)[:N], ora.keep["fct_plus"][:N]) <= TOL_STEP
+        assert rel_err(ctx.get_work("fct_minus", k)[:N], ora.keep["fct_minus"][:N]) <= TOL_STEP
+    return worst
+
+
+def test_config1_pi_muscl_qr4c_fct(pi_mesh):
+    """BASELINE config 1: dwarf_tracer on the pi mesh, T+S MUSCL + QR4C + FCT (ph=0, pv=1)."""
+    st, trs, nb, dt = make_case(pi_mesh, 2, "MUSCL", "QR4C", "FCT")
+    ora = run_oracle(pi_mesh, st, trs, nb, dt)
+    ctx, dh, dv = run_cuda(pi_mesh, st, trs, nb, dt)
+    _compare(pi_mesh, ctx, dh, dv, ora, 2, exact=True)
+    ctx.close()
+
+
+def test_config1_pi_dwarf_dt(pi_mesh):
+    """same with the dwarf's literal dt = 1.e-3 (dwarf_ini/fesom.F90:97)."""
+    st, trs, nb, _ = make_case(pi_mesh, 1, "MUSCL", "QR4C", "FCT")
+    ora = run_oracle(pi_mesh, st, trs, nb, 1.0e-3)
+    ctx, dh, dv = run_cuda(pi_mesh, st, trs, nb, 1.0e-3)
+    _compare(pi_mesh, ctx, dh, dv, ora, 1, exact=True)
+    ctx.close()
+
+
+def test_config2_soufflet_mfct_qr4c_fct(souf_mesh):
+    """BASELINE config 2: soufflet channel mesh (cyclic_length 4.5 deg), MFCT + QR4C + FCT."""
+    st, trs, nb, dt = make_case(souf_mesh, 2, "MFCT", "QR4C", "FCT")
+    ora = run_oracle(souf_mesh, st, trs, nb, dt)
+    ctx, dh, dv = run_cuda(souf_mesh, st, trs, nb, dt)
+    _compare(souf_mesh, ctx, dh, dv, ora, 2, exact=True)
+    ctx.close()
+
+
+@pytest.mark.parametrize("hor,ver,lim", list(itertools.product(("UPW1", "MUSCL", "MFCT"),
+                                                               ("UPW1", "QR4C", "PPM", "CDIFF"), ("FCT", "NON"))))
+def test_all_scheme_combinations(small_mesh, hor, ver, lim):
+    """every tra_adv_hor x tra_adv_ver x tra_adv_lim the driver dispatches on
+    (oce_adv_tra_driver.F90:343-379), with fractional num_ord"""
+    st, trs, nb, dt = make_case(small_mesh, 2, hor, ver, lim, ph=0.25, pv=0.75)
+    ora = run_oracle(small_mesh, st, trs, nb, dt)
+    ctx, dh, dv = run_cuda(small_mesh, st, trs, nb, dt)
+    _compare(small_mesh, ctx, dh, dv, ora, 2, fct=(lim == "FCT"))
+    ctx.close()
+
+
+def test_odd_tracer_count_and_mixed_schemes(small_mesh):
+    st, trs, nb, dt = make_case(small_mesh, 5, "MFCT", "QR4C", "FCT")
+    trs[1].tra_adv_hor = "MUSCL"
+    trs[3].tra_adv_ver = "PPM"
+    trs[4].tra_adv_lim = "NON"
+    ora = run_oracle(small_mesh, st, trs, nb, dt)
+    ctx, dh, dv = run_cuda(small_mesh, st, trs, nb, dt)
+    _compare(small_mesh, ctx, dh, dv, ora, 5, fct=False)
+    ctx.close()
+
+
+def test_use_wsplit(small_mesh):
+    """dynamics%use_wsplit: implicit vertical part adv_tra_vert_impl (oce_adv_tra_driver.F90:323-334)"""
+    st, trs, nb, dt = make_case(small_mesh, 2, "MFCT", "QR4C", "FCT", use_wsplit=True)
+    assert st.w_i.abs().max() > 0
+    ora = run_oracle(small_mesh, st, trs, nb, dt)
+    ctx, dh, dv = run_cuda(small_mesh, st, trs, nb, dt)
+    _compare(small_mesh, ctx, dh, dv, ora, 2)
+    ctx.close()
+
+
+def test_ale_thickness_change(small_mesh):
+    """hnode_new /= hnode (zlevel / zstar ALE)"""
+    st, trs, nb, dt = make_case(small_mesh, 2, "MFCT", "QR4C", "FCT", ale_amp=0.3)
+    ora = run_oracle(small_mesh, st, trs, nb, dt)
+    ctx, dh, dv = run_cuda(small_mesh, st, trs, nb, dt)
+    _compare(small_mesh, ctx, dh, dv, ora, 2)
+    ctx.close()
+
+
+def test_host_pointer_call(pi_mesh):
+    """the HOST-pointer flavour of the C ABI (H2D / D2H inside the call)"""
+    st, trs, nb, dt = make_case(pi_mesh, 2, "MFCT", "QR4C", "FCT")
+    ora = run_oracle(pi_mesh, st, trs, nb, dt)
+    ctx, dh, dv = run_cuda(pi_mesh, st, trs, nb, dt, host_ptrs=True)
+    _compare(pi_mesh, ctx, dh, dv, ora, 2, exact=True)
+    ctx.close()
+
+
+def test_accumulates_into_del_ttf(small_mesh):
+    """do_oce_adv_tra ACCUMULATES into del_ttf_advhoriz/advvert (driver :535,:556,:607)"""
+    from fesom2_b200.driver import AdvB200
+    from common import to_device
+    st, trs, nb, dt = make_case(small_mesh, 1)
+    dev = torch.device("cuda:0")
+    st_d, trs_d = to_device(st, trs, dev)
+    ctx = AdvB200(small_mesh, nb, max_tracers=1)
+    ctx.set_state(st_d)
+    dh = [torch.full((small_mesh.Nh, small_mesh.L), 1.5, dtype=torch.float64, device=dev)]
+    dv = [torch.full((small_mesh.Nh, small_mesh.L), -2.5, dtype=torch.float64, device=dev)]
+    ctx.do_oce_adv_tra(dt, trs_d, dh, dv)
+    from oracle import oracle_py as O
+    rk = O.OracleRank(small_mesh, st, trs, nb)
+    rk.dttf_h[0][:] = 1.5
+    rk.dttf_v[0][:] = -2.5
+    O.run([rk], dt, 1, 0)
+    assert rel_err(dh[0].cpu().numpy(), rk.dttf_h[0]) <= TOL_STEP
+    assert rel_err(dv[0].cpu().numpy(), rk.dttf_v[0]) <= TOL_STEP
+    ctx.close()
+
+
+def test_unknown_scheme_is_an_error(small_mesh):
+    """unknown scheme string -> error code (the reference calls par_ex, driver :351-353,:373-375)"""
+    from fesom2_b200.driver import AdvError, ADV_ESCHEME
+    st, trs, nb, dt = make_case(small_mesh, 1)
+    trs[0].tra_adv_hor = "WENO"
+    with pytest.raises(AdvError) as ei:
+        run_cuda(small_mesh, st, trs, nb, dt)
+    assert ei.value.code == ADV_ESCHEME
