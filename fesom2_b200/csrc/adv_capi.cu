@@ -115,6 +115,7 @@ struct adv_ctx {
     DevBuf<double2> edge_c;
     DevBuf<double> area, areasvol, Q;
     int nS = 0, nI = 0, nSH = 0;
+    int ms_all = 0, ms_allh = 0, ms_S = 0, ms_I = 0, ms_SH = 0;  // max (column, edge) slots per CTA of each node range
     std::vector<Peer> rpeers, speers;
     int send_cols = 0;
     // state (ADV_HOST staging)
@@ -241,8 +242,19 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
         if (d->nlevels_nod2D[n] > nl || d->ulevels_nod2D[n] < 1) return fail(ADV_EINVAL, "node levels out of range");
     }
 
+    const int cpb0 = kBlock / L;
+    auto max_slots = [&](const int* list, int count) {
+        int best = 0;
+        for (int i = 0; i < count; i += cpb0) {
+            int sum = 0;
+            for (int j = i; j < std::min(count, i + cpb0); ++j) { const int n = list ? list[j] : j; sum += ne_ptr[n + 1] - ne_ptr[n]; }
+            best = std::max(best, sum);
+        }
+        return best;
+    };
     adv_ctx* c = new adv_ctx();
     c->device = device; c->max_tr = max_tracers; c->mype = d->mype; c->npes = std::max(1, d->npes);
+    c->ms_all = max_slots(nullptr, N); c->ms_allh = max_slots(nullptr, Nh);
 #define CUF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { delete c; return fail(ADV_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
     CUF(c->ne_ptr.upload(ne_ptr)); CUF(c->ne_ent.upload(ne_ent));
     CUF(c->cl_ptr.upload(cl_ptr)); CUF(c->cl_ent.upload(cl_ent));
@@ -291,6 +303,7 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
         SH = S;
         for (int n = N; n < Nh; ++n) SH.push_back(n);
         c->nS = (int)S.size(); c->nI = (int)I.size(); c->nSH = (int)SH.size();
+        c->ms_S = max_slots(S.data(), c->nS); c->ms_I = max_slots(I.data(), c->nI); c->ms_SH = max_slots(SH.data(), c->nSH);
         CUF(c->list_S.upload(S)); CUF(c->list_I.upload(I)); CUF(c->list_SH.upload(SH)); CUF(c->slist.upload(sl));
     }
     c->slots.resize(max_tracers);
@@ -417,9 +430,17 @@ void launch_hv(adv_ctx* c, Phase ph, const TrBatch<TB>& b, const NodeRange& r, d
 {
     if (r.count <= 0) return;
     const int grid = nblocks(r.count, r.cpb);
-    const size_t sm2 = (size_t)2 * TB * kBlock * sizeof(double), sm1 = (size_t)TB * kBlock * sizeof(double);
-    if (ph == PH_K1) k_fct_lo_adf<HOR, VER, TB><<<grid, kBlock, sm2, c->s_comp>>>(c->m, b, r, dt);
-    else k_nofct<HOR, VER, TB><<<grid, kBlock, sm1, c->s_comp>>>(c->m, b, r, dt);
+    const int nthr = r.cpb * c->m.L;
+    const size_t sm1 = (size_t)TB * nthr * sizeof(double);
+    if (ph == PH_K1) {
+        const size_t smk = k1_smem_bytes<TB>(c->m.L, r.cpb, r.max_slots);
+        static size_t configured = 0;   // per instantiation: opt in to > 48 KB of dynamic shared memory
+        if (smk > configured) {
+            cudaFuncSetAttribute(k_fct_lo_adf<HOR, VER, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smk);
+            configured = smk;
+        }
+        k_fct_lo_adf<HOR, VER, TB><<<grid, nthr, smk, c->s_comp>>>(c->m, b, r, dt);
+    } else k_nofct<HOR, VER, TB><<<grid, nthr, sm1, c->s_comp>>>(c->m, b, r, dt);
     ++c->launches;
 }
 
@@ -428,9 +449,9 @@ void launch_phase(adv_ctx* c, Phase ph, int hor, int ver, const TrBatch<TB>& b, 
 {
     if (r.count <= 0) return;
     if (ph == PH_K2 || ph == PH_K3) {
-        const int grid = nblocks(r.count, r.cpb);
-        if (ph == PH_K2) k_fct_bounds<TB><<<grid, kBlock, (size_t)2 * TB * kBlock * sizeof(double), c->s_comp>>>(c->m, b, r, dt);
-        else k_fct_update<TB><<<grid, kBlock, (size_t)TB * kBlock * sizeof(double), c->s_comp>>>(c->m, b, r, dt);
+        const int grid = nblocks(r.count, r.cpb), nthr = r.cpb * c->m.L;
+        if (ph == PH_K2) k_fct_bounds<TB><<<grid, nthr, (size_t)2 * TB * nthr * sizeof(double), c->s_comp>>>(c->m, b, r, dt);
+        else k_fct_update<TB><<<grid, nthr, (size_t)TB * nthr * sizeof(double), c->s_comp>>>(c->m, b, r, dt);
         ++c->launches;
         return;
     }
@@ -513,8 +534,9 @@ static int run_batch(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr
         c->q_valid = true;
     }
     mark(1);
-    const NodeRange rAll{nullptr, 0, m.N, cpb}, rS{c->list_S.p, 0, c->nS, cpb}, rI{c->list_I.p, 0, c->nI, cpb},
-        rSH{c->list_SH.p, 0, c->nSH, cpb}, rAllH{nullptr, 0, m.Nh, cpb};
+    const NodeRange rAll{nullptr, 0, m.N, cpb, c->ms_all}, rS{c->list_S.p, 0, c->nS, cpb, c->ms_S},
+        rI{c->list_I.p, 0, c->nI, cpb, c->ms_I}, rSH{c->list_SH.p, 0, c->nSH, cpb, c->ms_SH},
+        rAllH{nullptr, 0, m.Nh, cpb, c->ms_allh};
     auto run = [&](Phase ph, const Chunk& ch, const NodeRange& r) {
         if (ch.tb == 2) launch_phase<2>(c, ph, ch.hor, ch.ver, make_batch<2>(c, ttf, ttfAB, grad, dh, dv, tr, ch.idx), r, dt);
         else launch_phase<1>(c, ph, ch.hor, ch.ver, make_batch<1>(c, ttf, ttfAB, grad, dh, dv, tr, ch.idx), r, dt);
@@ -697,6 +719,20 @@ int adv_ctx_get_work(adv_ctx_t* c, const char* name, int slot, double* out)
         else return fail(ADV_EINVAL, "unknown work array " + s);
     }
     CU(cudaMemcpy(out, src, n * sizeof(double), cudaMemcpyDeviceToHost));
+    return ADV_OK;
+}
+
+int adv_selftest_div(uint64_t count, uint64_t seed, int mode, uint64_t* mismatches)
+{
+    if (!mismatches) return fail(ADV_EINVAL, "null argument");
+    unsigned long long* d = nullptr;
+    CU(cudaMalloc(&d, sizeof(unsigned long long)));
+    CU(cudaMemset(d, 0, sizeof(unsigned long long)));
+    k_selftest_div<<<148 * 8, 256>>>(count, seed, mode, d);
+    unsigned long long h = 0;
+    CU(cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    *mismatches = h;
     return ADV_OK;
 }
 

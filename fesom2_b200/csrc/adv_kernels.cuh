@@ -73,10 +73,28 @@ struct NodeRange {
     const int* list;  // optional indirection (0-based node ids); nullptr = identity
     int begin, count;
     int cpb;          // columns per CTA
+    int max_slots;    // max over CTAs of the number of (column, incident edge) pairs
 };
 
 __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
 __device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
+
+// Correctly rounded x / b from y = RN(1/b): q0 = x*y is refined twice with exact FMA residuals
+// (Markstein: a faithful quotient plus one residual step with the correctly rounded reciprocal
+// is the correctly rounded quotient; the first step makes q faithful).  Bit-identical to the IEEE
+// division of the CPU restatement at a fraction of its ~25 instructions; checked against `/` on
+// 2^28 operands per divisor class by adv_selftest_div (tests/test_gpu_division.py).
+__device__ __forceinline__ double div_rcp(double x, double b, double y)
+{
+    double q = x * y;
+    double r = fma(-b, q, x);
+    q = fma(r, y, q);
+    r = fma(-b, q, x);
+    return fma(r, y, q);
+}
+constexpr double kInv6 = 1.0 / 6.0, kInv3 = 1.0 / 3.0;   // RN(1/6), RN(1/3): compile-time IEEE division
+__device__ __forceinline__ double div6(double x) { return div_rcp(x, 6.0, kInv6); }
+__device__ __forceinline__ double div3(double x) { return div_rcp(x, 3.0, kInv3); }
 
 // ----------------------------------------------------------------------------------------------
 // Q(nz,e): vflux of oce_adv_tra_hor.F90:170,190,211-212,226,242 on the level ranges A-E (:127-160)
@@ -170,8 +188,8 @@ __device__ __forceinline__ double ver_qr4c(const ColV& c, int k, double fin)
         const double qu = (t0 - tp1) / (z0 - zp1);
         const double qd = (tm2 - tm1) / (zm2 - zm1);
         const double zb = CZB(k);
-        const double Tmean1 = t0 + (2 * qc + qu) * (zb - z0) / 3.0;
-        const double Tmean2 = tm1 + (2 * qc + qd) * (zb - zm1) / 3.0;
+        const double Tmean1 = t0 + div3((2 * qc + qu) * (zb - z0));
+        const double Tmean2 = tm1 + div3((2 * qc + qd) * (zb - zm1));
         const double w = CW(k);
         const double Tmean = (w + fabs(w)) * Tmean1 + (w - fabs(w)) * Tmean2;
         v = (-0.5 * (1.0 - c.num_ord) * Tmean - c.num_ord * (0.5 * (Tmean1 + Tmean2)) * w) * CA(k) - v;
@@ -293,16 +311,16 @@ __device__ __forceinline__ double hor_ho(double a1, double a2, double q, double 
                                          double fin)
 {
     if (HOR == HOR_UPW1) return -0.5 * (a1 * qp + a2 * qm) - fin;
-    const double2 g12 = reinterpret_cast<const double2*>(g)[0];  // gx_up, gx_dn
-    const double2 g34 = reinterpret_cast<const double2*>(g)[1];  // gy_up, gy_dn
+    const double2 g12 = __ldg(reinterpret_cast<const double2*>(g));      // gx_up, gx_dn
+    const double2 g34 = __ldg(reinterpret_cast<const double2*>(g) + 1);  // gy_up, gy_dn
     const double d = 2.0 * (a2 - a1);
     double Tmean2, Tmean1;
     if (HOR == HOR_MUSCL) {
-        Tmean2 = a2 - (d + ec.x * g12.y + ec.y * g34.y) / 6.0 * clo2;
-        Tmean1 = a1 + (d + ec.x * g12.x + ec.y * g34.x) / 6.0 * clo1;
+        Tmean2 = a2 - div6(d + ec.x * g12.y + ec.y * g34.y) * clo2;
+        Tmean1 = a1 + div6(d + ec.x * g12.x + ec.y * g34.x) * clo1;
     } else {
-        Tmean2 = a2 - (d + ec.x * g12.y + ec.y * g34.y) / 6.0;
-        Tmean1 = a1 + (d + ec.x * g12.x + ec.y * g34.x) / 6.0;
+        Tmean2 = a2 - div6(d + ec.x * g12.y + ec.y * g34.y);
+        Tmean1 = a1 + div6(d + ec.x * g12.x + ec.y * g34.x);
     }
     const double cHO = qp * Tmean1 + qm * Tmean2;
     return -0.5 * (1.0 - num_ord) * cHO - q * num_ord * 0.5 * (Tmean1 + Tmean2) - fin;
@@ -336,26 +354,110 @@ __device__ __forceinline__ ThreadCol decode(const MeshDev& m, const NodeRange& r
 //              oce_adv_tra_fct.F90:265-377 (b1)
 // outputs: lo(nz,n), adf_v(1:nl,n), adf_h(nz,e) (written by the designated end node), raw P+/P-
 // sums into plus/minus.
+//
+// Two phases per CTA so that no thread walks its edges serially behind dependent loads:
+//   A  every (incident-edge slot, layer) pair of the CTA's columns is one work item: its thread
+//      loads Q, both end values, the 4 gradients and stores the LO and antidiffusive edge flux in
+//      shared memory -- all loads of all slots are in flight together;
+//   B  thread (column, layer) adds the slots in ascending-edge order (the serial order of the
+//      reference's scatter loops), so the sums are bit-identical to the CPU result.
 // ----------------------------------------------------------------------------------------------
+template <int TB>
+__host__ __device__ inline size_t k1_smem_bytes(int L, int cpb, int max_slots)
+{
+    return ((size_t)2 * TB * cpb * L + (size_t)max_slots * TB * 2 * L) * sizeof(double) +
+           (size_t)(3 * cpb + 2 + 2 * max_slots) * sizeof(int);
+}
+
+// launch with blockDim.x == cpb * L: thread = (column g, layer nz0), no idle threads
 template <int HOR, int VER, int TB>
 __global__ void __launch_bounds__(kBlock) k_fct_lo_adf(MeshDev m, TrBatch<TB> b, NodeRange r, double dt)
 {
-    extern __shared__ double sm[];  // [2*TB][blockDim]: LO(we) flux and adf_v at the thread's top interface
-    const int L = m.L, nl = m.nl;
-    const ThreadCol tc = decode(m, r);
-    const int n = tc.n, nz0 = tc.nz0, nz = nz0 + 1;
-    const size_t oL = (size_t)n * L + nz0;       // (L,*) offset
-    const size_t cL = (size_t)n * L, cN = (size_t)n * nl;
-    const bool valid = tc.active && nz >= tc.nzmin && nz <= tc.nzmax - 1;
+    extern __shared__ double sm[];
+    const int L = m.L, nl = m.nl, nthr = blockDim.x;
+    double* s_vert = sm;                                   // [2*TB][nthr] LO(we) flux, adf_v at the top interface
+    double* s_flux = sm + (size_t)2 * TB * nthr;           // [slot][TB][2][L]
+    int2* s_slot = reinterpret_cast<int2*>(s_flux + (size_t)r.max_slots * TB * 2 * L);  // [slot] {node, CSR index}
+    int* s_node = reinterpret_cast<int*>(s_slot + r.max_slots);
+    int* s_k0 = s_node + r.cpb;                            // first CSR entry of the column
+    int* s_off = s_k0 + r.cpb;                             // [cpb+1] slot offset of the column
+    const int c0 = blockIdx.x * r.cpb;
+    const int ncols = min(r.cpb, r.count - c0);
+    const int g = threadIdx.x / L;                         // the only integer division of the kernel
+    const int nz0 = threadIdx.x - g * L, nz = nz0 + 1;
+    if (threadIdx.x < ncols) {
+        const int n = r.list ? r.list[r.begin + c0 + threadIdx.x] : r.begin + c0 + threadIdx.x;
+        s_node[threadIdx.x] = n;
+        s_k0[threadIdx.x] = m.ne_ptr[n];
+        s_off[threadIdx.x + 1] = m.ne_ptr[n + 1] - m.ne_ptr[n];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int off = 0;
+        for (int c = 0; c < ncols; ++c) { const int cnt = s_off[c + 1]; s_off[c] = off; off += cnt; }
+        s_off[ncols] = off;
+    }
+    __syncthreads();
+    const int nslots = s_off[ncols];
+    for (int s = threadIdx.x; s < nslots; s += nthr) {
+        int c = 0;
+        while (c + 1 < ncols && s >= s_off[c + 1]) ++c;
+        s_slot[s] = make_int2(s_node[c], s_k0[c] + (s - s_off[c]));
+    }
+    __syncthreads();
 
+    // ---- phase A: edge fluxes; column group g takes slots g, g+cpb, ... at its layer ----------
+    for (int s = g; s < nslots; s += r.cpb) {
+        const int2 sl = s_slot[s];
+        const int4 ent = __ldg(&m.ne_ent[sl.y]);
+        const int lo = ent.z & 0xff, hi = (ent.z >> 8) & 0xff;
+        if (nz < lo || nz > hi) continue;
+        const int e = ent.x;
+        const bool second = (ent.z >> 16) & 1, writer = (ent.z >> 17) & 1;
+        const int i1 = second ? ent.y : sl.x, i2 = second ? sl.x : ent.y;      // edges(1,e), edges(2,e)
+        const unsigned oe = (unsigned)e * L + nz0, o1 = (unsigned)i1 * L + nz0, o2 = (unsigned)i2 * L + nz0;
+        const double q = __ldg(&m.Q[oe]);
+        const double aq = fabs(q), qp = q + aq, qm = q - aq;
+        double2 ec = make_double2(0.0, 0.0);
+        double clo1 = 1.0, clo2 = 1.0;
+        if (HOR != HOR_UPW1) ec = __ldg(&m.edge_c[e]);
+        if (HOR == HOR_MUSCL) {
+            clo1 = (__ldg(&m.nboundary_lay[i1]) - nz >= 0) ? 1.0 : 0.0;   // oce_adv_tra_hor.F90:411-412
+            clo2 = (__ldg(&m.nboundary_lay[i2]) - nz >= 0) ? 1.0 : 0.0;
+        }
+        double* f = s_flux + (size_t)s * TB * 2 * L + nz0;
+#pragma unroll
+        for (int t = 0; t < TB; ++t) {
+            const double t1 = __ldg(&b.ttf[t][o1]), t2 = __ldg(&b.ttf[t][o2]);
+            const double a1 = __ldg(&b.ttfAB[t][o1]), a2 = __ldg(&b.ttfAB[t][o2]);
+            const double flo = hor_lo(t1, t2, qp, qm);                                  // driver :115
+            const double* gr = (HOR != HOR_UPW1) ? (b.grad[t] + (size_t)oe * 4) : nullptr;
+            const double adf = hor_ho<HOR>(a1, a2, q, qp, qm, ec, gr, b.ph[t], clo1, clo2, flo);  // driver :343-354
+            f[(2 * t) * L] = flo;
+            f[(2 * t + 1) * L] = adf;
+            if (writer) b.adf_h[t][oe] = adf;
+        }
+    }
+
+    // ---- vertical fluxes at the thread's top interface ------------------------------------------
+    const bool active = g < ncols;
+    int n = 0, nzmin = 1, nzmax = 0;
+    if (active) {
+        n = s_node[g];
+        const uchar4 lv = m.node_lev[n];
+        nzmin = lv.x; nzmax = lv.y;
+    }
+    const size_t oL = (size_t)n * L + nz0;
+    const size_t cL = (size_t)n * L, cN = (size_t)n * nl;
+    const bool valid = active && nz >= nzmin && nz <= nzmax - 1;
     double flo_top[TB], adfv_top[TB];
 #pragma unroll
     for (int t = 0; t < TB; ++t) { flo_top[t] = 0.0; adfv_top[t] = 0.0; }
-    if (tc.active && nz >= tc.nzmin && nz <= tc.nzmax) {
+    if (active && nz >= nzmin && nz <= nzmax) {
         ColV c;
         c.area = m.area + cN; c.Z = m.Z3d + cL; c.zbar = m.zbar3d + cN;
         c.hnode = m.hnode + cL; c.hnode_new = m.hnode_new + cL;
-        c.nzmin = tc.nzmin; c.nzmax = tc.nzmax; c.dt = dt;
+        c.nzmin = nzmin; c.nzmax = nzmax; c.dt = dt;
 #pragma unroll
         for (int t = 0; t < TB; ++t) {
             c.ttf = b.ttf[t] + cL; c.w = m.we + cN; c.num_ord = 0.0;
@@ -369,11 +471,11 @@ __global__ void __launch_bounds__(kBlock) k_fct_lo_adf(MeshDev m, TrBatch<TB> b,
     }
 #pragma unroll
     for (int t = 0; t < TB; ++t) {
-        sm[(2 * t) * blockDim.x + threadIdx.x] = flo_top[t];
-        sm[(2 * t + 1) * blockDim.x + threadIdx.x] = adfv_top[t];
+        s_vert[(2 * t) * nthr + threadIdx.x] = flo_top[t];
+        s_vert[(2 * t + 1) * nthr + threadIdx.x] = adfv_top[t];
     }
     __syncthreads();
-    if (tc.active) {
+    if (active) {
 #pragma unroll
         for (int t = 0; t < TB; ++t) {
             b.adf_v[t][cN + nz0] = adfv_top[t];
@@ -382,46 +484,28 @@ __global__ void __launch_bounds__(kBlock) k_fct_lo_adf(MeshDev m, TrBatch<TB> b,
     }
     if (!valid) return;
 
-    double losum[TB], pp[TB], pm[TB], tn[TB], tabn[TB];
+    // ---- phase B: ordered accumulation -----------------------------------------------------------
+    double losum[TB], pp[TB], pm[TB];
     const bool has_below = nz0 + 1 < L;
 #pragma unroll
     for (int t = 0; t < TB; ++t) {
-        const double flo_bot = has_below ? sm[(2 * t) * blockDim.x + threadIdx.x + 1] : 0.0;
-        const double adfv_bot = has_below ? sm[(2 * t + 1) * blockDim.x + threadIdx.x + 1] : 0.0;
+        const double flo_bot = has_below ? s_vert[(2 * t) * nthr + threadIdx.x + 1] : 0.0;
+        const double adfv_bot = has_below ? s_vert[(2 * t + 1) * nthr + threadIdx.x + 1] : 0.0;
         flo_top[t] = flo_top[t] - flo_bot;                                             // fv(nz)-fv(nz+1)
         pp[t] = 0.0 + (dmax(0.0, adfv_top[t]) + dmax(0.0, -adfv_bot));                 // fct :291
         pm[t] = 0.0 + (dmin(0.0, adfv_top[t]) + dmin(0.0, -adfv_bot));                 // fct :292
         losum[t] = 0.0;
-        tn[t] = b.ttf[t][oL];
-        tabn[t] = b.ttfAB[t][oL];
     }
-    const int nb_n = (HOR == HOR_MUSCL) ? m.nboundary_lay[n] : 0;
-    const int k1 = m.ne_ptr[n + 1];
-    for (int k = m.ne_ptr[n]; k < k1; ++k) {
-        const int4 ent = m.ne_ent[k];
-        const int lo = ent.z & 0xff, hi = (ent.z >> 8) & 0xff;
+    const int s1 = s_off[g + 1];
+    for (int s = s_off[g]; s < s1; ++s) {
+        const int z = __ldg(&m.ne_ent[s_slot[s].y]).z;
+        const int lo = z & 0xff, hi = (z >> 8) & 0xff;
         if (nz < lo || nz > hi) continue;
-        const int e = ent.x, mo = ent.y;
-        const bool second = (ent.z >> 16) & 1, writer = (ent.z >> 17) & 1;
-        const size_t oe = (size_t)e * L + nz0, om = (size_t)mo * L + nz0;
-        const double q = m.Q[oe];
-        const double aq = fabs(q), qp = q + aq, qm = q - aq;
-        double2 ec = make_double2(0.0, 0.0);
-        double clo_n = 1.0, clo_m = 1.0;
-        if (HOR != HOR_UPW1) ec = m.edge_c[e];
-        if (HOR == HOR_MUSCL) {
-            clo_n = (nb_n - nz >= 0) ? 1.0 : 0.0;                 // oce_adv_tra_hor.F90:411-412
-            clo_m = (m.nboundary_lay[mo] - nz >= 0) ? 1.0 : 0.0;
-        }
+        const bool second = (z >> 16) & 1;
+        const double* f = s_flux + (size_t)s * TB * 2 * L + nz0;
 #pragma unroll
         for (int t = 0; t < TB; ++t) {
-            const double tm = b.ttf[t][om], tabm = b.ttfAB[t][om];
-            const double t1 = second ? tm : tn[t], t2 = second ? tn[t] : tm;
-            const double a1 = second ? tabm : tabn[t], a2 = second ? tabn[t] : tabm;
-            const double flo = hor_lo(t1, t2, qp, qm);                                  // driver :115
-            const double* g = (HOR != HOR_UPW1) ? (b.grad[t] + oe * 4) : nullptr;
-            const double adf = hor_ho<HOR>(a1, a2, q, qp, qm, ec, g, b.ph[t], second ? clo_m : clo_n,
-                                           second ? clo_n : clo_m, flo);                // driver :343-354
+            const double flo = f[(2 * t) * L], adf = f[(2 * t + 1) * L];
             if (!second) {
                 losum[t] = losum[t] + flo;                                              // driver :175
                 pp[t] = pp[t] + dmax(0.0, adf);                                         // fct :342
@@ -431,13 +515,14 @@ __global__ void __launch_bounds__(kBlock) k_fct_lo_adf(MeshDev m, TrBatch<TB> b,
                 pp[t] = pp[t] + dmax(0.0, -adf);                                        // fct :360
                 pm[t] = pm[t] + dmin(0.0, -adf);                                        // fct :364
             }
-            if (writer) b.adf_h[t][oe] = adf;
         }
     }
     const double av = m.areasvol[cN + nz0], hn = m.hnode[oL], hnn = m.hnode_new[oL];
+    const double r_av = 1.0 / av, r_hnn = 1.0 / hnn;
 #pragma unroll
     for (int t = 0; t < TB; ++t) {
-        b.lo[t][oL] = (tn[t] * hn + (losum[t] + flo_top[t]) * dt / av) / hnn;           // driver :249
+        const double num = b.ttf[t][oL] * hn + div_rcp((losum[t] + flo_top[t]) * dt, av, r_av);
+        b.lo[t][oL] = div_rcp(num, hnn, r_hnn);                                         // driver :249
         b.plus[t][oL] = pp[t];
         b.minus[t][oL] = pm[t];
     }
@@ -534,16 +619,20 @@ __global__ void __launch_bounds__(kBlock) k_fct_bounds(MeshDev m, TrBatch<TB> b,
             tmin[t] = padded ? 1.0e3 : CUDART_INF;
         }
         const int k1 = m.cl_ptr[n + 1];
+        // branch-free body (an out-of-range entry is loaded and discarded) so that the unrolled
+        // iterations issue their loads together
+#pragma unroll 4
         for (int k = m.cl_ptr[n]; k < k1; ++k) {
-            const int2 ent = m.cl_ent[k];
+            const int2 ent = __ldg(&m.cl_ent[k]);
             const int lo = ent.y & 0xff, hi = (ent.y >> 8) & 0xff;
-            if (nz < lo || nz > hi) continue;
+            const bool inr = nz >= lo && nz <= hi;
             const size_t o = (size_t)ent.x * L + nz0;
 #pragma unroll
             for (int t = 0; t < TB; ++t) {
-                const double a = b.lo[t][o], c = b.ttf[t][o];
-                tmax[t] = dmax(tmax[t], dmax(a, c));          // a1 :129, a2 :166, a3 :209
-                tmin[t] = dmin(tmin[t], dmin(a, c));
+                const double a = __ldg(&b.lo[t][o]), c = __ldg(&b.ttf[t][o]);
+                const double hi2 = dmax(a, c), lo2 = dmin(a, c);
+                tmax[t] = (inr && hi2 > tmax[t]) ? hi2 : tmax[t];   // a1 :129, a2 :166, a3 :209
+                tmin[t] = (inr && lo2 < tmin[t]) ? lo2 : tmin[t];
             }
         }
 #pragma unroll
@@ -556,6 +645,7 @@ __global__ void __launch_bounds__(kBlock) k_fct_bounds(MeshDev m, TrBatch<TB> b,
     if (!valid) return;
     const size_t oL = (size_t)n * L + nz0;
     const double av = m.areasvol[(size_t)n * nl + nz0], hnn = m.hnode_new[oL];
+    const double r_av = 1.0 / av, r_hnn = 1.0 / hnn;
     const bool edge_layer = (nz == tc.nzmin) || (nz == tc.nzmax - 1);   // :233-234, :245-247
 #pragma unroll
     for (int t = 0; t < TB; ++t) {
@@ -568,9 +658,9 @@ __global__ void __launch_bounds__(kBlock) k_fct_bounds(MeshDev m, TrBatch<TB> b,
         }
         const double lo = b.lo[t][oL];
         const double inc_max = vmax - lo, inc_min = vmin - lo;
-        double flux = b.plus[t][oL] * dt / av / hnn + 1e-16;             // b2 :399
+        double flux = div_rcp(div_rcp(b.plus[t][oL] * dt, av, r_av), hnn, r_hnn) + 1e-16;   // b2 :399
         b.plus[t][oL] = dmin(1.0, inc_max / flux);
-        flux = b.minus[t][oL] * dt / av / hnn - 1e-16;                   // :401
+        flux = div_rcp(div_rcp(b.minus[t][oL] * dt, av, r_av), hnn, r_hnn) - 1e-16;         // :401
         b.minus[t][oL] = dmin(1.0, inc_min / flux);
     }
 }
@@ -612,6 +702,7 @@ __global__ void __launch_bounds__(kBlock) k_fct_update(MeshDev m, TrBatch<TB> b,
     __syncthreads();
     if (!valid) return;
     const double av = m.areasvol[cN + nz0];
+    const double r_av = 1.0 / av;
     const bool has_below = nz0 + 1 < L;
     double dh[TB];
 #pragma unroll
@@ -623,26 +714,35 @@ __global__ void __launch_bounds__(kBlock) k_fct_update(MeshDev m, TrBatch<TB> b,
             const double fv_bot = has_below ? sm[t * blockDim.x + threadIdx.x + 1] : 0.0;
             double dv = b.dttf_v[t][oL];
             dv = dv - b.ttf[t][oL] * hn + b.lo[t][oL] * hnn;              // driver :535
-            dv = dv + (fv_top[t] - fv_bot) * dt / av;                     // driver :556
+            dv = dv + div_rcp((fv_top[t] - fv_bot) * dt, av, r_av);       // driver :556
             b.dttf_v[t][oL] = dv;
         }
     }
     const int k1 = m.ne_ptr[n + 1];
+    double pn[TB], mn[TB];
+#pragma unroll
+    for (int t = 0; t < TB; ++t) { pn[t] = __ldg(&b.plus[t][oL]); mn[t] = __ldg(&b.minus[t][oL]); }
+    // branch-free body: all four factors are loaded whatever the sign of the flux, out-of-range
+    // entries are loaded and discarded, so the unrolled iterations issue their loads together
+#pragma unroll 3
     for (int k = m.ne_ptr[n]; k < k1; ++k) {
-        const int4 ent = m.ne_ent[k];
+        const int4 ent = __ldg(&m.ne_ent[k]);
         const int lo = ent.z & 0xff, hi = (ent.z >> 8) & 0xff;
-        if (nz < lo || nz > hi) continue;
+        const bool inr = nz >= lo && nz <= hi;
         const bool second = (ent.z >> 16) & 1;
         const size_t oe = (size_t)ent.x * L + nz0, om = (size_t)ent.y * L + nz0;
-        const size_t o1 = second ? om : oL, o2 = second ? oL : om;       // edges(1,e), edges(2,e)
 #pragma unroll
         for (int t = 0; t < TB; ++t) {
-            const double f = b.adf_h[t][oe];
+            const double f = __ldg(&b.adf_h[t][oe]);
+            const double pmo = __ldg(&b.plus[t][om]), mmo = __ldg(&b.minus[t][om]);
+            const double p1 = second ? pmo : pn[t], m1 = second ? mmo : mn[t];   // factors at edges(1,e)
+            const double p2 = second ? pn[t] : pmo, m2 = second ? mn[t] : mmo;   // factors at edges(2,e)
             double ae = 1.0;
-            if (f >= 0.0) { ae = dmin(ae, b.plus[t][o1]); ae = dmin(ae, b.minus[t][o2]); }   // fct :489-491
-            else { ae = dmin(ae, b.minus[t][o1]); ae = dmin(ae, b.plus[t][o2]); }            // :493-494
-            const double term = ae * f * dt / av;                         // fct :497, driver :607,:620
-            dh[t] = second ? dh[t] - term : dh[t] + term;
+            if (f >= 0.0) { ae = dmin(ae, p1); ae = dmin(ae, m2); }       // fct :489-491
+            else { ae = dmin(ae, m1); ae = dmin(ae, p2); }                // :493-494
+            const double term = div_rcp(ae * f * dt, av, r_av);           // fct :497, driver :607,:620
+            const double nd = second ? dh[t] - term : dh[t] + term;
+            dh[t] = inr ? nd : dh[t];
         }
     }
 #pragma unroll
@@ -689,6 +789,7 @@ __global__ void __launch_bounds__(kBlock) k_nofct(MeshDev m, TrBatch<TB> b, Node
     }
     if (!valid) return;
     const double av = m.areasvol[cN + nz0];
+    const double r_av = 1.0 / av;
     const bool has_below = nz0 + 1 < L;
     double dh[TB], tabn[TB];
 #pragma unroll
@@ -697,7 +798,7 @@ __global__ void __launch_bounds__(kBlock) k_nofct(MeshDev m, TrBatch<TB> b, Node
 #pragma unroll
         for (int t = 0; t < TB; ++t) {
             const double fv_bot = has_below ? sm[t * blockDim.x + threadIdx.x + 1] : 0.0;
-            b.dttf_v[t][oL] = b.dttf_v[t][oL] + (fv_top[t] - fv_bot) * dt / av;     // driver :556
+            b.dttf_v[t][oL] = b.dttf_v[t][oL] + div_rcp((fv_top[t] - fv_bot) * dt, av, r_av);   // driver :556
         }
     }
     const int nb_n = (HOR == HOR_MUSCL) ? m.nboundary_lay[n] : 0;
@@ -725,7 +826,7 @@ __global__ void __launch_bounds__(kBlock) k_nofct(MeshDev m, TrBatch<TB> b, Node
             const double* g = (HOR != HOR_UPW1) ? (b.grad[t] + oe * 4) : nullptr;
             const double f = hor_ho<HOR>(a1, a2, q, qp, qm, ec, g, b.ph[t], second ? clo_m : clo_n,
                                          second ? clo_n : clo_m, 0.0);
-            const double term = f * dt / av;                                        // driver :607,:620
+            const double term = div_rcp(f * dt, av, r_av);                          // driver :607,:620
             dh[t] = second ? dh[t] - term : dh[t] + term;
             if (writer && owned) b.adf_h[t][oe] = f;
         }
@@ -759,6 +860,30 @@ __global__ void __launch_bounds__(kBlock) k_update_values(MeshDev m, double* __r
     if (nz < lv.x || nz > lv.y - 1) return;
     const double del = 0.0 + dh[idx] + dv[idx];
     values[idx] = values[idx] + del / m.hnode_new[idx];
+}
+
+// self-test of div_rcp against the IEEE division: returns the number of mismatching results over
+// `count` pseudo-random operand pairs (mode 0: b = 6, 1: b = 3, 2: random b in [1e-3, 1e13])
+__global__ void k_selftest_div(unsigned long long count, unsigned long long seed, int mode, unsigned long long* bad)
+{
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long nbad = 0;
+    for (; i < count; i += stride) {
+        unsigned long long z = (i + seed) * 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+        unsigned long long z2 = (z + 0x632BE59BD9B4E019ull) * 0xD6E8FEB86659FD93ull; z2 ^= z2 >> 32;
+        // x: random significand, exponent in [-40, 40], random sign
+        const int ex = (int)((z >> 52) % 81) - 40;
+        double x = ldexp(1.0 + (double)(z & 0xFFFFFFFFFFFFFull) * 0x1p-52, ex);
+        if (z2 & 1) x = -x;
+        double b = 6.0;
+        if (mode == 1) b = 3.0;
+        if (mode == 2) b = ldexp(1.0 + (double)((z2 >> 1) & 0xFFFFFFFFFFFFFull) * 0x1p-52, (int)((z2 >> 54) % 54) - 10);
+        const double y = (mode == 0) ? kInv6 : (mode == 1) ? kInv3 : 1.0 / b;
+        if (div_rcp(x, b, y) != x / b) ++nbad;
+    }
+    if (nbad) atomicAdd(bad, nbad);
 }
 
 }  // namespace adv

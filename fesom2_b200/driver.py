@@ -64,7 +64,7 @@ EXPORTS = ["adv_ctx_create", "adv_ctx_destroy", "adv_last_error", "adv_comm_uniq
            "adv_ctx_comm_init", "adv_ctx_set_state", "adv_do_oce_adv_tra", "adv_do_oce_adv_tra_async",
            "adv_ctx_synchronize", "adv_exchange_nod", "adv_update_values", "adv_ctx_get_work",
            "adv_ctx_launch_count", "adv_ctx_stream", "adv_ctx_last_elapsed_ms",
-           "adv_ctx_set_profiling", "adv_ctx_phase_ms"]
+           "adv_ctx_set_profiling", "adv_ctx_phase_ms", "adv_selftest_div"]
 
 _lib = None
 
@@ -103,6 +103,15 @@ def load_library():
 def _check(rc: int):
     if rc != 0:
         raise AdvError(rc, load_library().adv_last_error().decode())
+
+
+def selftest_div(count: int, seed: int, mode: int) -> int:
+    """number of mismatches between the library's reciprocal-based division and IEEE `/`"""
+    L = load_library()
+    bad = C.c_uint64(0)
+    L.adv_selftest_div.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
+    _check(L.adv_selftest_div(int(count), int(seed), int(mode), C.byref(bad)))
+    return int(bad.value)
 
 
 def unique_id() -> bytes:

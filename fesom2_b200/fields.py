@@ -332,3 +332,15 @@ def scatter_to_local(g: Mesh, loc: Mesh, st: OceanState, trs: List[TracerFields]
                         tra_adv_ver=t.tra_adv_ver, tra_adv_lim=t.tra_adv_lim, tra_adv_ph=t.tra_adv_ph,
                         tra_adv_pv=t.tra_adv_pv) for t in trs]
     return lst, ltr
+
+
+def make_tracers_kind(m: Mesh, kind: int, device, up_dn_tri: np.ndarray, hor="MFCT", ver="QR4C", lim="FCT",
+                      ph: float = 0.0, pv: float = 1.0) -> List[TracerFields]:
+    """One tracer of the given kind (0 = T, 1 = S, k>=2 = T*(1+0.01k)+k) as a one-element list."""
+    v, vo = make_tracer_values(m, device, kind=kind)
+    vab = ab2(v, vo).contiguous()
+    tr_xy = tracer_gradient_elements(m, v, device)
+    g = fill_up_dn_grad(m, tr_xy, up_dn_tri, device)
+    del tr_xy, vo
+    return [TracerFields(values=v, valuesAB=vab, edge_up_dn_grad=g, tra_adv_hor=hor, tra_adv_ver=ver,
+                         tra_adv_lim=lim, tra_adv_ph=ph, tra_adv_pv=pv)]

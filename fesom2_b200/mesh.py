@@ -251,10 +251,16 @@ def derive_geometry(m: Mesh, need_nod_in_elem_for_all: bool = True) -> Mesh:
     area = np.zeros((Nh, nl))
     third = area_rad / 3.0
     flat_nodes = en.ravel()                                   # element-major = nod_in_elem order
-    for nz in range(1, nl):                                   # 1-based layer index
-        act = (m.ulevels <= nz) & (nz <= m.nlevels - 1)
-        w = np.repeat(np.where(act, third, 0.0), 3)
-        area[:, nz - 1] = np.bincount(flat_nodes, weights=w, minlength=Nh)
+    if (m.ulevels == 1).all():
+        # no cavity: bin every element at its deepest layer, then sum bottom-up (additions only)
+        deepest = np.repeat(m.nlevels.astype(np.int64) - 2, 3)              # 0-based layer index
+        c = np.bincount(flat_nodes * nl + deepest, weights=np.repeat(third, 3), minlength=Nh * nl)
+        area = np.cumsum(c.reshape(Nh, nl)[:, ::-1], axis=1)[:, ::-1].copy()
+    else:
+        for nz in range(1, nl):                               # 1-based layer index
+            act = (m.ulevels <= nz) & (nz <= m.nlevels - 1)
+            w = np.repeat(np.where(act, third, 0.0), 3)
+            area[:, nz - 1] = np.bincount(flat_nodes, weights=w, minlength=Nh)
     area *= R_EARTH * R_EARTH
     m.area = area
     m.areasvol = np.zeros_like(area)

@@ -155,6 +155,11 @@ int adv_ctx_last_elapsed_ms(adv_ctx_t *ctx, float *ms);
 int adv_ctx_set_profiling(adv_ctx_t *ctx, int on);
 int adv_ctx_phase_ms(adv_ctx_t *ctx, float ms[8]);
 
+/* Self-test of the library's exact reciprocal-based division against the IEEE `/` on `count`
+ * pseudo-random operand pairs (mode 0: divisor 6, 1: divisor 3, 2: random divisor); writes the
+ * number of results that differ (must be 0). */
+int adv_selftest_div(uint64_t count, uint64_t seed, int mode, uint64_t *mismatches);
+
 #ifdef __cplusplus
 }
 #endif
