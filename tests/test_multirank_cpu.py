@@ -1,0 +1,87 @@
+"""CPU tests of the N>1 path: partition lists against the reference's checked-in dist_N files,
+world_size-2 gloo exchange over those lists, and 1-rank vs N-rank identity of the oracle."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+from fesom2_b200 import fields as F
+from fesom2_b200 import mesh as M
+
+REF_MESHES = "/root/reference/test/meshes"
+
+
+def _spawn(world, backend, mesh_name, nsteps=1):
+    import mgpu_worker
+    out = tempfile.mkdtemp()
+    port = 29500 + (os.getpid() % 400)
+    mp.spawn(mgpu_worker.worker, args=(world, backend, mesh_name, port, out, nsteps), nprocs=world, join=True)
+    return [np.load(os.path.join(out, f"rank{r}.npy"), allow_pickle=True)[0] for r in range(world)]
+
+
+@pytest.mark.parametrize("mesh_name", ["pi", "synth"])
+def test_gloo_world2_halo_exchange(mesh_name):
+    """two processes, gloo: the send/recv lists deliver every owner's column into the halo tail"""
+    res = _spawn(2, "gloo", mesh_name)
+    assert all(r["halo_ok"] for r in res)
+    owned = np.concatenate([r["owned"] for r in res])
+    assert len(np.unique(owned)) == len(owned)          # every node has exactly one owner
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_MESHES), reason="reference fixtures not mounted")
+@pytest.mark.parametrize("name,npes", [("pi", 2), ("pi", 8), ("soufflet", 2), ("soufflet", 8)])
+def test_localize_reproduces_reference_dist_files(name, npes):
+    """mesh.localize == the reference's own partition bookkeeping (test/meshes/*/dist_N)"""
+    g = M.read_fesom_mesh(os.path.join(REF_MESHES, name), cyclic_length_deg=4.5 if name == "soufflet" else 360.0)
+    d = M.read_dist(os.path.join(REF_MESHES, name), npes)
+    for r in range(npes):
+        m = M.localize(g, d["part"], r)
+        info = d["ranks"][r]
+        c = info["com_nod2D"]
+        assert m.N == info["myDim_nod2D"] and m.eDim_nod2D == info["eDim_nod2D"]
+        assert np.array_equal(m.myList_nod2D, info["myList_nod2D"])
+        assert np.array_equal(m.myList_elem2D, info["myList_elem2D"][:m.T])
+        assert np.array_equal(m.myList_edge2D, info["myList_edge2D"][:m.E])
+        for a in ("rPE", "rptr", "rlist", "sPE", "sptr", "slist"):
+            assert np.array_equal(getattr(m.com_nod2D, a), getattr(c, a)), a
+
+
+def test_npz_fixture_matches_reference_mesh():
+    if not os.path.isdir(REF_MESHES):
+        pytest.skip("reference fixtures not mounted")
+    here = os.path.dirname(os.path.abspath(__file__))
+    a = M.load_npz_mesh(os.path.join(here, "golden", "mesh_pi.npz"))
+    b = M.read_fesom_mesh(os.path.join(REF_MESHES, "pi"))
+    assert np.array_equal(a.edges, b.edges) and np.array_equal(a.elem2D_nodes, b.elem2D_nodes)
+    assert np.allclose(a.area, b.area, rtol=1e-9) and np.array_equal(a.nlevels, b.nlevels)
+    assert np.array_equal(a.parts[2], M.read_dist(os.path.join(REF_MESHES, "pi"), 2)["part"])
+
+
+@pytest.mark.parametrize("npes", [2, 8])
+def test_oracle_1rank_vs_nrank_identical_on_owned_nodes(pi_mesh, npes):
+    """with the reference's numbering every owned node sees the same sequence of
+    addends on 1 or N ranks, so the results are bit-identical"""
+    from oracle import oracle_py as O
+    g = pi_mesh
+    st = F.make_state(g, "cpu")
+    dt = F.cfl_dt(g, st, 0.3)
+    trs = F.make_tracers(g, 2, "cpu", hor="MUSCL", ver="QR4C", lim="FCT")
+    nbg = M.nboundary_lay(g)
+    one = O.OracleRank(g, st, trs, nbg)
+    O.run([one], dt, 3, 1)
+    ranks = []
+    for r in range(npes):
+        loc = M.localize(g, g.parts[npes], r)
+        lst, ltr = F.scatter_to_local(g, loc, st, trs)
+        ranks.append(O.OracleRank(loc, lst, ltr, nbg[loc.myList_nod2D - 1]))
+    O.run(ranks, dt, 3, 1)
+    for rk in ranks:
+        loc = rk.mesh_py
+        own = loc.myList_nod2D[:loc.N] - 1
+        alln = loc.myList_nod2D - 1
+        for k in range(2):
+            assert np.array_equal(rk.dttf_v[k][:loc.N], one.dttf_v[k][own])
+            assert np.array_equal(rk.dttf_h[k][:loc.N], one.dttf_h[k][own])
+            assert np.array_equal(rk.values[k], one.values[k][alln])     # halo refreshed by the exchange
