@@ -269,7 +269,7 @@ def main():
     alg = algorithmic_bytes(loc.L, loc.N, loc.E, loc.T, ntr)
     roof = {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
             "algorithmic_bytes_per_step_per_gpu": alg,
-            "kernel": "whole step = k_edge_volflux + k_fct_lo_adf + k_fct_bounds + k_fct_update (section-8d bytes are per step)"}
+            "kernel": "whole step = k_edge_flux + k_node_lo + k_fct_bounds + k_fct_update (section-8d bytes are per step)"}
     if world == 1:
         ctx.set_profiling(True)
         ph = np.zeros(4)
@@ -282,7 +282,7 @@ def main():
         ph /= reps
         ksum = float(ph[0] + ph[1] + ph[2] + ph[3])
         roof["achieved"] = alg / (ksum * 1e-3) / 1e9
-        roof["kernel_ms"] = {"k_edge_volflux": float(ph[0]), "k_fct_lo_adf": float(ph[1]),
+        roof["kernel_ms"] = {"k_edge_flux": float(ph[0]), "k_node_lo": float(ph[1]),
                              "k_fct_bounds": float(ph[2]), "k_fct_update": float(ph[3])}
     else:
         # per-rank algorithmic bytes over the max-over-ranks step time (includes exposed halo waits)

@@ -16,10 +16,11 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
               "-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared"]
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
+def build_library(force: bool = False, verbose: bool = False, out: str = OUT, defines=()) -> str:
+    """``out``/``defines`` build tuning variants next to the product library (experiments only)."""
     newest = max(os.path.getmtime(p) for p in DEPS)
-    if force or not os.path.exists(OUT) or os.path.getmtime(OUT) < newest:
+    if force or not os.path.exists(out) or os.path.getmtime(out) < newest:
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC, "-ldl"]
+        cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, SRC, "-ldl"]
         subprocess.check_call(cmd)
-    return OUT
+    return out

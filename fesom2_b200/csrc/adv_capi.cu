@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -71,6 +72,10 @@ template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;              // owns device memory: never copied
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
     cudaError_t alloc(size_t count, bool zero = true)
     {
         release();
@@ -91,11 +96,18 @@ struct DevBuf {
     ~DevBuf() { release(); }
 };
 
-struct Slot {  // per-tracer work arrays (t_tracer_work, allocated by oce_adv_tra_fct_init) + host staging
-    DevBuf<double> lo, plus, minus, adf_h, adf_v;
-    DevBuf<double> ttf, ttfAB, grad, dh, dv;  // only used with ADV_HOST pointers
-    DevBuf<double> sendbuf;                   // 2 x (send columns x L)
+struct Slot {  // per-tracer host staging, only used with ADV_HOST pointers
+    DevBuf<double> ttf, ttfAB, grad, dh, dv;
 };
+
+// work arrays of one chunk of <= 2 tracers (t_tracer_work, allocated by oce_adv_tra_fct_init in the
+// reference), tracer-interleaved, always sized for 2 tracers
+struct ChunkBuf {
+    DevBuf<double> lo, pm, adf_h, adf_v;
+    DevBuf<double> sendbuf;                   // send columns x L x 4
+};
+
+struct TrLoc { int chunk = -1, pos = 0, tb = 1; };  // where tracer i of the last call lives
 
 struct Peer { int pe; int off, cnt; };  // segment of slist / halo tail, in columns
 
@@ -107,15 +119,19 @@ struct adv_ctx {
     MeshDev m{};
     int mype = 0, npes = 1;
     // topology
-    DevBuf<int> ne_ptr, cl_ptr, nboundary_lay, list_S, list_I, list_SH, slist;
+    DevBuf<int> ne_ptr, nboundary_lay, list_S, list_I, list_SH, slist;
     DevBuf<int4> ne_ent;
-    DevBuf<int2> cl_ent, edge_el;
+    DevBuf<int2> edge_el;
+    DevBuf<int4> edge_meta;
     DevBuf<uchar4> node_lev, edge_lev;
+    DevBuf<uint2> node_rec;
+    DevBuf<int4> ne_ell;
     DevBuf<double4> edge_cross;
     DevBuf<double2> edge_c;
     DevBuf<double> area, areasvol, Q;
     int nS = 0, nI = 0, nSH = 0;
-    int ms_all = 0, ms_allh = 0, ms_S = 0, ms_I = 0, ms_SH = 0;  // max (column, edge) slots per CTA of each node range
+    int pf_dist = 0;                          // L2 prefetch distance in CTAs (ADV_PF; 0 = off)
+    int g_lo = 6, g_k2 = 3, g_k3 = 3;         // gather batch sizes (tunable: ADV_G_LO / ADV_G_K2 / ADV_G_K3)
     std::vector<Peer> rpeers, speers;
     int send_cols = 0;
     // state (ADV_HOST staging)
@@ -123,6 +139,8 @@ struct adv_ctx {
     bool state_set = false, q_valid = false;
     DevBuf<double> impl_cp, impl_tp;
     std::vector<Slot> slots;
+    std::vector<std::unique_ptr<ChunkBuf>> cbufs;
+    std::vector<TrLoc> trloc;
     DevBuf<double> xbuf;  // adv_exchange_nod pack buffer
     cudaStream_t s_comp = nullptr, s_comm = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
@@ -162,6 +180,7 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
 
     // ---- host-side gather lists ----------------------------------------------------------------
     std::vector<int2> edge_el(E);
+    std::vector<int4> edge_meta(E);
     std::vector<uchar4> edge_lev(E);
     std::vector<double4> edge_cross(E);
     std::vector<double2> edge_c(E);
@@ -182,6 +201,7 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
         }
         if (nu1 < 1 || nl1 > L || nl2 > L || nu1 > nl1) return fail(ADV_EINVAL, "element levels out of range");
         edge_el[e] = make_int2(el1, el2);
+        edge_meta[e] = make_int4(n1, n2, el1, el2);
         edge_lev[e] = make_uchar4((unsigned char)nu1, (unsigned char)nl1, (unsigned char)nu2, (unsigned char)nl2);
         edge_cross[e] = make_double4(d->edge_cross_dxdy[4 * e], d->edge_cross_dxdy[4 * e + 1],
                                      d->edge_cross_dxdy[4 * e + 2], d->edge_cross_dxdy[4 * e + 3]);
@@ -199,27 +219,32 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
             // scatter range of oce_adv_tra_driver.F90:154-156: [min(nu1, nu2>0), max(nl1, nl2)]
             const int lo = lv.z > 0 ? std::min<int>(lv.x, lv.z) : lv.x;
             const int hi = std::max<int>(lv.y, lv.w);
-            const bool w1 = n1 < N;   // designated writer of adf_h(:,e): edges(1,e) if owned, else edges(2,e)
+            const bool w1 = n1 < N;   // designated writer of adf_h(:,e) in k_nofct: edges(1,e) if owned, else edges(2,e)
             ne_ent[fill[n1]++] = make_int4(e, n2, lo | (hi << 8) | (0 << 16) | ((w1 ? 1 : 0) << 17), 0);
             ne_ent[fill[n2]++] = make_int4(e, n1, lo | (hi << 8) | (1 << 16) | ((w1 ? 0 : 1) << 17), 0);
         }
     }
     // FCT clusters (oce_adv_tra_fct.F90:148-215 collapsed): for owned node n the distinct nodes of
-    // its elements, each with the union of the level ranges of the elements that contain it.
+    // its elements, each with the union of the level ranges of the elements that contain it.  On a
+    // triangulation that is the node itself plus its edge neighbours with the edge's scatter range,
+    // so the kernels reuse the edge slots; the equivalence is verified here for every owned node.
     std::vector<uchar4> node_lev(Nh);
-    std::vector<int> cl_ptr(N + 1, 0);
-    std::vector<int2> cl_ent;
-    cl_ent.reserve((size_t)N * 8);
+    std::vector<uint2> node_rec(Nh);
+    int ell_w = 1;
+    for (int n = 0; n < Nh; ++n) ell_w = std::max(ell_w, ne_ptr[n + 1] - ne_ptr[n]);
+    if (ell_w > 255) return fail(ADV_EINVAL, "node degree > 255");
+    std::vector<int4> ne_ell((size_t)Nh * ell_w, make_int4(0, 0, 0xff, 0));   // padding: lo = 255 > hi = 0
+    for (int n = 0; n < Nh; ++n)
+        for (int k = ne_ptr[n]; k < ne_ptr[n + 1]; ++k) ne_ell[(size_t)n * ell_w + (k - ne_ptr[n])] = ne_ent[k];
     const int ld = d->nod_in_elem2D_ld;
     struct Iv { int node, lo, hi; };
-    std::vector<Iv> iv;
+    std::vector<Iv> iv, cl;
     for (int n = 0; n < Nh; ++n) {
-        int pad_lo = 0, pad_hi = 255;
+        int pad_lo = 0, pad_hi = 255, self_lo = 1, self_hi = 0;
         if (n < N) {
-            iv.clear();
+            iv.clear(); cl.clear();
             const int num = d->nod_in_elem2D_num[n];
             if (num < 1 || num > ld) return fail(ADV_EINVAL, "nod_in_elem2D_num out of range");
-            pad_lo = 0; pad_hi = 255;
             for (int k = 0; k < num; ++k) {
                 const int el = d->nod_in_elem2D[(size_t)n * ld + k] - 1;
                 if (el < 0 || el >= T) return fail(ADV_EINVAL, "nod_in_elem2D out of range");
@@ -232,33 +257,41 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
                 Iv cur = iv[i];
                 size_t j = i + 1;
                 for (; j < iv.size() && iv[j].node == cur.node && iv[j].lo <= cur.hi + 1; ++j) cur.hi = std::max(cur.hi, iv[j].hi);
-                cl_ent.push_back(make_int2(cur.node, cur.lo | (cur.hi << 8)));
+                cl.push_back(cur);
                 i = j;
             }
-            cl_ptr[n + 1] = (int)cl_ent.size();
+            // compare with {self} + edge slots
+            std::vector<Iv> ref;
+            for (int k = ne_ptr[n]; k < ne_ptr[n + 1]; ++k) ref.push_back({ne_ent[k].y, ne_ent[k].z & 0xff, (ne_ent[k].z >> 8) & 0xff});
+            std::sort(ref.begin(), ref.end(), [](const Iv& a, const Iv& b) { return a.node < b.node; });
+            bool ok = cl.size() == ref.size() + 1;
+            self_lo = 0; self_hi = -1;
+            for (size_t i = 0, j = 0; ok && i < cl.size(); ++i) {
+                if (cl[i].node == n) { self_lo = cl[i].lo; self_hi = cl[i].hi; continue; }
+                ok = j < ref.size() && ref[j].node == cl[i].node && ref[j].lo == cl[i].lo && ref[j].hi == cl[i].hi;
+                ++j;
+            }
+            if (!ok || self_hi < self_lo)
+                return fail(ADV_EINVAL, "node " + std::to_string(n + 1) + ": FCT cluster is not {node} + edge neighbours "
+                                        "(non-triangular mesh or non-contiguous element level ranges)");
         }
+        node_rec[n] = make_uint2((unsigned)d->ulevels_nod2D[n] | ((unsigned)d->nlevels_nod2D[n] << 8) | ((unsigned)pad_lo << 16) | ((unsigned)pad_hi << 24),
+                                 (unsigned)self_lo | ((unsigned)self_hi << 8) | ((unsigned)(ne_ptr[n + 1] - ne_ptr[n]) << 16));
         node_lev[n] = make_uchar4((unsigned char)d->ulevels_nod2D[n], (unsigned char)d->nlevels_nod2D[n],
                                   (unsigned char)pad_lo, (unsigned char)pad_hi);
         if (d->nlevels_nod2D[n] > nl || d->ulevels_nod2D[n] < 1) return fail(ADV_EINVAL, "node levels out of range");
     }
 
-    const int cpb0 = kBlock / L;
-    auto max_slots = [&](const int* list, int count) {
-        int best = 0;
-        for (int i = 0; i < count; i += cpb0) {
-            int sum = 0;
-            for (int j = i; j < std::min(count, i + cpb0); ++j) { const int n = list ? list[j] : j; sum += ne_ptr[n + 1] - ne_ptr[n]; }
-            best = std::max(best, sum);
-        }
-        return best;
-    };
     adv_ctx* c = new adv_ctx();
     c->device = device; c->max_tr = max_tracers; c->mype = d->mype; c->npes = std::max(1, d->npes);
-    c->ms_all = max_slots(nullptr, N); c->ms_allh = max_slots(nullptr, Nh);
+    if (const char* v = getenv("ADV_PF")) c->pf_dist = std::max(0, atoi(v));
+    if (const char* v = getenv("ADV_G_LO")) c->g_lo = atoi(v) == 3 ? 3 : 6;
+    if (const char* v = getenv("ADV_G_K2")) c->g_k2 = atoi(v) == 6 ? 6 : 3;
+    if (const char* v = getenv("ADV_G_K3")) c->g_k3 = atoi(v) == 6 ? 6 : 3;
 #define CUF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { delete c; return fail(ADV_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
     CUF(c->ne_ptr.upload(ne_ptr)); CUF(c->ne_ent.upload(ne_ent));
-    CUF(c->cl_ptr.upload(cl_ptr)); CUF(c->cl_ent.upload(cl_ent));
-    CUF(c->node_lev.upload(node_lev)); CUF(c->edge_el.upload(edge_el)); CUF(c->edge_lev.upload(edge_lev));
+    CUF(c->node_lev.upload(node_lev)); CUF(c->node_rec.upload(node_rec)); CUF(c->ne_ell.upload(ne_ell));
+    CUF(c->edge_el.upload(edge_el)); CUF(c->edge_meta.upload(edge_meta)); CUF(c->edge_lev.upload(edge_lev));
     CUF(c->edge_cross.upload(edge_cross)); CUF(c->edge_c.upload(edge_c));
     {
         std::vector<int> nb(Nh, L);
@@ -303,15 +336,10 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
         SH = S;
         for (int n = N; n < Nh; ++n) SH.push_back(n);
         c->nS = (int)S.size(); c->nI = (int)I.size(); c->nSH = (int)SH.size();
-        c->ms_S = max_slots(S.data(), c->nS); c->ms_I = max_slots(I.data(), c->nI); c->ms_SH = max_slots(SH.data(), c->nSH);
         CUF(c->list_S.upload(S)); CUF(c->list_I.upload(I)); CUF(c->list_SH.upload(SH)); CUF(c->slist.upload(sl));
     }
     c->slots.resize(max_tracers);
-    for (auto& s : c->slots) {
-        CUF(s.lo.alloc((size_t)L * Nh)); CUF(s.plus.alloc((size_t)L * Nh)); CUF(s.minus.alloc((size_t)L * Nh));
-        CUF(s.adf_h.alloc((size_t)L * E)); CUF(s.adf_v.alloc((size_t)nl * N));
-        if (c->npes > 1) CUF(s.sendbuf.alloc((size_t)2 * c->send_cols * L));
-    }
+    c->trloc.resize(max_tracers);
     CUF(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
     CUF(cudaStreamCreateWithFlags(&c->s_comm, cudaStreamNonBlocking));
     for (cudaEvent_t* ev : {&c->ev_a, &c->ev_b, &c->ev_c, &c->ev_d}) CUF(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
@@ -320,8 +348,12 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
 #undef CUF
     MeshDev& m = c->m;
     m.L = L; m.nl = nl; m.N = N; m.Nh = Nh; m.T = T; m.E = E;
-    m.ne_ptr = c->ne_ptr.p; m.ne_ent = c->ne_ent.p; m.cl_ptr = c->cl_ptr.p; m.cl_ent = c->cl_ent.p;
-    m.node_lev = c->node_lev.p; m.edge_el = c->edge_el.p; m.edge_lev = c->edge_lev.p;
+    m.div_magic = ((1u << 20) + L - 1) / L;
+    for (unsigned t = 0; t < 1024; ++t)
+        if (((t * m.div_magic) >> 20) != t / L) { delete c; return fail(ADV_EINVAL, "internal: division magic"); }
+    m.ne_ptr = c->ne_ptr.p; m.ne_ent = c->ne_ent.p;
+    m.node_lev = c->node_lev.p; m.node_rec = c->node_rec.p; m.ne_ell = c->ne_ell.p; m.ell_w = ell_w;
+    m.edge_meta = c->edge_meta.p; m.edge_el = c->edge_el.p; m.edge_lev = c->edge_lev.p;
     m.edge_cross = c->edge_cross.p; m.edge_c = c->edge_c.p; m.nboundary_lay = c->nboundary_lay.p;
     m.area = c->area.p; m.areasvol = c->areasvol.p; m.Q = c->Q.p;
     *out = c;
@@ -402,84 +434,96 @@ int adv_ctx_set_state(adv_ctx_t* c, const adv_state_desc_t* st, int where)
 namespace {
 
 struct Group { int fct, hor, ver; std::vector<int> idx; };
+struct ChunkSel { int fct, hor, ver, tb; int idx[2]; int buf; };
 
 inline int cols_per_block(int L) { return kBlock / L; }
 inline int nblocks(int count, int cpb) { return (count + cpb - 1) / cpb; }
 
+struct TrPtrs {   // device pointers of the call's tracers
+    std::vector<const double*> ttf, ttfAB, grad;
+    std::vector<double*> dh, dv;
+};
+
 template <int TB>
-TrBatch<TB> make_batch(adv_ctx* c, const std::vector<const double*>& ttf, const std::vector<const double*>& ttfAB,
-                       const std::vector<const double*>& grad, const std::vector<double*>& dh,
-                       const std::vector<double*>& dv, const adv_tracer_desc_t* tr, const int* idx)
+Chunk<TB> make_chunk(adv_ctx* c, const TrPtrs& p, const adv_tracer_desc_t* tr, const ChunkSel& ch)
 {
-    TrBatch<TB> b;
+    Chunk<TB> b;
+    ChunkBuf& cb = *c->cbufs[ch.buf];
     for (int t = 0; t < TB; ++t) {
-        const int i = idx[t];
-        Slot& s = c->slots[i];
-        b.ttf[t] = ttf[i]; b.ttfAB[t] = ttfAB[i]; b.grad[t] = grad[i];
-        b.lo[t] = s.lo.p; b.adf_h[t] = s.adf_h.p; b.adf_v[t] = s.adf_v.p; b.plus[t] = s.plus.p; b.minus[t] = s.minus.p;
-        b.dttf_h[t] = dh[i]; b.dttf_v[t] = dv[i];
+        const int i = ch.idx[t];
+        b.ttf[t] = p.ttf[i]; b.ttfAB[t] = p.ttfAB[i]; b.grad[t] = p.grad[i];
+        b.dttf_h[t] = p.dh[i]; b.dttf_v[t] = p.dv[i];
         b.ph[t] = tr[i].tra_adv_ph; b.pv[t] = tr[i].tra_adv_pv;
     }
+    b.lo = cb.lo.p; b.adf_h = cb.adf_h.p; b.adf_v = cb.adf_v.p; b.pm = cb.pm.p;
     return b;
 }
 
-enum Phase { PH_K1, PH_K2, PH_K3, PH_NOFCT };
-
-template <int HOR, int VER, int TB>
-void launch_hv(adv_ctx* c, Phase ph, const TrBatch<TB>& b, const NodeRange& r, double dt)
-{
-    if (r.count <= 0) return;
-    const int grid = nblocks(r.count, r.cpb);
-    const int nthr = r.cpb * c->m.L;
-    const size_t sm1 = (size_t)TB * nthr * sizeof(double);
-    if (ph == PH_K1) {
-        const size_t smk = k1_smem_bytes<TB>(c->m.L, r.cpb, r.max_slots);
-        static size_t configured = 0;   // per instantiation: opt in to > 48 KB of dynamic shared memory
-        if (smk > configured) {
-            cudaFuncSetAttribute(k_fct_lo_adf<HOR, VER, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smk);
-            configured = smk;
-        }
-        k_fct_lo_adf<HOR, VER, TB><<<grid, nthr, smk, c->s_comp>>>(c->m, b, r, dt);
-    } else k_nofct<HOR, VER, TB><<<grid, nthr, sm1, c->s_comp>>>(c->m, b, r, dt);
-    ++c->launches;
-}
+enum Phase { PH_E1, PH_N1, PH_K2, PH_K3, PH_NOFCT };
 
 template <int TB>
-void launch_phase(adv_ctx* c, Phase ph, int hor, int ver, const TrBatch<TB>& b, const NodeRange& r, double dt)
+int launch_phase(adv_ctx* c, Phase ph, int hor, int ver, bool q_stored, const Chunk<TB>& b, const NodeRange& r, double dt)
 {
-    if (r.count <= 0) return;
-    if (ph == PH_K2 || ph == PH_K3) {
-        const int grid = nblocks(r.count, r.cpb), nthr = r.cpb * c->m.L;
-        if (ph == PH_K2) k_fct_bounds<TB><<<grid, nthr, (size_t)2 * TB * nthr * sizeof(double), c->s_comp>>>(c->m, b, r, dt);
-        else k_fct_update<TB><<<grid, nthr, (size_t)TB * nthr * sizeof(double), c->s_comp>>>(c->m, b, r, dt);
+    const MeshDev& m = c->m;
+    cudaStream_t s = c->s_comp;
+    if (ph == PH_E1) {
+        const int epb = cols_per_block(m.L), grid = nblocks(m.E, epb), nthr = epb * m.L;
+#define E1(H) if (hor == H) { if (q_stored) k_edge_flux<H, TB, 1><<<grid, nthr, 0, s>>>(m, b, epb, c->pf_dist); \
+                              else k_edge_flux<H, TB, 0><<<grid, nthr, 0, s>>>(m, b, epb, c->pf_dist); }
+        E1(HOR_UPW1) E1(HOR_MUSCL) E1(HOR_MFCT)
+#undef E1
         ++c->launches;
-        return;
+        if (cudaError_t e = cudaGetLastError()) return fail(ADV_ECUDA, std::string("launch k_edge_flux: ") + cudaGetErrorString(e));
+        return ADV_OK;
     }
-#define HV(H, V) if (hor == H && ver == V) { launch_hv<H, V, TB>(c, ph, b, r, dt); return; }
-    HV(HOR_UPW1, VER_UPW1) HV(HOR_UPW1, VER_QR4C) HV(HOR_UPW1, VER_PPM) HV(HOR_UPW1, VER_CDIFF)
-    HV(HOR_MUSCL, VER_UPW1) HV(HOR_MUSCL, VER_QR4C) HV(HOR_MUSCL, VER_PPM) HV(HOR_MUSCL, VER_CDIFF)
-    HV(HOR_MFCT, VER_UPW1) HV(HOR_MFCT, VER_QR4C) HV(HOR_MFCT, VER_PPM) HV(HOR_MFCT, VER_CDIFF)
+    if (r.count <= 0) return ADV_OK;
+    const int grid = nblocks(r.count, r.cpb), nthr = r.cpb * m.L;
+    const size_t sm1 = (size_t)TB * nthr * sizeof(double);
+    if (ph == PH_N1) {
+#define N1(V) if (ver == V) { const size_t smn = (size_t)n1_smem_arrays<V, TB>() * nthr * sizeof(double); \
+                              if (c->g_lo == 6) k_node_lo<V, TB, 6><<<grid, nthr, smn, s>>>(m, b, r, dt); \
+                              else k_node_lo<V, TB, 3><<<grid, nthr, smn, s>>>(m, b, r, dt); }
+        N1(VER_UPW1) N1(VER_QR4C) N1(VER_PPM) N1(VER_CDIFF)
+#undef N1
+    } else if (ph == PH_K2) {
+        if (c->g_k2 == 6) k_fct_bounds<TB, 6><<<grid, nthr, 2 * sm1, s>>>(m, b, r, dt);
+        else k_fct_bounds<TB, 3><<<grid, nthr, 2 * sm1, s>>>(m, b, r, dt);
+    } else if (ph == PH_K3) {
+        if (c->g_k3 == 6) k_fct_update<TB, 6><<<grid, nthr, 0, s>>>(m, b, r, dt);
+        else k_fct_update<TB, 3><<<grid, nthr, 0, s>>>(m, b, r, dt);
+    } else {
+#define HV(H, V) if (hor == H && ver == V) k_nofct<H, V, TB><<<grid, nthr, sm1, s>>>(m, b, r, dt);
+        HV(HOR_UPW1, VER_UPW1) HV(HOR_UPW1, VER_QR4C) HV(HOR_UPW1, VER_PPM) HV(HOR_UPW1, VER_CDIFF)
+        HV(HOR_MUSCL, VER_UPW1) HV(HOR_MUSCL, VER_QR4C) HV(HOR_MUSCL, VER_PPM) HV(HOR_MUSCL, VER_CDIFF)
+        HV(HOR_MFCT, VER_UPW1) HV(HOR_MFCT, VER_QR4C) HV(HOR_MFCT, VER_PPM) HV(HOR_MFCT, VER_CDIFF)
 #undef HV
+    }
+    ++c->launches;
+    if (cudaError_t e = cudaGetLastError()) {
+        static const char* names[] = {"k_edge_flux", "k_node_lo", "k_fct_bounds", "k_fct_update", "k_nofct"};
+        return fail(ADV_ECUDA, std::string("launch ") + names[ph] + " (grid " + std::to_string(grid) + ", block " + std::to_string(nthr) +
+                                   ", hor " + std::to_string(hor) + ", ver " + std::to_string(ver) + ", tb " + std::to_string(TB) + "): " + cudaGetErrorString(e));
+    }
+    return ADV_OK;
 }
 
-// one exchange_nod over NCCL for `nf` fields of nlev levels each: pack the send columns per field,
-// then one grouped send/recv per (peer, field); receives land directly in the halo tail.
-int halo_exchange(adv_ctx* c, cudaStream_t s, int nf, double* const* fields, double* const* sendbufs, int nlev)
+// one exchange_nod over NCCL for `nf` fields of nlev[f] doubles per column: pack the send columns
+// per field, then one grouped send/recv per (peer, field); receives land directly in the halo tail.
+int halo_exchange(adv_ctx* c, cudaStream_t s, int nf, double* const* fields, double* const* sendbufs, const int* nlev)
 {
     const int cols = c->send_cols;
     for (int f = 0; f < nf; ++f) {
-        const long long tot = (long long)cols * nlev;
-        if (tot > 0) {
-            k_pack_halo<<<(unsigned)((tot + kBlock - 1) / kBlock), kBlock, 0, s>>>(fields[f], c->slist.p, cols, nlev, sendbufs[f]);
+        if (cols > 0) {
+            k_pack_halo<<<cols, std::min(kBlock, ((nlev[f] + 31) / 32) * 32), 0, s>>>(fields[f], c->slist.p, nlev[f], sendbufs[f]);
             ++c->launches;
         }
     }
     NC(g_nccl.GroupStart());
     for (int f = 0; f < nf; ++f) {
         for (const Peer& p : c->rpeers)
-            NC(g_nccl.Recv(fields[f] + ((size_t)c->m.N + p.off) * nlev, (size_t)p.cnt * nlev, ncclDouble, p.pe, c->comm, s));
+            NC(g_nccl.Recv(fields[f] + ((size_t)c->m.N + p.off) * nlev[f], (size_t)p.cnt * nlev[f], ncclDouble, p.pe, c->comm, s));
         for (const Peer& p : c->speers)
-            NC(g_nccl.Send(sendbufs[f] + (size_t)p.off * nlev, (size_t)p.cnt * nlev, ncclDouble, p.pe, c->comm, s));
+            NC(g_nccl.Send(sendbufs[f] + (size_t)p.off * nlev[f], (size_t)p.cnt * nlev[f], ncclDouble, p.pe, c->comm, s));
     }
     NC(g_nccl.GroupEnd());
     return ADV_OK;
@@ -487,10 +531,20 @@ int halo_exchange(adv_ctx* c, cudaStream_t s, int nf, double* const* fields, dou
 
 }  // namespace
 
-static int run_batch(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr,
-                     const std::vector<const double*>& ttf, const std::vector<const double*>& ttfAB,
-                     const std::vector<const double*>& grad, const std::vector<double*>& dh,
-                     const std::vector<double*>& dv)
+static int ensure_chunk_bufs(adv_ctx* c, int count)
+{
+    const MeshDev& m = c->m;
+    while ((int)c->cbufs.size() < count) {
+        c->cbufs.emplace_back(new ChunkBuf());
+        ChunkBuf& b = *c->cbufs.back();
+        CU(b.lo.alloc((size_t)m.L * m.Nh * 2)); CU(b.pm.alloc((size_t)m.L * m.Nh * 4));
+        CU(b.adf_h.alloc((size_t)m.L * m.E * 2)); CU(b.adf_v.alloc((size_t)m.nl * m.N * 2));
+        if (c->npes > 1) CU(b.sendbuf.alloc((size_t)c->send_cols * m.L * 4));
+    }
+    return ADV_OK;
+}
+
+static int run_batch(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr, const TrPtrs& p)
 {
     static const char* hn[] = {"MUSCL", "MFCT", "UPW1"};
     static const int hc[] = {HOR_MUSCL, HOR_MFCT, HOR_UPW1};
@@ -506,18 +560,22 @@ static int run_batch(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr
         static const char* ln[] = {"FCT"};
         static const int lc[] = {1};
         const int fct = parse_scheme(tr[i].tra_adv_lim, ln, lc, 1) == 1 ? 1 : 0;   // driver :111: anything else = no limiter
-        if (hor != HOR_UPW1 && !grad[i]) return fail(ADV_EINVAL, "edge_up_dn_grad is NULL for a gradient-based scheme");
+        if (hor != HOR_UPW1 && !p.grad[i]) return fail(ADV_EINVAL, "edge_up_dn_grad is NULL for a gradient-based scheme");
         bool found = false;
         for (auto& g : groups)
             if (g.fct == fct && g.hor == hor && g.ver == ver) { g.idx.push_back(i); found = true; break; }
         if (!found) groups.push_back(Group{fct, hor, ver, {i}});
     }
-    struct Chunk { int fct, hor, ver, tb; int idx[2]; };
-    std::vector<Chunk> chunks;
+    std::vector<ChunkSel> chunks;
     for (auto& g : groups) {
         size_t i = 0;
-        for (; i + 2 <= g.idx.size(); i += 2) chunks.push_back(Chunk{g.fct, g.hor, g.ver, 2, {g.idx[i], g.idx[i + 1]}});
-        if (i < g.idx.size()) chunks.push_back(Chunk{g.fct, g.hor, g.ver, 1, {g.idx[i], 0}});
+        for (; i + 2 <= g.idx.size(); i += 2) chunks.push_back(ChunkSel{g.fct, g.hor, g.ver, 2, {g.idx[i], g.idx[i + 1]}, 0});
+        if (i < g.idx.size()) chunks.push_back(ChunkSel{g.fct, g.hor, g.ver, 1, {g.idx[i], g.idx[i]}, 0});
+    }
+    if (int rc = ensure_chunk_bufs(c, (int)chunks.size())) return rc;
+    for (size_t k = 0; k < chunks.size(); ++k) {
+        chunks[k].buf = (int)k;
+        for (int t = 0; t < chunks[k].tb; ++t) c->trloc[chunks[k].idx[t]] = TrLoc{(int)k, t, chunks[k].tb};
     }
     cudaStream_t sc = c->s_comp, sx = c->s_comm;
     const int cpb = cols_per_block(m.L);
@@ -526,58 +584,63 @@ static int run_batch(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr
     const bool prof = c->profiling && !multi;
     auto mark = [&](int i) { if (prof) cudaEventRecord(c->ev_ph[i], sc); };
 
+    const NodeRange rAll{nullptr, 0, m.N, cpb}, rS{c->list_S.p, 0, c->nS, cpb}, rI{c->list_I.p, 0, c->nI, cpb},
+        rSH{c->list_SH.p, 0, c->nSH, cpb}, rAllH{nullptr, 0, m.Nh, cpb};
+    int launch_rc = ADV_OK;
+    std::string launch_msg;
+    auto run = [&](Phase ph, const ChunkSel& ch, const NodeRange& r) {
+        const bool qs = c->q_valid;
+        int rc;
+        if (ch.tb == 2) rc = launch_phase<2>(c, ph, ch.hor, ch.ver, qs, make_chunk<2>(c, p, tr, ch), r, dt);
+        else rc = launch_phase<1>(c, ph, ch.hor, ch.ver, qs, make_chunk<1>(c, p, tr, ch), r, dt);
+        if (rc && !launch_rc) { launch_rc = rc; launch_msg = g_err; }
+        if (ph == PH_E1) c->q_valid = true;
+    };
+    std::vector<double*> f1, s1, f2, s2;   // exchange field / send buffer lists over all FCT chunks
+    std::vector<int> n1, n2;
+    bool any_fct = false, any_nofct = false;
+    for (auto& ch : chunks) {
+        if (ch.fct) {
+            any_fct = true;
+            ChunkBuf& cb = *c->cbufs[ch.buf];
+            f1.push_back(cb.lo.p); s1.push_back(cb.sendbuf.p); n1.push_back(m.L * ch.tb);
+            f2.push_back(cb.pm.p); s2.push_back(cb.sendbuf.p); n2.push_back(m.L * ch.tb * 2);
+        } else any_nofct = true;
+    }
     mark(0);
-    if (!c->q_valid) {
-        const long long tot = (long long)m.E * m.L;
-        k_edge_volflux<<<(unsigned)((tot + kBlock - 1) / kBlock), kBlock, 0, sc>>>(m);
+    // ---- phase 0: antidiffusive edge fluxes (the first launch of a step also produces Q)
+    for (auto& ch : chunks) if (ch.fct) run(PH_E1, ch, rAll);
+    if (any_nofct && !c->q_valid) {
+        k_edge_volflux<<<nblocks(m.E, cpb), cpb * m.L, 0, sc>>>(m, cpb);
         ++c->launches;
         c->q_valid = true;
     }
-    mark(1);
-    const NodeRange rAll{nullptr, 0, m.N, cpb, c->ms_all}, rS{c->list_S.p, 0, c->nS, cpb, c->ms_S},
-        rI{c->list_I.p, 0, c->nI, cpb, c->ms_I}, rSH{c->list_SH.p, 0, c->nSH, cpb, c->ms_SH},
-        rAllH{nullptr, 0, m.Nh, cpb, c->ms_allh};
-    auto run = [&](Phase ph, const Chunk& ch, const NodeRange& r) {
-        if (ch.tb == 2) launch_phase<2>(c, ph, ch.hor, ch.ver, make_batch<2>(c, ttf, ttfAB, grad, dh, dv, tr, ch.idx), r, dt);
-        else launch_phase<1>(c, ph, ch.hor, ch.ver, make_batch<1>(c, ttf, ttfAB, grad, dh, dv, tr, ch.idx), r, dt);
-    };
-    std::vector<double*> f1, s1, f2, s2;   // exchange field / send buffer lists over all FCT tracers
-    bool any_fct = false;
-    for (auto& ch : chunks)
-        if (ch.fct) {
-            any_fct = true;
-            for (int t = 0; t < ch.tb; ++t) {
-                Slot& s = c->slots[ch.idx[t]];
-                f1.push_back(s.lo.p); s1.push_back(s.sendbuf.p);
-                f2.push_back(s.plus.p); s2.push_back(s.sendbuf.p);
-                f2.push_back(s.minus.p); s2.push_back(s.sendbuf.p + (size_t)c->send_cols * m.L);
-            }
-        }
     // non-FCT tracers: one sweep, no exchange inside the path
     for (auto& ch : chunks)
         if (!ch.fct) run(PH_NOFCT, ch, multi ? rAllH : rAll);
+    mark(1);
     if (any_fct) {
         const bool overlap = multi && !m.use_wsplit;
-        // ---- phase 1: LO + antidiffusive fluxes (boundary set first, then start exchange 1)
+        // ---- phase 1: LO solution (boundary set first, then start exchange 1)
         if (overlap) {
-            for (auto& ch : chunks) if (ch.fct) run(PH_K1, ch, rS);
+            for (auto& ch : chunks) if (ch.fct) run(PH_N1, ch, rS);
             CU(cudaEventRecord(c->ev_a, sc));
             CU(cudaStreamWaitEvent(sx, c->ev_a, 0));
-            if (int rc = halo_exchange(c, sx, (int)f1.size(), f1.data(), s1.data(), m.L)) return rc;   // driver :335
+            if (int rc = halo_exchange(c, sx, (int)f1.size(), f1.data(), s1.data(), n1.data())) return rc;   // driver :335
             CU(cudaEventRecord(c->ev_b, sx));
-            for (auto& ch : chunks) if (ch.fct) run(PH_K1, ch, rI);
+            for (auto& ch : chunks) if (ch.fct) run(PH_N1, ch, rI);
             CU(cudaStreamWaitEvent(sc, c->ev_b, 0));
         } else {
-            for (auto& ch : chunks) if (ch.fct) run(PH_K1, ch, rAll);
+            for (auto& ch : chunks) if (ch.fct) run(PH_N1, ch, rAll);
             if (m.use_wsplit) {
                 for (auto& ch : chunks)
                     if (ch.fct)
                         for (int t = 0; t < ch.tb; ++t) {
-                            k_vert_impl<<<(m.N + 127) / 128, 128, 0, sc>>>(m, c->slots[ch.idx[t]].lo.p, c->impl_cp.p, c->impl_tp.p, dt);
+                            k_vert_impl<<<(m.N + 127) / 128, 128, 0, sc>>>(m, c->cbufs[ch.buf]->lo.p, ch.tb, t, c->impl_cp.p, c->impl_tp.p, dt);
                             ++c->launches;
                         }
             }
-            if (multi) if (int rc = halo_exchange(c, sc, (int)f1.size(), f1.data(), s1.data(), m.L)) return rc;
+            if (multi) if (int rc = halo_exchange(c, sc, (int)f1.size(), f1.data(), s1.data(), n1.data())) return rc;
         }
         mark(2);
         // ---- phase 2: bounds + R+/R- (boundary set first, then start exchange 2)
@@ -585,7 +648,7 @@ static int run_batch(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr
             for (auto& ch : chunks) if (ch.fct) run(PH_K2, ch, rS);
             CU(cudaEventRecord(c->ev_c, sc));
             CU(cudaStreamWaitEvent(sx, c->ev_c, 0));
-            if (int rc = halo_exchange(c, sx, (int)f2.size(), f2.data(), s2.data(), m.L)) return rc;   // fct :413
+            if (int rc = halo_exchange(c, sx, (int)f2.size(), f2.data(), s2.data(), n2.data())) return rc;   // fct :413
             CU(cudaEventRecord(c->ev_d, sx));
             for (auto& ch : chunks) if (ch.fct) run(PH_K2, ch, rI);
             // ---- phase 3: interior update overlaps exchange 2
@@ -600,6 +663,7 @@ static int run_batch(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr
     } else { mark(2); mark(3); }
     mark(4);
     c->ph_valid = prof;
+    if (launch_rc) { cudaGetLastError(); return fail(launch_rc, launch_msg); }
     CU(cudaGetLastError());
     return ADV_OK;
 }
@@ -612,14 +676,14 @@ static int do_adv(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr, i
     CU(cudaSetDevice(c->device));
     MeshDev& m = c->m;
     const size_t nLN = (size_t)m.L * m.Nh, nLE = (size_t)m.L * m.E;
-    std::vector<const double*> ttf(ntr), ttfAB(ntr), grad(ntr);
-    std::vector<double*> dh(ntr), dv(ntr);
+    TrPtrs p;
+    p.ttf.resize(ntr); p.ttfAB.resize(ntr); p.grad.resize(ntr); p.dh.resize(ntr); p.dv.resize(ntr);
     for (int i = 0; i < ntr; ++i) {
         if (!tr[i].values || !tr[i].valuesAB || !tr[i].del_ttf_advhoriz || !tr[i].del_ttf_advvert)
             return fail(ADV_EINVAL, "tracer " + std::to_string(i + 1) + ": null field");
         if (where == ADV_DEVICE) {
-            ttf[i] = tr[i].values; ttfAB[i] = tr[i].valuesAB; grad[i] = tr[i].edge_up_dn_grad;
-            dh[i] = tr[i].del_ttf_advhoriz; dv[i] = tr[i].del_ttf_advvert;
+            p.ttf[i] = tr[i].values; p.ttfAB[i] = tr[i].valuesAB; p.grad[i] = tr[i].edge_up_dn_grad;
+            p.dh[i] = tr[i].del_ttf_advhoriz; p.dv[i] = tr[i].del_ttf_advvert;
         } else {
             Slot& s = c->slots[i];
             if (s.ttf.n != nLN) { CU(s.ttf.alloc(nLN, false)); CU(s.ttfAB.alloc(nLN, false)); CU(s.dh.alloc(nLN, false)); CU(s.dv.alloc(nLN, false)); }
@@ -627,23 +691,23 @@ static int do_adv(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr, i
             CU(cudaMemcpyAsync(s.ttfAB.p, tr[i].valuesAB, nLN * 8, cudaMemcpyHostToDevice, c->s_comp));
             CU(cudaMemcpyAsync(s.dh.p, tr[i].del_ttf_advhoriz, nLN * 8, cudaMemcpyHostToDevice, c->s_comp));
             CU(cudaMemcpyAsync(s.dv.p, tr[i].del_ttf_advvert, nLN * 8, cudaMemcpyHostToDevice, c->s_comp));
-            grad[i] = nullptr;
+            p.grad[i] = nullptr;
             if (tr[i].edge_up_dn_grad) {
                 if (s.grad.n != 4 * nLE) CU(s.grad.alloc(4 * nLE, false));
                 CU(cudaMemcpyAsync(s.grad.p, tr[i].edge_up_dn_grad, 4 * nLE * 8, cudaMemcpyHostToDevice, c->s_comp));
-                grad[i] = s.grad.p;
+                p.grad[i] = s.grad.p;
             }
-            ttf[i] = s.ttf.p; ttfAB[i] = s.ttfAB.p; dh[i] = s.dh.p; dv[i] = s.dv.p;
+            p.ttf[i] = s.ttf.p; p.ttfAB[i] = s.ttfAB.p; p.dh[i] = s.dh.p; p.dv[i] = s.dv.p;
         }
     }
     CU(cudaEventRecord(c->ev_t0, c->s_comp));
-    if (int rc = run_batch(c, dt, ntr, tr, ttf, ttfAB, grad, dh, dv)) return rc;
+    if (int rc = run_batch(c, dt, ntr, tr, p)) return rc;
     CU(cudaEventRecord(c->ev_t1, c->s_comp));
     c->timed = true;
     if (where == ADV_HOST) {
         for (int i = 0; i < ntr; ++i) {
-            CU(cudaMemcpyAsync(tr[i].del_ttf_advhoriz, dh[i], nLN * 8, cudaMemcpyDeviceToHost, c->s_comp));
-            CU(cudaMemcpyAsync(tr[i].del_ttf_advvert, dv[i], nLN * 8, cudaMemcpyDeviceToHost, c->s_comp));
+            CU(cudaMemcpyAsync(tr[i].del_ttf_advhoriz, p.dh[i], nLN * 8, cudaMemcpyDeviceToHost, c->s_comp));
+            CU(cudaMemcpyAsync(tr[i].del_ttf_advvert, p.dv[i], nLN * 8, cudaMemcpyDeviceToHost, c->s_comp));
         }
     }
     if (blocking) CU(cudaStreamSynchronize(c->s_comp));
@@ -679,7 +743,8 @@ int adv_exchange_nod(adv_ctx_t* c, int nfields, double* const* fields, int nlev)
     if (c->xbuf.n < need) { CU(cudaStreamSynchronize(c->s_comp)); CU(c->xbuf.alloc(need, false)); }
     std::vector<double*> sb(nfields);
     for (int f = 0; f < nfields; ++f) sb[f] = c->xbuf.p + (size_t)f * c->send_cols * nlev;
-    return halo_exchange(c, c->s_comp, nfields, fields, sb.data(), nlev);
+    std::vector<int> nl(nfields, nlev);
+    return halo_exchange(c, c->s_comp, nfields, fields, sb.data(), nl.data());
 }
 
 int adv_update_values(adv_ctx_t* c, int ntr, double* const* values, const double* const* dh, const double* const* dv)
@@ -687,9 +752,10 @@ int adv_update_values(adv_ctx_t* c, int ntr, double* const* values, const double
     if (!c || !values || !dh || !dv || ntr < 1) return fail(ADV_EINVAL, "bad argument");
     if (!c->state_set) return fail(ADV_ESTATE, "adv_ctx_set_state has not been called");
     CU(cudaSetDevice(c->device));
-    const long long tot = (long long)c->m.N * c->m.L;
+    const int cpb = cols_per_block(c->m.L);
+    const NodeRange rAll{nullptr, 0, c->m.N, cpb};
     for (int i = 0; i < ntr; ++i) {
-        k_update_values<<<(unsigned)((tot + kBlock - 1) / kBlock), kBlock, 0, c->s_comp>>>(c->m, values[i], dh[i], dv[i]);
+        k_update_values<<<nblocks(c->m.N, cpb), cpb * c->m.L, 0, c->s_comp>>>(c->m, rAll, values[i], dh[i], dv[i]);
         ++c->launches;
     }
     CU(cudaGetLastError());
@@ -704,21 +770,25 @@ int adv_ctx_get_work(adv_ctx_t* c, const char* name, int slot, double* out)
     CU(cudaStreamSynchronize(c->s_comp));
     CU(cudaStreamSynchronize(c->s_comm));
     const MeshDev& m = c->m;
-    const double* src = nullptr;
-    size_t n = 0;
     const std::string s(name);
-    if (s == "edge_volflux") { src = c->Q.p; n = (size_t)m.L * m.E; }
-    else {
-        if (slot < 0 || slot >= c->max_tr) return fail(ADV_EINVAL, "slot out of range");
-        Slot& sl = c->slots[slot];
-        if (s == "fct_LO") { src = sl.lo.p; n = (size_t)m.L * m.Nh; }
-        else if (s == "fct_plus") { src = sl.plus.p; n = (size_t)m.L * m.Nh; }
-        else if (s == "fct_minus") { src = sl.minus.p; n = (size_t)m.L * m.Nh; }
-        else if (s == "adv_flux_hor") { src = sl.adf_h.p; n = (size_t)m.L * m.E; }
-        else if (s == "adv_flux_ver") { src = sl.adf_v.p; n = (size_t)m.nl * m.N; }
-        else return fail(ADV_EINVAL, "unknown work array " + s);
+    if (s == "edge_volflux") {
+        CU(cudaMemcpy(out, c->Q.p, (size_t)m.L * m.E * sizeof(double), cudaMemcpyDeviceToHost));
+        return ADV_OK;
     }
-    CU(cudaMemcpy(out, src, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (slot < 0 || slot >= c->max_tr || c->trloc[slot].chunk < 0 || c->trloc[slot].chunk >= (int)c->cbufs.size())
+        return fail(ADV_EINVAL, "slot out of range / tracer not part of the last call");
+    const TrLoc loc = c->trloc[slot];
+    ChunkBuf& cb = *c->cbufs[loc.chunk];
+    // the work arrays interleave the chunk's tracers (and R+ with R-): copy the strided slice
+    const double* src = nullptr;
+    size_t n = 0, stride = loc.tb, off = loc.pos;
+    if (s == "fct_LO") { src = cb.lo.p; n = (size_t)m.L * m.Nh; }
+    else if (s == "fct_plus") { src = cb.pm.p; n = (size_t)m.L * m.Nh; stride = 2 * loc.tb; off = 2 * loc.pos; }
+    else if (s == "fct_minus") { src = cb.pm.p; n = (size_t)m.L * m.Nh; stride = 2 * loc.tb; off = 2 * loc.pos + 1; }
+    else if (s == "adv_flux_hor") { src = cb.adf_h.p; n = (size_t)m.L * m.E; }
+    else if (s == "adv_flux_ver") { src = cb.adf_v.p; n = (size_t)m.nl * m.N; }
+    else return fail(ADV_EINVAL, "unknown work array " + s);
+    CU(cudaMemcpy2D(out, sizeof(double), src + off, stride * sizeof(double), sizeof(double), n, cudaMemcpyDeviceToHost));
     return ADV_OK;
 }
 

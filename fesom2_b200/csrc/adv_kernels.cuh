@@ -1,23 +1,33 @@
 // fesom2_b200/csrc/adv_kernels.cuh -- sm_100a kernels of the tracer-advection path.
 //
 // Hand-written CUDA (FP64, no tensor cores: a bandwidth-bound sparse stencil).  The reference's
-// ~22 sweeps per tracer are recast as node-centred, deterministic gathers:
+// ~22 sweeps per tracer become four passes per tracer chunk, separated only
+// by the two dependency fronts that carry a halo exchange:
 //
-//   k_edge_volflux   Q(nz,e): the tracer-independent volume flux of adv_tra_hor_* (once per step)
-//   k_fct_lo_adf     D1-D5 + D7/D8 + F5-F7: LO solution, antidiffusive fluxes HO-LO, P+/P- sums
-//   k_vert_impl      adv_tra_vert_impl (use_wsplit only)
-//   k_fct_bounds     F1-F4 + F8: cluster bounds and the limiter factors R+/R-
-//   k_fct_update     F10-F11 + U1-U3: limit and accumulate del_ttf_advhoriz / del_ttf_advvert
-//   k_nofct          D7/D8 + U2-U3 when tra_adv_lim /= 'FCT'
+//   k_edge_flux    D1 + D7 (+ the tracer-independent volume flux Q): one thread per (edge, layer)
+//                  computes the low-order and high-order edge flux ONCE and stores the antidiffusive
+//                  flux HO-LO; a pure streaming kernel, every operand read exactly once
+//   k_node_lo      D2-D5 + D8: LO solution by an ordered gather of the upwind edge fluxes
+//                  (recomputed from Q: 3 flops instead of a stored field), vertical LO/HO fluxes
+//   ------------------------------------------------------------ exchange_nod(fct_LO)
+//   k_fct_bounds   F1-F8: cluster bounds, P+/P- sums and the limiter factors R+/R-
+//   ------------------------------------------------------------ exchange_nod(fct_plus, fct_minus)
+//   k_fct_update   F10-F11 + U1-U3: limit and accumulate del_ttf_advhoriz / del_ttf_advvert
+//   k_nofct        D7/D8 + U2-U3 when tra_adv_lim /= 'FCT'
+//   k_vert_impl    adv_tra_vert_impl (use_wsplit only)
 //
-// Thread mapping: a CTA owns `cpb` node columns, thread = (column, layer).  Fields keep the
-// reference layout (level fastest, src/associate_mesh_ass.h:9-79) so the layer index of adjacent
-// lanes is contiguous in HBM: every field access is a coalesced run of 8-byte words per column and
-// the 4-component gradient is one 32-byte vector per thread.  Edge->node scatters of the reference
-// (oce_adv_tra_driver.F90:142-201,:575-633; oce_adv_tra_fct.F90:312-377) become gathers over a
-// node->edge CSR sorted by ascending edge id, which reproduces the serial summation order bit for
-// bit.  Compile with -fmad=false: parity is checked against a non-contracted
-// CPU restatement.
+// Thread mapping: a CTA owns `cpb` whole columns (nodes or edges), thread = (column, layer).  All
+// caller-visible fields keep the reference layout (level fastest, src/associate_mesh_ass.h:9-79),
+// so adjacent lanes touch adjacent 8-byte words.  The library-owned work arrays (fct_LO, adv_flux_*,
+// fct_plus/minus) interleave the TB tracers of a chunk -- and R+ with R- -- at every (level, column)
+// so that one 16/32-byte vector access serves the whole chunk.
+//
+// Edge->node scatters of the reference (oce_adv_tra_driver.F90:142-201,:575-633;
+// oce_adv_tra_fct.F90:312-377) are gathers over a node->edge CSR sorted by ascending edge id, which
+// reproduces the serial summation order bit for bit.  Gathers are written as
+// "load a batch of G slots into registers, then accumulate in order" so that G x fields loads are
+// in flight per thread.  Compile with -fmad=false: parity is checked against a non-contracted CPU
+// restatement.
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -29,15 +39,31 @@ enum { HOR_UPW1 = 0, HOR_MUSCL = 1, HOR_MFCT = 2 };
 enum { VER_UPW1 = 0, VER_QR4C = 1, VER_PPM = 2, VER_CDIFF = 3 };
 
 constexpr int kBlock = 256;
+#ifndef ADV_E1_MINB
+#define ADV_E1_MINB 4
+#endif
+#ifndef ADV_N1_MINB
+#define ADV_N1_MINB 2
+#endif
+#ifndef ADV_K2_MINB
+#define ADV_K2_MINB 2
+#endif
+#ifndef ADV_K3_MINB
+#define ADV_K3_MINB 2
+#endif
 
 struct MeshDev {
     int L, nl, N, Nh, T, E;
+    unsigned div_magic;      // ceil(2^20 / L): (tid * div_magic) >> 20 == tid / L for tid < 1024
     // topology (built in adv_ctx_create)
     const int*    ne_ptr;    // (Nh+1) node -> incident edges, ascending edge id
-    const int4*   ne_ent;    // {edge, other node, lo | hi<<8 | flags<<16, 0}; flags bit0: node is edges(2,e); bit1: writes adf_h
-    const int*    cl_ptr;    // (N+1) FCT cluster of an owned node
-    const int2*   cl_ent;    // {node, lo | hi<<8}
+    const int4*   ne_ent;    // {edge, other node, lo | hi<<8 | flags<<16, 0}; flags bit0: node is edges(2,e)
+    const int4*   ne_ell;    // (Nh, ell_w) the same entries padded to the maximum degree (ELL): no pointer chase
+    int ell_w;
     const uchar4* node_lev;  // (Nh) {ulevels_nod2D, nlevels_nod2D, pad_lo, pad_hi}
+    const uint2*  node_rec;  // (Nh) bytes {ulev, nlev, pad_lo, pad_hi, self_lo, self_hi, degree, 0}: pad = levels where
+                             //      every element of the FCT cluster is wet; self = range covered by the node's own elements
+    const int4*   edge_meta; // (E) {edges(1,e), edges(2,e), el1, el2} 0-based, el2 = -1: none
     const int2*   edge_el;   // (E) {el1, el2} 0-based, -1 none
     const uchar4* edge_lev;  // (E) {nu1, nl1, nu2, nl2}  (nl = nlevels-1; 0,0 for a missing el2)
     const double4* edge_cross; // (E) edge_cross_dxdy
@@ -54,30 +80,66 @@ struct MeshDev {
     double* Q;               // (L,E) volume flux
 };
 
+// One chunk of TB tracers.  Work arrays are tracer-interleaved:
+//   lo[(n*L+nz0)*TB+t], adf_h[(e*L+nz0)*TB+t], adf_v[(n*nl+k0)*TB+t], pm[((n*L+nz0)*TB+t)*2+{0:plus,1:minus}]
 template <int TB>
-struct TrBatch {
+struct Chunk {
     const double* ttf[TB];
     const double* ttfAB[TB];
     const double* grad[TB];
-    double* lo[TB];
-    double* adf_h[TB];
-    double* adf_v[TB];
-    double* plus[TB];
-    double* minus[TB];
     double* dttf_h[TB];
     double* dttf_v[TB];
     double ph[TB], pv[TB];
+    double *lo, *adf_h, *adf_v, *pm;
 };
 
 struct NodeRange {
     const int* list;  // optional indirection (0-based node ids); nullptr = identity
     int begin, count;
     int cpb;          // columns per CTA
-    int max_slots;    // max over CTAs of the number of (column, incident edge) pairs
 };
 
 __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
 __device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
+
+// L2 software prefetch of [p, p+bytes), widened to the 16-byte granularity of the bulk-prefetch
+// instruction (sm_90+: one instruction per column instead of one per 128-byte line).  CTAs
+// prefetch the operands of the CTA `pf` launches ahead so that the dependent metadata -> data
+// load chain of a gather finds its lines in the 126 MB L2 instead of paying HBM latency twice.
+__device__ __forceinline__ void l2_prefetch(const void* p, unsigned bytes)
+{
+    const unsigned long long a = (unsigned long long)p, a0 = a & ~15ull;
+    const unsigned sz = (unsigned)(((a + bytes + 15ull) & ~15ull) - a0);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch_line(const void* p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// vector access to the tracer-interleaved work arrays: TB doubles at p (16-byte aligned for TB=2)
+template <int TB> __device__ __forceinline__ void ldv(const double* __restrict__ p, double (&v)[TB]);
+template <> __device__ __forceinline__ void ldv<1>(const double* __restrict__ p, double (&v)[1]) { v[0] = __ldg(p); }
+template <> __device__ __forceinline__ void ldv<2>(const double* __restrict__ p, double (&v)[2])
+{
+    const double2 t = __ldg(reinterpret_cast<const double2*>(p));
+    v[0] = t.x; v[1] = t.y;
+}
+template <int TB> __device__ __forceinline__ void stv(double* __restrict__ p, const double (&v)[TB]);
+template <> __device__ __forceinline__ void stv<1>(double* __restrict__ p, const double (&v)[1]) { p[0] = v[0]; }
+template <> __device__ __forceinline__ void stv<2>(double* __restrict__ p, const double (&v)[2])
+{
+    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+}
+// {plus, minus} pairs of the TB tracers at p
+template <int TB> __device__ __forceinline__ void ldpm(const double* __restrict__ p, double (&pl)[TB], double (&mi)[TB])
+{
+#pragma unroll
+    for (int t = 0; t < TB; ++t) {
+        const double2 v = __ldg(reinterpret_cast<const double2*>(p) + t);
+        pl[t] = v.x; mi[t] = v.y;
+    }
+}
 
 // Correctly rounded x / b from y = RN(1/b): q0 = x*y is refined twice with exact FMA residuals
 // (Markstein: a faithful quotient plus one residual step with the correctly rounded reciprocal
@@ -96,18 +158,20 @@ constexpr double kInv6 = 1.0 / 6.0, kInv3 = 1.0 / 3.0;   // RN(1/6), RN(1/3): co
 __device__ __forceinline__ double div6(double x) { return div_rcp(x, 6.0, kInv6); }
 __device__ __forceinline__ double div3(double x) { return div_rcp(x, 3.0, kInv3); }
 
-// ----------------------------------------------------------------------------------------------
-// Q(nz,e): vflux of oce_adv_tra_hor.F90:170,190,211-212,226,242 on the level ranges A-E (:127-160)
-// ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_edge_volflux(MeshDev m)
+// thread -> (column, layer) of a CTA that owns cpb whole columns: blockDim.x == cpb * L
+struct ColThread { int g, nz0; };
+__device__ __forceinline__ ColThread col_thread(const MeshDev& m)
 {
-    const int L = m.L;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)m.E * L) return;
-    const int e = (int)(idx / L);
-    const int nz = (int)(idx - (long long)e * L) + 1;
-    const int2 el = m.edge_el[e];
-    const uchar4 lv = m.edge_lev[e];
+    ColThread c;
+    c.g = (int)((threadIdx.x * m.div_magic) >> 20);
+    c.nz0 = (int)threadIdx.x - c.g * m.L;
+    return c;
+}
+
+// the level ranges A-E of an edge column (oce_adv_tra_hor.F90:127-160) -> which element(s)
+// contribute to the volume flux at level nz
+__device__ __forceinline__ void edge_use(uchar4 lv, int nz, bool& use1, bool& use2)
+{
     const int nu1 = lv.x, nl1 = lv.y, nu2 = lv.z, nl2 = lv.w;
     const int nl12 = min(nl1, nl2), nu12 = max(nu1, nu2);
     const bool inA = nz >= nu1 && nz <= nu12 - 1;
@@ -115,24 +179,41 @@ __global__ void __launch_bounds__(kBlock) k_edge_volflux(MeshDev m)
     const bool inC = nz >= nu12 && nz <= nl12;
     const bool inD = nz >= nl12 + 1 && nz <= nl1;
     const bool inE = nz >= nl12 + 1 && nz <= nl2;
-    const bool use1 = inA || inC || inD, use2 = inB || inC || inE;
-    const double4 cr = m.edge_cross[e];
+    use1 = inA || inC || inD;
+    use2 = inB || inC || inE;
+}
+
+// Q(nz,e): vflux of oce_adv_tra_hor.F90:170,190,211-212,226,242
+__device__ __forceinline__ double edge_volflux(const MeshDev& m, int2 el, double4 cr, bool use1, bool use2, int nz0)
+{
     double v1 = 0.0, v2 = 0.0;
     if (use1) {
-        const size_t o = (size_t)el.x * L + (nz - 1);
-        const double2 uv = reinterpret_cast<const double2*>(m.uv)[o];
-        v1 = (-uv.y * cr.x + uv.x * cr.y) * m.helem[o];
+        const unsigned o = (unsigned)el.x * m.L + nz0;
+        const double2 uv = __ldg(reinterpret_cast<const double2*>(m.uv) + o);
+        v1 = (-uv.y * cr.x + uv.x * cr.y) * __ldg(&m.helem[o]);
     }
     if (use2) {
-        const size_t o = (size_t)el.y * L + (nz - 1);
-        const double2 uv = reinterpret_cast<const double2*>(m.uv)[o];
-        v2 = (uv.y * cr.z - uv.x * cr.w) * m.helem[o];
+        const unsigned o = (unsigned)el.y * m.L + nz0;
+        const double2 uv = __ldg(reinterpret_cast<const double2*>(m.uv) + o);
+        v2 = (uv.y * cr.z - uv.x * cr.w) * __ldg(&m.helem[o]);
     }
     double q = 0.0;
     if (use1 && use2) q = v1 + v2;
     else if (use1) q = v1;
     else if (use2) q = v2;
-    m.Q[idx] = q;
+    return q;
+}
+
+// stand-alone Q kernel (only the non-FCT path needs it; the FCT path fuses Q into k_edge_flux)
+__global__ void __launch_bounds__(kBlock) k_edge_volflux(MeshDev m, int epb)
+{
+    const ColThread c = col_thread(m);
+    const int e = blockIdx.x * epb + c.g;
+    if (e >= m.E) return;
+    const int nz = c.nz0 + 1;
+    bool use1, use2;
+    edge_use(m.edge_lev[e], nz, use1, use2);
+    m.Q[(size_t)e * m.L + c.nz0] = edge_volflux(m, m.edge_el[e], m.edge_cross[e], use1, use2, c.nz0);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -307,12 +388,11 @@ __device__ __forceinline__ double hor_lo(double t1, double t2, double qp, double
 
 template <int HOR>
 __device__ __forceinline__ double hor_ho(double a1, double a2, double q, double qp, double qm, double2 ec,
-                                         const double* __restrict__ g, double num_ord, double clo1, double clo2,
+                                         double2 g12, double2 g34, double num_ord, double clo1, double clo2,
                                          double fin)
 {
+    // g12 = (gx_up, gx_dn), g34 = (gy_up, gy_dn): edge_up_dn_grad(1:4,nz,e), oce_adv_tra_hor.F90:431-434
     if (HOR == HOR_UPW1) return -0.5 * (a1 * qp + a2 * qm) - fin;
-    const double2 g12 = __ldg(reinterpret_cast<const double2*>(g));      // gx_up, gx_dn
-    const double2 g34 = __ldg(reinterpret_cast<const double2*>(g) + 1);  // gy_up, gy_dn
     const double d = 2.0 * (a2 - a1);
     double Tmean2, Tmean1;
     if (HOR == HOR_MUSCL) {
@@ -326,214 +406,312 @@ __device__ __forceinline__ double hor_ho(double a1, double a2, double q, double 
     return -0.5 * (1.0 - num_ord) * cHO - q * num_ord * 0.5 * (Tmean1 + Tmean2) - fin;
 }
 
-// thread -> (column, layer) decode shared by the node kernels
-struct ThreadCol {
+// node decode shared by the node kernels
+struct NodeThread {
     int n, nz0, nzmin, nzmax;
+    int pad_lo, pad_hi, self_lo, self_hi, deg;
     bool active;
 };
-__device__ __forceinline__ ThreadCol decode(const MeshDev& m, const NodeRange& r)
+__device__ __forceinline__ NodeThread node_thread(const MeshDev& m, const NodeRange& r)
 {
-    ThreadCol t;
-    const int L = m.L;
-    const int col = threadIdx.x / L;
-    t.nz0 = threadIdx.x - col * L;
-    const int i = blockIdx.x * r.cpb + col;
-    t.active = (col < r.cpb) && (i < r.count);
+    NodeThread t;
+    const ColThread c = col_thread(m);
+    t.nz0 = c.nz0;
+    const int i = blockIdx.x * r.cpb + c.g;
+    t.active = i < r.count;
     t.n = 0; t.nzmin = 1; t.nzmax = 0;
+    t.pad_lo = 0; t.pad_hi = 255; t.self_lo = 1; t.self_hi = 0; t.deg = 0;
     if (t.active) {
-        t.n = r.list ? r.list[r.begin + i] : r.begin + i;
-        const uchar4 lv = m.node_lev[t.n];
-        t.nzmin = lv.x; t.nzmax = lv.y;
+        t.n = r.list ? __ldg(&r.list[r.begin + i]) : r.begin + i;
+        const uint2 rec = __ldg(&m.node_rec[t.n]);
+        t.nzmin = rec.x & 0xff; t.nzmax = (rec.x >> 8) & 0xff;
+        t.pad_lo = (rec.x >> 16) & 0xff; t.pad_hi = rec.x >> 24;
+        t.self_lo = rec.y & 0xff; t.self_hi = (rec.y >> 8) & 0xff; t.deg = (rec.y >> 16) & 0xff;
     }
     return t;
 }
 
-// ----------------------------------------------------------------------------------------------
-// K1: LO solution + antidiffusive fluxes + P+/P- (owned nodes)
-//   reference: oce_adv_tra_driver.F90:115-252 (D1-D5), :343-379 (D7-D8),
-//              oce_adv_tra_fct.F90:265-377 (b1)
-// outputs: lo(nz,n), adf_v(1:nl,n), adf_h(nz,e) (written by the designated end node), raw P+/P-
-// sums into plus/minus.
-//
-// Two phases per CTA so that no thread walks its edges serially behind dependent loads:
-//   A  every (incident-edge slot, layer) pair of the CTA's columns is one work item: its thread
-//      loads Q, both end values, the 4 gradients and stores the LO and antidiffusive edge flux in
-//      shared memory -- all loads of all slots are in flight together;
-//   B  thread (column, layer) adds the slots in ascending-edge order (the serial order of the
-//      reference's scatter loops), so the sums are bit-identical to the CPU result.
-// ----------------------------------------------------------------------------------------------
-template <int TB>
-__host__ __device__ inline size_t k1_smem_bytes(int L, int cpb, int max_slots)
-{
-    return ((size_t)2 * TB * cpb * L + (size_t)max_slots * TB * 2 * L) * sizeof(double) +
-           (size_t)(3 * cpb + 2 + 2 * max_slots) * sizeof(int);
-}
+// an empty gather slot: lo = 255 > hi = 0, never in range (nl <= 255)
+#define ADV_EMPTY_SLOT make_int4(0, 0, 0xff, 0)
 
-// launch with blockDim.x == cpb * L: thread = (column g, layer nz0), no idle threads
-template <int HOR, int VER, int TB>
-__global__ void __launch_bounds__(kBlock) k_fct_lo_adf(MeshDev m, TrBatch<TB> b, NodeRange r, double dt)
+// ----------------------------------------------------------------------------------------------
+// E1: antidiffusive horizontal flux HO-LO per (edge, layer), every operand read once.
+//   reference: oce_adv_tra_driver.F90:115 (LO = adv_tra_hor_upw1 on ttf), :343-354 (HO on ttfAB
+//   with o_init_zero=.false.: flux := HO - LO), bodies oce_adv_tra_hor.F90:214-216, :446-461,
+//   :488-489, :736-751, :777-778.
+// QMODE 0: compute the volume flux Q from uv/helem and store it (first chunk of a step);
+// QMODE 1: read the stored Q (later chunks of the same step: geometry reads amortised).
+// ----------------------------------------------------------------------------------------------
+template <int HOR, int TB, int QMODE>
+__global__ void __launch_bounds__(kBlock, ADV_E1_MINB) k_edge_flux(MeshDev m, Chunk<TB> b, int epb, int pf)
 {
-    extern __shared__ double sm[];
-    const int L = m.L, nl = m.nl, nthr = blockDim.x;
-    double* s_vert = sm;                                   // [2*TB][nthr] LO(we) flux, adf_v at the top interface
-    double* s_flux = sm + (size_t)2 * TB * nthr;           // [slot][TB][2][L]
-    int2* s_slot = reinterpret_cast<int2*>(s_flux + (size_t)r.max_slots * TB * 2 * L);  // [slot] {node, CSR index}
-    int* s_node = reinterpret_cast<int*>(s_slot + r.max_slots);
-    int* s_k0 = s_node + r.cpb;                            // first CSR entry of the column
-    int* s_off = s_k0 + r.cpb;                             // [cpb+1] slot offset of the column
-    const int c0 = blockIdx.x * r.cpb;
-    const int ncols = min(r.cpb, r.count - c0);
-    const int g = threadIdx.x / L;                         // the only integer division of the kernel
-    const int nz0 = threadIdx.x - g * L, nz = nz0 + 1;
-    if (threadIdx.x < ncols) {
-        const int n = r.list ? r.list[r.begin + c0 + threadIdx.x] : r.begin + c0 + threadIdx.x;
-        s_node[threadIdx.x] = n;
-        s_k0[threadIdx.x] = m.ne_ptr[n];
-        s_off[threadIdx.x + 1] = m.ne_ptr[n + 1] - m.ne_ptr[n];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int off = 0;
-        for (int c = 0; c < ncols; ++c) { const int cnt = s_off[c + 1]; s_off[c] = off; off += cnt; }
-        s_off[ncols] = off;
-    }
-    __syncthreads();
-    const int nslots = s_off[ncols];
-    for (int s = threadIdx.x; s < nslots; s += nthr) {
-        int c = 0;
-        while (c + 1 < ncols && s >= s_off[c + 1]) ++c;
-        s_slot[s] = make_int2(s_node[c], s_k0[c] + (s - s_off[c]));
-    }
-    __syncthreads();
-
-    // ---- phase A: edge fluxes; column group g takes slots g, g+cpb, ... at its layer ----------
-    for (int s = g; s < nslots; s += r.cpb) {
-        const int2 sl = s_slot[s];
-        const int4 ent = __ldg(&m.ne_ent[sl.y]);
-        const int lo = ent.z & 0xff, hi = (ent.z >> 8) & 0xff;
-        if (nz < lo || nz > hi) continue;
-        const int e = ent.x;
-        const bool second = (ent.z >> 16) & 1, writer = (ent.z >> 17) & 1;
-        const int i1 = second ? ent.y : sl.x, i2 = second ? sl.x : ent.y;      // edges(1,e), edges(2,e)
-        const unsigned oe = (unsigned)e * L + nz0, o1 = (unsigned)i1 * L + nz0, o2 = (unsigned)i2 * L + nz0;
-        const double q = __ldg(&m.Q[oe]);
-        const double aq = fabs(q), qp = q + aq, qm = q - aq;
-        double2 ec = make_double2(0.0, 0.0);
-        double clo1 = 1.0, clo2 = 1.0;
-        if (HOR != HOR_UPW1) ec = __ldg(&m.edge_c[e]);
-        if (HOR == HOR_MUSCL) {
-            clo1 = (__ldg(&m.nboundary_lay[i1]) - nz >= 0) ? 1.0 : 0.0;   // oce_adv_tra_hor.F90:411-412
-            clo2 = (__ldg(&m.nboundary_lay[i2]) - nz >= 0) ? 1.0 : 0.0;
+    const ColThread c = col_thread(m);
+    const int L = m.L;
+    // ---- prefetch-ahead, part 1: thread j < epb looks up future edge (blockIdx.x + pf) * epb + j
+    int ef = -1;
+    int4 mf = make_int4(0, 0, 0, -1);
+    if (pf > 0 && threadIdx.x < epb) {
+        const long long cand = ((long long)blockIdx.x + pf) * epb + threadIdx.x;
+        if (cand < m.E) {
+            ef = (int)cand;
+            mf = __ldg(&m.edge_meta[ef]);
+            l2_prefetch_line(&m.edge_lev[ef]);
+            l2_prefetch_line(&m.edge_cross[ef]);
+            if (HOR != HOR_UPW1) l2_prefetch_line(&m.edge_c[ef]);
         }
-        double* f = s_flux + (size_t)s * TB * 2 * L + nz0;
+    }
+    const int e = blockIdx.x * epb + c.g;
+    if (e >= m.E) return;
+    const int nz0 = c.nz0, nz = nz0 + 1;
+    // ---- wait 1: all per-edge metadata, issued together ---------------------------------------
+    const int4 em = __ldg(&m.edge_meta[e]);          // {edges(1,e), edges(2,e), el1, el2} 0-based, el2 = -1: none
+    const uchar4 lv = __ldg(&m.edge_lev[e]);
+    const double2 cr12 = __ldg(reinterpret_cast<const double2*>(&m.edge_cross[e]));
+    const double2 cr34 = __ldg(reinterpret_cast<const double2*>(&m.edge_cross[e]) + 1);
+    double2 ec = make_double2(0.0, 0.0);
+    if (HOR != HOR_UPW1) ec = __ldg(&m.edge_c[e]);
+    const unsigned oe = (unsigned)e * L + nz0, o1 = (unsigned)em.x * L + nz0, o2 = (unsigned)em.y * L + nz0;
+    // scatter range of oce_adv_tra_driver.F90:154-156: [min(nu1, nu2>0), max(nl1, nl2)]
+    const int lo = lv.z > 0 ? min((int)lv.x, (int)lv.z) : (int)lv.x;
+    const int hi = max((int)lv.y, (int)lv.w);
+    const bool inr = nz >= lo && nz <= hi;
+    bool use1 = false, use2 = false;
+    if (QMODE == 0) edge_use(lv, nz, use1, use2);
+    // ---- wait 2: all operand loads, issued together -------------------------------------------
+    double t1[TB], t2[TB], a1[TB], a2[TB];
+    double2 g12[TB], g34[TB];
+    double2 uv1 = make_double2(0.0, 0.0), uv2 = uv1;
+    double he1 = 0.0, he2 = 0.0, q = 0.0, clo1 = 1.0, clo2 = 1.0;
+#pragma unroll
+    for (int t = 0; t < TB; ++t) {
+        t1[t] = t2[t] = a1[t] = a2[t] = 0.0;
+        g12[t] = g34[t] = make_double2(0.0, 0.0);
+    }
+    if (inr) {
 #pragma unroll
         for (int t = 0; t < TB; ++t) {
-            const double t1 = __ldg(&b.ttf[t][o1]), t2 = __ldg(&b.ttf[t][o2]);
-            const double a1 = __ldg(&b.ttfAB[t][o1]), a2 = __ldg(&b.ttfAB[t][o2]);
-            const double flo = hor_lo(t1, t2, qp, qm);                                  // driver :115
-            const double* gr = (HOR != HOR_UPW1) ? (b.grad[t] + (size_t)oe * 4) : nullptr;
-            const double adf = hor_ho<HOR>(a1, a2, q, qp, qm, ec, gr, b.ph[t], clo1, clo2, flo);  // driver :343-354
-            f[(2 * t) * L] = flo;
-            f[(2 * t + 1) * L] = adf;
-            if (writer) b.adf_h[t][oe] = adf;
+            if (HOR != HOR_UPW1) {
+                const double2* gp = reinterpret_cast<const double2*>(b.grad[t]) + (size_t)oe * 2;
+                g12[t] = __ldg(gp);
+                g34[t] = __ldg(gp + 1);
+            }
+            t1[t] = __ldg(&b.ttf[t][o1]); t2[t] = __ldg(&b.ttf[t][o2]);
+            a1[t] = __ldg(&b.ttfAB[t][o1]); a2[t] = __ldg(&b.ttfAB[t][o2]);
+        }
+        if (HOR == HOR_MUSCL) {
+            clo1 = (__ldg(&m.nboundary_lay[em.x]) - nz >= 0) ? 1.0 : 0.0;   // oce_adv_tra_hor.F90:411-412
+            clo2 = (__ldg(&m.nboundary_lay[em.y]) - nz >= 0) ? 1.0 : 0.0;
+        }
+        if (QMODE == 1) q = __ldg(&m.Q[oe]);
+    }
+    if (QMODE == 0) {
+        if (use1) {
+            const unsigned o = (unsigned)em.z * L + nz0;
+            uv1 = __ldg(reinterpret_cast<const double2*>(m.uv) + o); he1 = __ldg(&m.helem[o]);
+        }
+        if (use2) {
+            const unsigned o = (unsigned)em.w * L + nz0;
+            uv2 = __ldg(reinterpret_cast<const double2*>(m.uv) + o); he2 = __ldg(&m.helem[o]);
+        }
+        // Q(nz,e): vflux of oce_adv_tra_hor.F90:170,190,211-212,226,242
+        const double v1 = (-uv1.y * cr12.x + uv1.x * cr12.y) * he1;
+        const double v2 = (uv2.y * cr34.x - uv2.x * cr34.y) * he2;
+        q = 0.0;
+        if (use1 && use2) q = v1 + v2;
+        else if (use1) q = v1;
+        else if (use2) q = v2;
+        m.Q[oe] = q;
+    }
+    double out[TB];
+#pragma unroll
+    for (int t = 0; t < TB; ++t) out[t] = 0.0;
+    if (inr) {
+        const double aq = fabs(q), qp = q + aq, qm = q - aq;
+#pragma unroll
+        for (int t = 0; t < TB; ++t) {
+            const double flo = hor_lo(t1[t], t2[t], qp, qm);
+            out[t] = hor_ho<HOR>(a1[t], a2[t], q, qp, qm, ec, g12[t], g34[t], b.ph[t], clo1, clo2, flo);
+        }
+    }
+    stv<TB>(b.adf_h + (size_t)oe * TB, out);
+    // ---- prefetch-ahead, part 2: the future edge's operand columns into L2
+    if (ef >= 0) {
+        const unsigned colb = (unsigned)L * 8u;
+#pragma unroll
+        for (int t = 0; t < TB; ++t) {
+            if (HOR != HOR_UPW1) l2_prefetch(b.grad[t] + (size_t)ef * L * 4, colb * 4);
+            l2_prefetch(b.ttf[t] + (size_t)mf.x * L, colb); l2_prefetch(b.ttf[t] + (size_t)mf.y * L, colb);
+            l2_prefetch(b.ttfAB[t] + (size_t)mf.x * L, colb); l2_prefetch(b.ttfAB[t] + (size_t)mf.y * L, colb);
+        }
+        if (QMODE == 0) {
+            l2_prefetch(m.uv + (size_t)mf.z * L * 2, colb * 2); l2_prefetch(m.helem + (size_t)mf.z * L, colb);
+            if (mf.w >= 0) { l2_prefetch(m.uv + (size_t)mf.w * L * 2, colb * 2); l2_prefetch(m.helem + (size_t)mf.w * L, colb); }
+        } else l2_prefetch(m.Q + (size_t)ef * L, colb);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// N1: LO solution + vertical antidiffusive flux (owned nodes)
+//   reference: oce_adv_tra_driver.F90:115-252 (D1-D5), :363-379 (D8)
+// The upwind edge flux is recomputed from Q and the two end values (3 flops) and added in
+// ascending-edge order, the serial order of the reference's scatter loop (:142-201).
+// Every thread first issues ALL its global loads (own level of the column operands + the first
+// gather batch), parks the column operands in shared memory and evaluates the vertical stencils
+// from there: one memory wait per thread instead of one per stencil point.
+// ----------------------------------------------------------------------------------------------
+template <int VER, int TB>
+__host__ __device__ constexpr int n1_smem_arrays() { return 3 * TB + 5 + (VER == VER_PPM ? 2 : 0); }
+
+template <int VER, int TB, int G>
+__global__ void __launch_bounds__(kBlock, ADV_N1_MINB) k_node_lo(MeshDev m, Chunk<TB> b, NodeRange r, double dt)
+{
+    extern __shared__ double sm[];      // n1_smem_arrays() arrays of [nthr]; element g*L+nz0 == threadIdx.x
+    const int L = m.L, nl = m.nl, nthr = blockDim.x, tid = threadIdx.x;
+    const NodeThread th = node_thread(m, r);
+    const int n = th.n, nz0 = th.nz0, nz = nz0 + 1, nzmin = th.nzmin, nzmax = th.nzmax;
+    const bool active = th.active;
+    const bool valid = active && nz >= nzmin && nz <= nzmax - 1;
+    const unsigned oL = (unsigned)n * L + nz0;
+    const size_t cN = (size_t)n * nl;
+    double* s_flo = sm;                               // [TB][nthr] LO vertical flux at the top interface
+    double* s_ttf = sm + (size_t)TB * nthr;           // [TB][nthr]
+    double* s_tab = s_ttf + (size_t)TB * nthr;        // [TB][nthr]
+    double* s_Z = s_tab + (size_t)TB * nthr;
+    double* s_zbar = s_Z + nthr;
+    double* s_w = s_zbar + nthr;
+    double* s_we = s_w + nthr;
+    double* s_area = s_we + nthr;
+    double* s_hn = s_area + nthr;                     // PPM only
+    double* s_hnn = s_hn + nthr;                      // PPM only
+
+    // ---- all global loads ---------------------------------------------------------------------
+    int4 ent[G];
+    double q[G], to[G][TB];
+    bool in[G];
+    double tn[TB], tab[TB];
+    double av = 1.0, hn = 0.0, hnn = 1.0, zz = 0.0, zb = 0.0, ww = 0.0, wwe = 0.0, ar = 0.0;
+    const int4* ell = m.ne_ell + (size_t)n * m.ell_w;
+#pragma unroll
+    for (int j = 0; j < G; ++j) ent[j] = (valid && j < th.deg) ? __ldg(&ell[j]) : ADV_EMPTY_SLOT;
+#pragma unroll
+    for (int t = 0; t < TB; ++t) { tn[t] = 0.0; tab[t] = 0.0; }
+    if (valid) {
+#pragma unroll
+        for (int t = 0; t < TB; ++t) { tn[t] = __ldg(&b.ttf[t][oL]); tab[t] = __ldg(&b.ttfAB[t][oL]); }
+        av = __ldg(&m.areasvol[cN + nz0]); hn = __ldg(&m.hnode[oL]); hnn = __ldg(&m.hnode_new[oL]);
+        zz = __ldg(&m.Z3d[oL]); zb = __ldg(&m.zbar3d[cN + nz0]);
+        ww = __ldg(&m.w[cN + nz0]); wwe = __ldg(&m.we[cN + nz0]); ar = __ldg(&m.area[cN + nz0]);
+    }
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+        const int lo = ent[j].z & 0xff, hi = (ent[j].z >> 8) & 0xff;
+        in[j] = nz >= lo && nz <= hi;
+        q[j] = 0.0;
+#pragma unroll
+        for (int t = 0; t < TB; ++t) to[j][t] = 0.0;
+        if (in[j]) {
+            q[j] = __ldg(&m.Q[(unsigned)ent[j].x * L + nz0]);
+            const unsigned oo = (unsigned)ent[j].y * L + nz0;
+#pragma unroll
+            for (int t = 0; t < TB; ++t) to[j][t] = __ldg(&b.ttf[t][oo]);
+        }
+    }
+    // ---- park the column operands in shared memory ---------------------------------------------
+#pragma unroll
+    for (int t = 0; t < TB; ++t) { s_ttf[t * nthr + tid] = tn[t]; s_tab[t * nthr + tid] = tab[t]; }
+    s_Z[tid] = zz; s_zbar[tid] = zb; s_w[tid] = ww; s_we[tid] = wwe; s_area[tid] = ar;
+    if (VER == VER_PPM) { s_hn[tid] = hn; s_hnn[tid] = hnn; }
+    __syncthreads();
+
+    // ---- horizontal LO gather: ordered accumulation ----------------------------------------------
+    double losum[TB];
+#pragma unroll
+    for (int t = 0; t < TB; ++t) losum[t] = 0.0;
+    if (valid) {
+        for (int j0 = 0;;) {
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                if (!in[j]) continue;
+                const bool second = (ent[j].z >> 16) & 1;
+                const double aq = fabs(q[j]), qp = q[j] + aq, qm = q[j] - aq;
+#pragma unroll
+                for (int t = 0; t < TB; ++t) {
+                    if (!second) losum[t] = losum[t] + hor_lo(tn[t], to[j][t], qp, qm);        // driver :175
+                    else losum[t] = losum[t] - hor_lo(to[j][t], tn[t], qp, qm);                // driver :188
+                }
+            }
+            j0 += G;
+            if (j0 >= th.deg) break;
+            // further batches (degree > G)
+#pragma unroll
+            for (int j = 0; j < G; ++j) ent[j] = (j0 + j < th.deg) ? __ldg(&ell[j0 + j]) : ADV_EMPTY_SLOT;
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                const int lo = ent[j].z & 0xff, hi = (ent[j].z >> 8) & 0xff;
+                in[j] = nz >= lo && nz <= hi;
+                if (in[j]) {
+                    q[j] = __ldg(&m.Q[(unsigned)ent[j].x * L + nz0]);
+                    const unsigned oo = (unsigned)ent[j].y * L + nz0;
+#pragma unroll
+                    for (int t = 0; t < TB; ++t) to[j][t] = __ldg(&b.ttf[t][oo]);
+                }
+            }
         }
     }
 
-    // ---- vertical fluxes at the thread's top interface ------------------------------------------
-    const bool active = g < ncols;
-    int n = 0, nzmin = 1, nzmax = 0;
-    if (active) {
-        n = s_node[g];
-        const uchar4 lv = m.node_lev[n];
-        nzmin = lv.x; nzmax = lv.y;
-    }
-    const size_t oL = (size_t)n * L + nz0;
-    const size_t cL = (size_t)n * L, cN = (size_t)n * nl;
-    const bool valid = active && nz >= nzmin && nz <= nzmax - 1;
+    // ---- vertical fluxes at the thread's top interface, stencils read from shared memory --------
     double flo_top[TB], adfv_top[TB];
 #pragma unroll
     for (int t = 0; t < TB; ++t) { flo_top[t] = 0.0; adfv_top[t] = 0.0; }
     if (active && nz >= nzmin && nz <= nzmax) {
+        const int c0 = tid - nz0;                 // first element of this thread's column
         ColV c;
-        c.area = m.area + cN; c.Z = m.Z3d + cL; c.zbar = m.zbar3d + cN;
-        c.hnode = m.hnode + cL; c.hnode_new = m.hnode_new + cL;
+        c.area = s_area + c0; c.Z = s_Z + c0; c.zbar = s_zbar + c0;
+        c.hnode = s_hn + c0; c.hnode_new = s_hnn + c0;
         c.nzmin = nzmin; c.nzmax = nzmax; c.dt = dt;
 #pragma unroll
         for (int t = 0; t < TB; ++t) {
-            c.ttf = b.ttf[t] + cL; c.w = m.we + cN; c.num_ord = 0.0;
+            c.ttf = s_ttf + t * nthr + c0; c.w = s_we + c0; c.num_ord = 0.0;
             const double fe = ver_upw1(c, nz, 0.0);                     // driver :235
             double flo = fe;
-            if (m.use_wsplit) { c.w = m.w + cN; flo = ver_upw1(c, nz, 0.0); }  // driver :333
-            c.ttf = b.ttfAB[t] + cL; c.w = m.w + cN; c.num_ord = b.pv[t];
+            if (m.use_wsplit) { c.w = s_w + c0; flo = ver_upw1(c, nz, 0.0); }  // driver :333
+            c.ttf = s_tab + t * nthr + c0; c.w = s_w + c0; c.num_ord = b.pv[t];
             flo_top[t] = fe;
             adfv_top[t] = ver_flux<VER>(c, nz, flo);                    // driver :363-379
         }
     }
 #pragma unroll
-    for (int t = 0; t < TB; ++t) {
-        s_vert[(2 * t) * nthr + threadIdx.x] = flo_top[t];
-        s_vert[(2 * t + 1) * nthr + threadIdx.x] = adfv_top[t];
-    }
+    for (int t = 0; t < TB; ++t) s_flo[t * nthr + tid] = flo_top[t];
     __syncthreads();
     if (active) {
+        stv<TB>(b.adf_v + (cN + nz0) * TB, adfv_top);
+        if (nz0 == L - 1) {                                  // interface nl is always the (zero) bottom
+            double z[TB];
 #pragma unroll
-        for (int t = 0; t < TB; ++t) {
-            b.adf_v[t][cN + nz0] = adfv_top[t];
-            if (nz0 == L - 1) b.adf_v[t][cN + L] = 0.0;  // interface nl is always the (zero) bottom
+            for (int t = 0; t < TB; ++t) z[t] = 0.0;
+            stv<TB>(b.adf_v + (cN + L) * TB, z);
         }
     }
     if (!valid) return;
-
-    // ---- phase B: ordered accumulation -----------------------------------------------------------
-    double losum[TB], pp[TB], pm[TB];
     const bool has_below = nz0 + 1 < L;
-#pragma unroll
-    for (int t = 0; t < TB; ++t) {
-        const double flo_bot = has_below ? s_vert[(2 * t) * nthr + threadIdx.x + 1] : 0.0;
-        const double adfv_bot = has_below ? s_vert[(2 * t + 1) * nthr + threadIdx.x + 1] : 0.0;
-        flo_top[t] = flo_top[t] - flo_bot;                                             // fv(nz)-fv(nz+1)
-        pp[t] = 0.0 + (dmax(0.0, adfv_top[t]) + dmax(0.0, -adfv_bot));                 // fct :291
-        pm[t] = 0.0 + (dmin(0.0, adfv_top[t]) + dmin(0.0, -adfv_bot));                 // fct :292
-        losum[t] = 0.0;
-    }
-    const int s1 = s_off[g + 1];
-    for (int s = s_off[g]; s < s1; ++s) {
-        const int z = __ldg(&m.ne_ent[s_slot[s].y]).z;
-        const int lo = z & 0xff, hi = (z >> 8) & 0xff;
-        if (nz < lo || nz > hi) continue;
-        const bool second = (z >> 16) & 1;
-        const double* f = s_flux + (size_t)s * TB * 2 * L + nz0;
-#pragma unroll
-        for (int t = 0; t < TB; ++t) {
-            const double flo = f[(2 * t) * L], adf = f[(2 * t + 1) * L];
-            if (!second) {
-                losum[t] = losum[t] + flo;                                              // driver :175
-                pp[t] = pp[t] + dmax(0.0, adf);                                         // fct :342
-                pm[t] = pm[t] + dmin(0.0, adf);                                         // fct :346
-            } else {
-                losum[t] = losum[t] - flo;                                              // driver :188
-                pp[t] = pp[t] + dmax(0.0, -adf);                                        // fct :360
-                pm[t] = pm[t] + dmin(0.0, -adf);                                        // fct :364
-            }
-        }
-    }
-    const double av = m.areasvol[cN + nz0], hn = m.hnode[oL], hnn = m.hnode_new[oL];
     const double r_av = 1.0 / av, r_hnn = 1.0 / hnn;
+    double lo_out[TB];
 #pragma unroll
     for (int t = 0; t < TB; ++t) {
-        const double num = b.ttf[t][oL] * hn + div_rcp((losum[t] + flo_top[t]) * dt, av, r_av);
-        b.lo[t][oL] = div_rcp(num, hnn, r_hnn);                                         // driver :249
-        b.plus[t][oL] = pp[t];
-        b.minus[t][oL] = pm[t];
+        const double flo_bot = has_below ? s_flo[t * nthr + tid + 1] : 0.0;
+        const double fv = flo_top[t] - flo_bot;                                          // fv(nz)-fv(nz+1)
+        const double num = tn[t] * hn + div_rcp((losum[t] + fv) * dt, av, r_av);
+        lo_out[t] = div_rcp(num, hnn, r_hnn);                                            // driver :249
     }
+    stv<TB>(b.lo + (size_t)oL * TB, lo_out);
 }
 
 // ----------------------------------------------------------------------------------------------
 // adv_tra_vert_impl (oce_adv_tra_ver.F90:120-236): one thread per owned column, Thomas algorithm.
-// cp/tp are kept in the (L,N) scratch arrays `cp`,`tp`.
+// cp/tp are kept in the (L,N) scratch arrays `cp`,`tp`; ttf is tracer t of a tb-interleaved array.
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_vert_impl(MeshDev m, double* __restrict__ ttf, double* __restrict__ cp,
-                                                   double* __restrict__ tp, double dt)
+__global__ void __launch_bounds__(128) k_vert_impl(MeshDev m, double* __restrict__ ttf, int tb, int t,
+                                                   double* __restrict__ cp, double* __restrict__ tp, double dt)
 {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= m.N) return;
@@ -544,7 +722,7 @@ __global__ void __launch_bounds__(128) k_vert_impl(MeshDev m, double* __restrict
     const double* area = m.area + (size_t)n * nl;
     const double* avol = m.areasvol + (size_t)n * nl;
     const double* hnn = m.hnode_new + (size_t)n * L;
-    double* T = ttf + (size_t)n * L;
+    double* T = ttf + (size_t)n * L * tb + t;   // tracer-interleaved fct_LO
     double* CP = cp + (size_t)n * L;
     double* TP = tp + (size_t)n * L;
     const double zinv = 1.0 * dt;
@@ -552,7 +730,7 @@ __global__ void __launch_bounds__(128) k_vert_impl(MeshDev m, double* __restrict
 #define AA(k) area[(k)-1]
 #define AV(k) avol[(k)-1]
 #define AH(k) hnn[(k)-1]
-#define AT(k) T[(k)-1]
+#define AT(k) T[((k)-1) * tb]
     double cp_prev = 0.0, tp_prev = 0.0;
     for (int nz = nzmin; nz <= nzmax - 1; ++nz) {
         double a, bb, c, tr, v_adv;
@@ -597,42 +775,96 @@ __global__ void __launch_bounds__(128) k_vert_impl(MeshDev m, double* __restrict
 }
 
 // ----------------------------------------------------------------------------------------------
-// K2: FCT bounds and limiter factors (owned nodes); needs lo on the halo.
-//   reference: oce_adv_tra_fct.F90:124-248 (a1-a3), :394-405 (b2)
-// plus/minus hold the raw P+/P- sums on entry and R+/R- on exit.
+// K2: FCT bounds, P+/P- sums and limiter factors (owned nodes); needs lo on the halo.
+//   reference: oce_adv_tra_fct.F90:124-248 (a1-a3), :265-377 (b1), :394-405 (b2)
+// The FCT cluster of a node (all nodes of its elements) is the node itself plus its edge
+// neighbours, each with the level range of the element(s) they share -- which is exactly the
+// scatter range stored with the edge slot -- so one gather serves the bounds and the P sums.
+// Output: pm = {R+, R-} per tracer.
 // ----------------------------------------------------------------------------------------------
-template <int TB>
-__global__ void __launch_bounds__(kBlock) k_fct_bounds(MeshDev m, TrBatch<TB> b, NodeRange r, double dt)
+template <int TB, int G>
+__global__ void __launch_bounds__(kBlock, ADV_K2_MINB) k_fct_bounds(MeshDev m, Chunk<TB> b, NodeRange r, double dt)
 {
     extern __shared__ double sm[];  // [2*TB][blockDim]: tvert_max, tvert_min
     const int L = m.L, nl = m.nl;
-    const ThreadCol tc = decode(m, r);
-    const int n = tc.n, nz0 = tc.nz0, nz = nz0 + 1;
-    const bool valid = tc.active && nz >= tc.nzmin && nz <= tc.nzmax - 1;
-    double tmax[TB], tmin[TB];
+    const NodeThread th = node_thread(m, r);
+    const int n = th.n, nz0 = th.nz0, nz = nz0 + 1;
+    const bool valid = th.active && nz >= th.nzmin && nz <= th.nzmax - 1;
+    const unsigned oL = (unsigned)n * L + nz0;
+    double tmax[TB], tmin[TB], pp[TB], pn[TB], lo_n[TB];
+    double av = 1.0, hnn = 1.0;
     if (valid) {
-        const uchar4 lv = m.node_lev[n];
-        const bool padded = nz < lv.z || nz > lv.w;   // some element of the cluster is dry at nz
+        // ---- all global loads of the first batch + the own column ------------------------------
+        const int4* ell = m.ne_ell + (size_t)n * m.ell_w;
+        int4 ent[G];
+        double lo_o[G][TB], t_o[G][TB], f[G][TB];
+        bool in[G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) ent[j] = (j < th.deg) ? __ldg(&ell[j]) : ADV_EMPTY_SLOT;
+        const size_t cN = (size_t)n * nl + nz0;
+        double tn[TB], vt[TB], vb[TB];
+        ldv<TB>(b.lo + (size_t)oL * TB, lo_n);
+#pragma unroll
+        for (int t = 0; t < TB; ++t) tn[t] = __ldg(&b.ttf[t][oL]);
+        ldv<TB>(b.adf_v + cN * TB, vt);
+        ldv<TB>(b.adf_v + (cN + 1) * TB, vb);
+        av = __ldg(&m.areasvol[cN]); hnn = __ldg(&m.hnode_new[oL]);
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const int lo = ent[j].z & 0xff, hi = (ent[j].z >> 8) & 0xff;
+            in[j] = nz >= lo && nz <= hi;
+#pragma unroll
+            for (int t = 0; t < TB; ++t) { lo_o[j][t] = 0.0; t_o[j][t] = 0.0; f[j][t] = 0.0; }
+            if (in[j]) {
+                const unsigned oo = (unsigned)ent[j].y * L + nz0;
+                ldv<TB>(b.adf_h + ((size_t)(unsigned)ent[j].x * L + nz0) * TB, f[j]);
+                ldv<TB>(b.lo + (size_t)oo * TB, lo_o[j]);
+#pragma unroll
+                for (int t = 0; t < TB; ++t) t_o[j][t] = __ldg(&b.ttf[t][oo]);
+            }
+        }
+        const bool padded = nz < th.pad_lo || nz > th.pad_hi;   // some element of the cluster is dry at nz
+        const bool self_in = nz >= th.self_lo && nz <= th.self_hi;
 #pragma unroll
         for (int t = 0; t < TB; ++t) {
-            tmax[t] = padded ? -1.0e3 : -CUDART_INF;  // bignumber, oce_adv_tra_fct.F90:100,159-176
+            tmax[t] = padded ? -1.0e3 : -CUDART_INF;        // bignumber, oce_adv_tra_fct.F90:100,159-176
             tmin[t] = padded ? 1.0e3 : CUDART_INF;
+            const double hi2 = dmax(lo_n[t], tn[t]), lo2 = dmin(lo_n[t], tn[t]);          // a1 :129-130
+            tmax[t] = (self_in && hi2 > tmax[t]) ? hi2 : tmax[t];
+            tmin[t] = (self_in && lo2 < tmin[t]) ? lo2 : tmin[t];
+            pp[t] = 0.0 + (dmax(0.0, vt[t]) + dmax(0.0, -vb[t]));                          // fct :291
+            pn[t] = 0.0 + (dmin(0.0, vt[t]) + dmin(0.0, -vb[t]));                          // fct :292
         }
-        const int k1 = m.cl_ptr[n + 1];
-        // branch-free body (an out-of-range entry is loaded and discarded) so that the unrolled
-        // iterations issue their loads together
-#pragma unroll 4
-        for (int k = m.cl_ptr[n]; k < k1; ++k) {
-            const int2 ent = __ldg(&m.cl_ent[k]);
-            const int lo = ent.y & 0xff, hi = (ent.y >> 8) & 0xff;
-            const bool inr = nz >= lo && nz <= hi;
-            const size_t o = (size_t)ent.x * L + nz0;
+        for (int j0 = 0;;) {
 #pragma unroll
-            for (int t = 0; t < TB; ++t) {
-                const double a = __ldg(&b.lo[t][o]), c = __ldg(&b.ttf[t][o]);
-                const double hi2 = dmax(a, c), lo2 = dmin(a, c);
-                tmax[t] = (inr && hi2 > tmax[t]) ? hi2 : tmax[t];   // a1 :129, a2 :166, a3 :209
-                tmin[t] = (inr && lo2 < tmin[t]) ? lo2 : tmin[t];
+            for (int j = 0; j < G; ++j) {
+                if (!in[j]) continue;
+                const bool second = (ent[j].z >> 16) & 1;
+#pragma unroll
+                for (int t = 0; t < TB; ++t) {
+                    const double hi2 = dmax(lo_o[j][t], t_o[j][t]), lo2 = dmin(lo_o[j][t], t_o[j][t]);
+                    tmax[t] = hi2 > tmax[t] ? hi2 : tmax[t];                  // a2 :166, a3 :209
+                    tmin[t] = lo2 < tmin[t] ? lo2 : tmin[t];
+                    const double a = second ? -f[j][t] : f[j][t];             // fct :342,:346 / :360,:364
+                    pp[t] = pp[t] + dmax(0.0, a);
+                    pn[t] = pn[t] + dmin(0.0, a);
+                }
+            }
+            j0 += G;
+            if (j0 >= th.deg) break;
+#pragma unroll
+            for (int j = 0; j < G; ++j) ent[j] = (j0 + j < th.deg) ? __ldg(&ell[j0 + j]) : ADV_EMPTY_SLOT;
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                const int lo = ent[j].z & 0xff, hi = (ent[j].z >> 8) & 0xff;
+                in[j] = nz >= lo && nz <= hi;
+                if (in[j]) {
+                    const unsigned oo = (unsigned)ent[j].y * L + nz0;
+                    ldv<TB>(b.adf_h + ((size_t)(unsigned)ent[j].x * L + nz0) * TB, f[j]);
+                    ldv<TB>(b.lo + (size_t)oo * TB, lo_o[j]);
+#pragma unroll
+                    for (int t = 0; t < TB; ++t) t_o[j][t] = __ldg(&b.ttf[t][oo]);
+                }
             }
         }
 #pragma unroll
@@ -643,10 +875,9 @@ __global__ void __launch_bounds__(kBlock) k_fct_bounds(MeshDev m, TrBatch<TB> b,
     }
     __syncthreads();
     if (!valid) return;
-    const size_t oL = (size_t)n * L + nz0;
-    const double av = m.areasvol[(size_t)n * nl + nz0], hnn = m.hnode_new[oL];
     const double r_av = 1.0 / av, r_hnn = 1.0 / hnn;
-    const bool edge_layer = (nz == tc.nzmin) || (nz == tc.nzmax - 1);   // :233-234, :245-247
+    const bool edge_layer = (nz == th.nzmin) || (nz == th.nzmax - 1);   // :233-234, :245-247
+    double* out = b.pm + (size_t)oL * TB * 2;
 #pragma unroll
     for (int t = 0; t < TB; ++t) {
         double vmax = tmax[t], vmin = tmin[t];
@@ -656,13 +887,25 @@ __global__ void __launch_bounds__(kBlock) k_fct_bounds(MeshDev m, TrBatch<TB> b,
             vmax = dmax(dmax(smax[-1], vmax), smax[1]);
             vmin = dmin(dmin(smin[-1], vmin), smin[1]);
         }
-        const double lo = b.lo[t][oL];
-        const double inc_max = vmax - lo, inc_min = vmin - lo;
-        double flux = div_rcp(div_rcp(b.plus[t][oL] * dt, av, r_av), hnn, r_hnn) + 1e-16;   // b2 :399
-        b.plus[t][oL] = dmin(1.0, inc_max / flux);
-        flux = div_rcp(div_rcp(b.minus[t][oL] * dt, av, r_av), hnn, r_hnn) - 1e-16;         // :401
-        b.minus[t][oL] = dmin(1.0, inc_min / flux);
+        const double inc_max = vmax - lo_n[t], inc_min = vmin - lo_n[t];
+        const double fp = div_rcp(div_rcp(pp[t] * dt, av, r_av), hnn, r_hnn) + 1e-16;   // b2 :399
+        const double fm = div_rcp(div_rcp(pn[t] * dt, av, r_av), hnn, r_hnn) - 1e-16;   // :401
+        reinterpret_cast<double2*>(out)[t] = make_double2(dmin(1.0, inc_max / fp), dmin(1.0, inc_min / fm));
     }
+}
+
+// limited vertical antidiffusive flux at interface k of a column (oce_adv_tra_fct.F90:425-455):
+// f = adf_v(k); (pa, ma) = R+/R- of layer k-1, (pk, mk) of layer k
+__device__ __forceinline__ double limit_v(double f, int k, int nzmin, int nzmax, double pa, double ma, double pk, double mk)
+{
+    double ae = 1.0;
+    if (k == nzmin) {                                                 // :430-438
+        ae = (f >= 0.0) ? dmin(ae, pk) : dmin(ae, mk);
+    } else if (k <= nzmax - 1) {                                      // :442-453
+        if (f >= 0.0) { ae = dmin(ae, ma); ae = dmin(ae, pk); }
+        else { ae = dmin(ae, pa); ae = dmin(ae, mk); }
+    }                                                                 // bottom interface untouched
+    return ae * f;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -670,79 +913,94 @@ __global__ void __launch_bounds__(kBlock) k_fct_bounds(MeshDev m, TrBatch<TB> b,
 // horizontal; halo nodes: the partial horizontal sums the reference's edge scatter leaves there.
 //   reference: oce_adv_tra_fct.F90:425-500 (b3), oce_adv_tra_driver.F90:529-633 (U1-U3)
 // ----------------------------------------------------------------------------------------------
-template <int TB>
-__global__ void __launch_bounds__(kBlock) k_fct_update(MeshDev m, TrBatch<TB> b, NodeRange r, double dt)
+template <int TB, int G>
+__global__ void __launch_bounds__(kBlock, ADV_K3_MINB) k_fct_update(MeshDev m, Chunk<TB> b, NodeRange r, double dt)
 {
-    extern __shared__ double sm[];  // [TB][blockDim]: limited vertical flux at the top interface
     const int L = m.L, nl = m.nl;
-    const ThreadCol tc = decode(m, r);
-    const int n = tc.n, nz0 = tc.nz0, nz = nz0 + 1;
-    const bool owned = n < m.N;
-    const bool valid = tc.active && nz >= tc.nzmin && nz <= tc.nzmax - 1;
-    const size_t oL = (size_t)n * L + nz0, cN = (size_t)n * nl;
-    double fv_top[TB];
-#pragma unroll
-    for (int t = 0; t < TB; ++t) fv_top[t] = 0.0;
-    if (tc.active && owned && nz >= tc.nzmin && nz <= tc.nzmax) {
-#pragma unroll
-        for (int t = 0; t < TB; ++t) {
-            const double f = b.adf_v[t][cN + nz0];
-            double ae = 1.0;
-            if (nz == tc.nzmin) {                                         // fct :430-438
-                ae = (f >= 0.0) ? dmin(ae, b.plus[t][oL]) : dmin(ae, b.minus[t][oL]);
-            } else if (nz <= tc.nzmax - 1) {                              // :442-453
-                if (f >= 0.0) { ae = dmin(ae, b.minus[t][oL - 1]); ae = dmin(ae, b.plus[t][oL]); }
-                else { ae = dmin(ae, b.plus[t][oL - 1]); ae = dmin(ae, b.minus[t][oL]); }
-            }                                                             // bottom interface untouched
-            fv_top[t] = ae * f;
-        }
-    }
-#pragma unroll
-    for (int t = 0; t < TB; ++t) sm[t * blockDim.x + threadIdx.x] = fv_top[t];
-    __syncthreads();
+    const NodeThread th = node_thread(m, r);
+    const int n = th.n, nz0 = th.nz0, nz = nz0 + 1;
+    const bool valid = th.active && nz >= th.nzmin && nz <= th.nzmax - 1;
     if (!valid) return;
-    const double av = m.areasvol[cN + nz0];
-    const double r_av = 1.0 / av;
-    const bool has_below = nz0 + 1 < L;
-    double dh[TB];
+    const bool owned = n < m.N;
+    const unsigned oL = (unsigned)n * L + nz0;
+    const size_t cN = (size_t)n * nl + nz0;
+    // ---- gather metadata first (its latency hides behind the vertical part) ----------------------
+    const int4* ell = m.ne_ell + (size_t)n * m.ell_w;
+    int4 ent[G];
+    double f[G][TB], po[G][TB], mo[G][TB];
+    bool in[G];
+#pragma unroll
+    for (int j = 0; j < G; ++j) ent[j] = (j < th.deg) ? __ldg(&ell[j]) : ADV_EMPTY_SLOT;
+    const double av = __ldg(&m.areasvol[cN]);
+    double pk[TB], mk[TB], dh[TB];
+    ldpm<TB>(b.pm + (size_t)oL * TB * 2, pk, mk);
 #pragma unroll
     for (int t = 0; t < TB; ++t) dh[t] = b.dttf_h[t][oL];
+    const double r_av = 1.0 / av;
+    // ---- vertical part (own column only), finished before the gather operands are loaded so that
+    //      the two register sets are never live together
     if (owned) {
-        const double hn = m.hnode[oL], hnn = m.hnode_new[oL];
+        double vt[TB], vb[TB], pa[TB], ma[TB], pb[TB], mb[TB], lo_n[TB], tn[TB], dv[TB];
+        const bool above = nz > th.nzmin, below = nz + 1 <= th.nzmax - 1;
+        ldv<TB>(b.adf_v + cN * TB, vt);
+        ldv<TB>(b.adf_v + (cN + 1) * TB, vb);
+        ldv<TB>(b.lo + (size_t)oL * TB, lo_n);
+#pragma unroll
+        for (int t = 0; t < TB; ++t) { pa[t] = ma[t] = pb[t] = mb[t] = 1.0; tn[t] = __ldg(&b.ttf[t][oL]); dv[t] = b.dttf_v[t][oL]; }
+        if (above) ldpm<TB>(b.pm + (size_t)(oL - 1) * TB * 2, pa, ma);
+        if (below) ldpm<TB>(b.pm + (size_t)(oL + 1) * TB * 2, pb, mb);
+        const double hn = __ldg(&m.hnode[oL]), hnn = __ldg(&m.hnode_new[oL]);
+        const bool has_below = nz0 + 1 < L;
 #pragma unroll
         for (int t = 0; t < TB; ++t) {
-            const double fv_bot = has_below ? sm[t * blockDim.x + threadIdx.x + 1] : 0.0;
-            double dv = b.dttf_v[t][oL];
-            dv = dv - b.ttf[t][oL] * hn + b.lo[t][oL] * hnn;              // driver :535
-            dv = dv + div_rcp((fv_top[t] - fv_bot) * dt, av, r_av);       // driver :556
-            b.dttf_v[t][oL] = dv;
+            const double fv_top = limit_v(vt[t], nz, th.nzmin, th.nzmax, pa[t], ma[t], pk[t], mk[t]);
+            const double fv_bot = has_below ? limit_v(vb[t], nz + 1, th.nzmin, th.nzmax, pk[t], mk[t], pb[t], mb[t]) : 0.0;
+            double d = dv[t];
+            d = d - tn[t] * hn + lo_n[t] * hnn;                           // driver :535
+            d = d + div_rcp((fv_top - fv_bot) * dt, av, r_av);            // driver :556
+            b.dttf_v[t][oL] = d;
         }
     }
-    const int k1 = m.ne_ptr[n + 1];
-    double pn[TB], mn[TB];
 #pragma unroll
-    for (int t = 0; t < TB; ++t) { pn[t] = __ldg(&b.plus[t][oL]); mn[t] = __ldg(&b.minus[t][oL]); }
-    // branch-free body: all four factors are loaded whatever the sign of the flux, out-of-range
-    // entries are loaded and discarded, so the unrolled iterations issue their loads together
-#pragma unroll 3
-    for (int k = m.ne_ptr[n]; k < k1; ++k) {
-        const int4 ent = __ldg(&m.ne_ent[k]);
-        const int lo = ent.z & 0xff, hi = (ent.z >> 8) & 0xff;
-        const bool inr = nz >= lo && nz <= hi;
-        const bool second = (ent.z >> 16) & 1;
-        const size_t oe = (size_t)ent.x * L + nz0, om = (size_t)ent.y * L + nz0;
+    for (int j = 0; j < G; ++j) {
+        const int lo = ent[j].z & 0xff, hi = (ent[j].z >> 8) & 0xff;
+        in[j] = nz >= lo && nz <= hi;
 #pragma unroll
-        for (int t = 0; t < TB; ++t) {
-            const double f = __ldg(&b.adf_h[t][oe]);
-            const double pmo = __ldg(&b.plus[t][om]), mmo = __ldg(&b.minus[t][om]);
-            const double p1 = second ? pmo : pn[t], m1 = second ? mmo : mn[t];   // factors at edges(1,e)
-            const double p2 = second ? pn[t] : pmo, m2 = second ? mn[t] : mmo;   // factors at edges(2,e)
-            double ae = 1.0;
-            if (f >= 0.0) { ae = dmin(ae, p1); ae = dmin(ae, m2); }       // fct :489-491
-            else { ae = dmin(ae, m1); ae = dmin(ae, p2); }                // :493-494
-            const double term = div_rcp(ae * f * dt, av, r_av);           // fct :497, driver :607,:620
-            const double nd = second ? dh[t] - term : dh[t] + term;
-            dh[t] = inr ? nd : dh[t];
+        for (int t = 0; t < TB; ++t) { f[j][t] = 0.0; po[j][t] = 1.0; mo[j][t] = 1.0; }
+        if (in[j]) {
+            ldv<TB>(b.adf_h + ((size_t)(unsigned)ent[j].x * L + nz0) * TB, f[j]);
+            ldpm<TB>(b.pm + ((size_t)(unsigned)ent[j].y * L + nz0) * TB * 2, po[j], mo[j]);
+        }
+    }
+    for (int j0 = 0;;) {
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            if (!in[j]) continue;
+            const bool second = (ent[j].z >> 16) & 1;
+#pragma unroll
+            for (int t = 0; t < TB; ++t) {
+                const double ff = f[j][t];
+                const double p1 = second ? po[j][t] : pk[t], m1 = second ? mo[j][t] : mk[t];   // factors at edges(1,e)
+                const double p2 = second ? pk[t] : po[j][t], m2 = second ? mk[t] : mo[j][t];   // factors at edges(2,e)
+                double ae = 1.0;
+                if (ff >= 0.0) { ae = dmin(ae, p1); ae = dmin(ae, m2); }      // fct :489-491
+                else { ae = dmin(ae, m1); ae = dmin(ae, p2); }                // :493-494
+                const double term = div_rcp(ae * ff * dt, av, r_av);          // fct :497, driver :607,:620
+                dh[t] = second ? dh[t] - term : dh[t] + term;
+            }
+        }
+        j0 += G;
+        if (j0 >= th.deg) break;
+#pragma unroll
+        for (int j = 0; j < G; ++j) ent[j] = (j0 + j < th.deg) ? __ldg(&ell[j0 + j]) : ADV_EMPTY_SLOT;
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const int lo = ent[j].z & 0xff, hi = (ent[j].z >> 8) & 0xff;
+            in[j] = nz >= lo && nz <= hi;
+            if (in[j]) {
+                ldv<TB>(b.adf_h + ((size_t)(unsigned)ent[j].x * L + nz0) * TB, f[j]);
+                ldpm<TB>(b.pm + ((size_t)(unsigned)ent[j].y * L + nz0) * TB * 2, po[j], mo[j]);
+            }
         }
     }
 #pragma unroll
@@ -754,11 +1012,11 @@ __global__ void __launch_bounds__(kBlock) k_fct_update(MeshDev m, TrBatch<TB> b,
 //   reference: oce_adv_tra_driver.F90:339-379, :387, :551-633 (vertical velocity is `we`, :358)
 // ----------------------------------------------------------------------------------------------
 template <int HOR, int VER, int TB>
-__global__ void __launch_bounds__(kBlock) k_nofct(MeshDev m, TrBatch<TB> b, NodeRange r, double dt)
+__global__ void __launch_bounds__(kBlock) k_nofct(MeshDev m, Chunk<TB> b, NodeRange r, double dt)
 {
     extern __shared__ double sm[];  // [TB][blockDim]
     const int L = m.L, nl = m.nl;
-    const ThreadCol tc = decode(m, r);
+    const NodeThread tc = node_thread(m, r);
     const int n = tc.n, nz0 = tc.nz0, nz = nz0 + 1;
     const bool owned = n < m.N;
     const bool valid = tc.active && nz >= tc.nzmin && nz <= tc.nzmax - 1;
@@ -781,10 +1039,12 @@ __global__ void __launch_bounds__(kBlock) k_nofct(MeshDev m, TrBatch<TB> b, Node
     for (int t = 0; t < TB; ++t) sm[t * blockDim.x + threadIdx.x] = fv_top[t];
     __syncthreads();
     if (tc.active && owned) {
+        stv<TB>(b.adf_v + (cN + nz0) * TB, fv_top);
+        if (nz0 == L - 1) {
+            double z[TB];
 #pragma unroll
-        for (int t = 0; t < TB; ++t) {
-            b.adf_v[t][cN + nz0] = fv_top[t];
-            if (nz0 == L - 1) b.adf_v[t][cN + L] = 0.0;
+            for (int t = 0; t < TB; ++t) z[t] = 0.0;
+            stv<TB>(b.adf_v + (cN + L) * TB, z);
         }
     }
     if (!valid) return;
@@ -823,12 +1083,16 @@ __global__ void __launch_bounds__(kBlock) k_nofct(MeshDev m, TrBatch<TB> b, Node
         for (int t = 0; t < TB; ++t) {
             const double tabm = b.ttfAB[t][om];
             const double a1 = second ? tabm : tabn[t], a2 = second ? tabn[t] : tabm;
-            const double* g = (HOR != HOR_UPW1) ? (b.grad[t] + oe * 4) : nullptr;
-            const double f = hor_ho<HOR>(a1, a2, q, qp, qm, ec, g, b.ph[t], second ? clo_m : clo_n,
+            double2 g12 = make_double2(0.0, 0.0), g34 = g12;
+            if (HOR != HOR_UPW1) {
+                const double2* gp = reinterpret_cast<const double2*>(b.grad[t]) + oe * 2;
+                g12 = __ldg(gp); g34 = __ldg(gp + 1);
+            }
+            const double f = hor_ho<HOR>(a1, a2, q, qp, qm, ec, g12, g34, b.ph[t], second ? clo_m : clo_n,
                                          second ? clo_n : clo_m, 0.0);
             const double term = div_rcp(f * dt, av, r_av);                          // driver :607,:620
             dh[t] = second ? dh[t] - term : dh[t] + term;
-            if (writer && owned) b.adf_h[t][oe] = f;
+            if (writer && owned) b.adf_h[oe * TB + t] = f;
         }
     }
 #pragma unroll
@@ -837,27 +1101,23 @@ __global__ void __launch_bounds__(kBlock) k_nofct(MeshDev m, TrBatch<TB> b, Node
 
 // ----------------------------------------------------------------------------------------------
 // halo pack (replaces the MPI_TYPE_INDEXED send types, gen_modules_partitioning.F90:462-473):
-// out[(i*nlev)+nz] = field[(slist[i])*nlev + nz]
+// one CTA per send column, out[i*nlev + k] = field[slist[i]*nlev + k]
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_pack_halo(const double* __restrict__ field, const int* __restrict__ slist,
-                                                      int count, int nlev, double* __restrict__ out)
+                                                      int nlev, double* __restrict__ out)
 {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)count * nlev) return;
-    const int i = (int)(idx / nlev), nz0 = (int)(idx - (long long)i * nlev);
-    out[idx] = field[(size_t)slist[i] * nlev + nz0];
+    const size_t src = (size_t)slist[blockIdx.x] * nlev, dst = (size_t)blockIdx.x * nlev;
+    for (int k = threadIdx.x; k < nlev; k += blockDim.x) out[dst + k] = field[src + k];
 }
 
 // dwarf epilogue (fesom.F90:105-125 with del_ttf reset per step): values += (dh+dv)/hnode_new
-__global__ void __launch_bounds__(kBlock) k_update_values(MeshDev m, double* __restrict__ values,
+__global__ void __launch_bounds__(kBlock) k_update_values(MeshDev m, NodeRange r, double* __restrict__ values,
                                                           const double* __restrict__ dh, const double* __restrict__ dv)
 {
-    const int L = m.L;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)m.N * L) return;
-    const int n = (int)(idx / L), nz = (int)(idx - (long long)n * L) + 1;
-    const uchar4 lv = m.node_lev[n];
-    if (nz < lv.x || nz > lv.y - 1) return;
+    const NodeThread th = node_thread(m, r);
+    const int nz = th.nz0 + 1;
+    if (!th.active || nz < th.nzmin || nz > th.nzmax - 1) return;
+    const size_t idx = (size_t)th.n * m.L + th.nz0;
     const double del = 0.0 + dh[idx] + dv[idx];
     values[idx] = values[idx] + del / m.hnode_new[idx];
 }

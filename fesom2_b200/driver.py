@@ -18,7 +18,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfesom_adv_b200.so")
+LIB_PATH = os.environ.get("FESOM_ADV_LIB") or os.path.join(_HERE, "libfesom_adv_b200.so")   # override: tuning builds only
 
 ADV_HOST, ADV_DEVICE = 0, 1
 ADV_ESCHEME = -3

@@ -150,8 +150,7 @@ void *adv_ctx_stream(adv_ctx_t *ctx);
 /* device-side duration [ms] of the last adv_do_oce_adv_tra[_async] call, measured with CUDA
  * events on the context's compute stream (valid after synchronisation) */
 int adv_ctx_last_elapsed_ms(adv_ctx_t *ctx, float *ms);
-/* per-phase kernel time of the last call [ms]: 0 volflux, 1 lo+adf, 2 bounds/R, 3 update, 4 halo
- * wait; valid only when profiling was switched on with adv_ctx_set_profiling(ctx, 1) */
+/* per-phase kernel time of the last call [ms]: 0 edge fluxes (+Q), 1 LO solution, 2 bounds/R, 3 update; valid only when profiling was switched on with adv_ctx_set_profiling(ctx, 1) */
 int adv_ctx_set_profiling(adv_ctx_t *ctx, int on);
 int adv_ctx_phase_ms(adv_ctx_t *ctx, float ms[8]);
 
