@@ -1,0 +1,270 @@
+!===============================================================================
+! oce_adv_tra_b200.F90 -- the thin ISO_C_BINDING layer between an unmodified FESOM2 host and
+! libfesom_adv_b200.so (include/fesom_adv_b200.h).
+!
+! Drop-in for the reference's external procedure
+!     subroutine do_oce_adv_tra(dt, vel, w, wi, we, tr_num, dynamics, tracers, partit, mesh)
+! (src/oce_adv_tra_driver.F90:46-490, interface module :1-21): same name, same argument list, same
+! in-place accumulation into tracers%work%del_ttf_advhoriz / del_ttf_advvert.  Link this file INSTEAD
+! of src/oce_adv_tra_driver.F90 (keep src/oce_adv_tra_{hor,ver,fct}.F90 out of the link as well: the
+! library replaces them) and add -lfesom_adv_b200 to the link line.  Nothing else in FESOM changes:
+! solve_tracers_ale (src/oce_ale_tracer.F90:312) and the dwarf (dwarf_ini/fesom.F90:97) call it as
+! before.
+!
+! Derived types with allocatable components are not C-interoperable, so this wrapper passes
+! c_loc() of every component the path reads plus the scalar dimensions.  It is shipped as source;
+! this image has no Fortran compiler, so it is compiled by the FESOM build (INTEGRATION.md).
+!
+! Batched entry: do_oce_adv_tra_b200_batch(dt, ..., tr_first, tr_last, ...) hands several tracers
+! to one library call so that geometry / volume-flux reads are amortised (RECOM-style runs).
+!===============================================================================
+module oce_adv_tra_b200
+  use, intrinsic :: iso_c_binding
+  implicit none
+  private
+  public :: adv_b200_init, adv_b200_finalize, do_oce_adv_tra_b200_batch, adv_b200_ctx
+
+  integer(c_int), parameter :: ADV_OK = 0, ADV_ESCHEME = -3
+  integer(c_int), parameter :: ADV_HOST = 0, ADV_DEVICE = 1
+
+  ! adv_mesh_desc_t (include/fesom_adv_b200.h)
+  type, bind(C) :: adv_mesh_desc_t
+     integer(c_int32_t) :: nl
+     integer(c_int32_t) :: myDim_nod2D, eDim_nod2D
+     integer(c_int32_t) :: myDim_elem2D, eDim_elem2D
+     integer(c_int32_t) :: myDim_edge2D
+     integer(c_int32_t) :: nod_in_elem2D_ld
+     type(c_ptr) :: edges, edge_tri, elem2D_nodes, nod_in_elem2D, nod_in_elem2D_num
+     type(c_ptr) :: nlevels, ulevels, nlevels_nod2D, ulevels_nod2D
+     type(c_ptr) :: edge_cross_dxdy, edge_dxdy, elem_cos, area, areasvol, nboundary_lay
+     integer(c_int32_t) :: mype, npes
+     integer(c_int32_t) :: rPEnum
+     type(c_ptr) :: rPE, rptr, rlist
+     integer(c_int32_t) :: sPEnum
+     type(c_ptr) :: sPE, sptr, slist
+  end type adv_mesh_desc_t
+
+  ! adv_state_desc_t
+  type, bind(C) :: adv_state_desc_t
+     type(c_ptr) :: uv, w, w_e, w_i, helem, hnode, hnode_new, zbar_3d_n, Z_3d_n, zbar_n_bot
+     integer(c_int32_t) :: use_wsplit
+  end type adv_state_desc_t
+
+  ! adv_tracer_desc_t
+  type, bind(C) :: adv_tracer_desc_t
+     type(c_ptr) :: values, valuesAB, edge_up_dn_grad, del_ttf_advhoriz, del_ttf_advvert
+     type(c_ptr) :: tra_adv_hor, tra_adv_ver, tra_adv_lim
+     real(c_double) :: tra_adv_ph, tra_adv_pv
+  end type adv_tracer_desc_t
+
+  interface
+     integer(c_int) function adv_ctx_create(ctx, mesh, device, max_tracers) bind(C, name='adv_ctx_create')
+       import :: c_int, c_ptr, adv_mesh_desc_t
+       type(c_ptr), intent(out) :: ctx
+       type(adv_mesh_desc_t), intent(in) :: mesh
+       integer(c_int), value :: device, max_tracers
+     end function
+     integer(c_int) function adv_ctx_destroy(ctx) bind(C, name='adv_ctx_destroy')
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+     end function
+     type(c_ptr) function adv_last_error() bind(C, name='adv_last_error')
+       import :: c_ptr
+     end function
+     integer(c_int) function adv_comm_unique_id(id) bind(C, name='adv_comm_unique_id')
+       import :: c_int, c_char
+       character(kind=c_char) :: id(128)
+     end function
+     integer(c_int) function adv_ctx_comm_init(ctx, id) bind(C, name='adv_ctx_comm_init')
+       import :: c_int, c_ptr, c_char
+       type(c_ptr), value :: ctx
+       character(kind=c_char) :: id(128)
+     end function
+     integer(c_int) function adv_ctx_set_state(ctx, st, where) bind(C, name='adv_ctx_set_state')
+       import :: c_int, c_ptr, adv_state_desc_t
+       type(c_ptr), value :: ctx
+       type(adv_state_desc_t), intent(in) :: st
+       integer(c_int), value :: where
+     end function
+     integer(c_int) function adv_do_oce_adv_tra(ctx, dt, ntr, tr, where) bind(C, name='adv_do_oce_adv_tra')
+       import :: c_int, c_ptr, c_double, adv_tracer_desc_t
+       type(c_ptr), value :: ctx
+       real(c_double), value :: dt
+       integer(c_int), value :: ntr
+       type(adv_tracer_desc_t), intent(in) :: tr(*)
+       integer(c_int), value :: where
+     end function
+  end interface
+
+  type(c_ptr), save :: adv_b200_ctx = c_null_ptr   ! one context per MPI rank (one rank <-> one GPU)
+
+contains
+
+  !-----------------------------------------------------------------------------
+  ! Call once after oce_adv_tra_fct_init / muscl_adv_init (src/oce_setup_step.F90:239): uploads the
+  ! static mesh slice, builds the gather lists and the NCCL communicator.
+  !-----------------------------------------------------------------------------
+  subroutine adv_b200_init(tracers, partit, mesh, device)
+    use MOD_MESH
+    use MOD_TRACER
+    use MOD_PARTIT
+    use MOD_PARSUP
+    use mpi
+    type(t_tracer), intent(inout), target :: tracers
+    type(t_partit), intent(inout), target :: partit
+    type(t_mesh),   intent(in),    target :: mesh
+    integer,        intent(in)            :: device
+    type(adv_mesh_desc_t) :: d
+    character(kind=c_char) :: id(128)
+    integer :: rc, ierr
+
+    d%nl = mesh%nl
+    d%myDim_nod2D = partit%myDim_nod2D;   d%eDim_nod2D = partit%eDim_nod2D
+    d%myDim_elem2D = partit%myDim_elem2D; d%eDim_elem2D = partit%eDim_elem2D
+    d%myDim_edge2D = partit%myDim_edge2D
+    d%nod_in_elem2D_ld = size(mesh%nod_in_elem2D, 1)
+    d%edges = c_loc(mesh%edges);                 d%edge_tri = c_loc(mesh%edge_tri)
+    d%elem2D_nodes = c_loc(mesh%elem2D_nodes);   d%nod_in_elem2D = c_loc(mesh%nod_in_elem2D)
+    d%nod_in_elem2D_num = c_loc(mesh%nod_in_elem2D_num)
+    d%nlevels = c_loc(mesh%nlevels);             d%ulevels = c_loc(mesh%ulevels)
+    d%nlevels_nod2D = c_loc(mesh%nlevels_nod2D); d%ulevels_nod2D = c_loc(mesh%ulevels_nod2D)
+    d%edge_cross_dxdy = c_loc(mesh%edge_cross_dxdy); d%edge_dxdy = c_loc(mesh%edge_dxdy)
+    d%elem_cos = c_loc(mesh%elem_cos)
+    d%area = c_loc(mesh%area);                   d%areasvol = c_loc(mesh%areasvol)
+    d%nboundary_lay = c_loc(tracers%work%nboundary_lay)
+    d%mype = partit%mype; d%npes = partit%npes
+    d%rPEnum = partit%com_nod2D%rPEnum
+    d%rPE = c_loc(partit%com_nod2D%rPE); d%rptr = c_loc(partit%com_nod2D%rptr); d%rlist = c_loc(partit%com_nod2D%rlist)
+    d%sPEnum = partit%com_nod2D%sPEnum
+    d%sPE = c_loc(partit%com_nod2D%sPE); d%sptr = c_loc(partit%com_nod2D%sptr); d%slist = c_loc(partit%com_nod2D%slist)
+
+    rc = adv_ctx_create(adv_b200_ctx, d, int(device, c_int), int(tracers%num_tracers, c_int))
+    call check(rc, partit)
+    if (partit%npes > 1) then
+       if (partit%mype == 0) call check(adv_comm_unique_id(id), partit)
+       call MPI_Bcast(id, 128, MPI_BYTE, 0, partit%MPI_COMM_FESOM, ierr)   ! replaces init_mpi_types for this path
+       call check(adv_ctx_comm_init(adv_b200_ctx, id), partit)
+    end if
+  end subroutine adv_b200_init
+
+  subroutine adv_b200_finalize()
+    integer :: rc
+    if (c_associated(adv_b200_ctx)) rc = adv_ctx_destroy(adv_b200_ctx)
+    adv_b200_ctx = c_null_ptr
+  end subroutine adv_b200_finalize
+
+  !-----------------------------------------------------------------------------
+  ! tracers tr_first..tr_last in ONE library call.  use_device=.true.: the arrays are resident on
+  ! the GPU (OpenACC build: call inside `!$ACC HOST_DATA USE_DEVICE(...)`, the dwarf's convention,
+  ! fesom.F90:71-83); .false.: host arrays, the library copies in and out.
+  !-----------------------------------------------------------------------------
+  subroutine do_oce_adv_tra_b200_batch(dt, vel, w, wi, we, tr_first, tr_last, dynamics, tracers, partit, mesh, use_device)
+    use MOD_MESH
+    use MOD_TRACER
+    use MOD_PARTIT
+    use MOD_PARSUP
+    use MOD_DYN
+    real(kind=WP),  intent(in),    target :: dt
+    integer,        intent(in)            :: tr_first, tr_last
+    type(t_partit), intent(inout), target :: partit
+    type(t_mesh),   intent(in),    target :: mesh
+    type(t_tracer), intent(inout), target :: tracers
+    type(t_dyn),    intent(inout), target :: dynamics
+    real(kind=WP),  intent(in),    target :: vel(2, mesh%nl-1, partit%myDim_elem2D+partit%eDim_elem2D)
+    real(kind=WP),  intent(in),    target :: W(mesh%nl,  partit%myDim_nod2D+partit%eDim_nod2D)
+    real(kind=WP),  intent(in),    target :: WI(mesh%nl, partit%myDim_nod2D+partit%eDim_nod2D)
+    real(kind=WP),  intent(in),    target :: WE(mesh%nl, partit%myDim_nod2D+partit%eDim_nod2D)
+    logical,        intent(in)            :: use_device
+    type(adv_state_desc_t) :: st
+    type(adv_tracer_desc_t), allocatable :: td(:)
+    character(kind=c_char, len=21), allocatable, target :: hs(:), vs(:), ls(:)
+    integer :: i, k, n, rc
+    integer(c_int) :: where
+
+    where = merge(ADV_DEVICE, ADV_HOST, use_device)
+    st%uv = c_loc(vel); st%w = c_loc(W); st%w_e = c_loc(WE); st%w_i = c_loc(WI)
+    st%helem = c_loc(mesh%helem); st%hnode = c_loc(mesh%hnode); st%hnode_new = c_loc(mesh%hnode_new)
+    st%zbar_3d_n = c_loc(mesh%zbar_3d_n); st%Z_3d_n = c_loc(mesh%Z_3d_n); st%zbar_n_bot = c_loc(mesh%zbar_n_bot)
+    st%use_wsplit = merge(1, 0, dynamics%use_wsplit)
+    call check(adv_ctx_set_state(adv_b200_ctx, st, where), partit)
+
+    n = tr_last - tr_first + 1
+    allocate(td(n), hs(n), vs(n), ls(n))
+    do k = 1, n
+       i = tr_first + k - 1
+       hs(k) = trim(tracers%data(i)%tra_adv_hor)//c_null_char
+       vs(k) = trim(tracers%data(i)%tra_adv_ver)//c_null_char
+       ls(k) = trim(tracers%data(i)%tra_adv_lim)//c_null_char
+       td(k)%values   = c_loc(tracers%data(i)%values)
+       td(k)%valuesAB = c_loc(tracers%data(i)%valuesAB)
+       ! one edge_up_dn_grad / del_ttf_adv* work array exists per t_tracer in the reference
+       ! (MOD_TRACER.F90:36,64); a batched host keeps one per tracer of the batch
+       td(k)%edge_up_dn_grad  = c_loc(tracers%work%edge_up_dn_grad)
+       td(k)%del_ttf_advhoriz = c_loc(tracers%work%del_ttf_advhoriz)
+       td(k)%del_ttf_advvert  = c_loc(tracers%work%del_ttf_advvert)
+       td(k)%tra_adv_hor = c_loc(hs(k)); td(k)%tra_adv_ver = c_loc(vs(k)); td(k)%tra_adv_lim = c_loc(ls(k))
+       td(k)%tra_adv_ph = tracers%data(i)%tra_adv_ph
+       td(k)%tra_adv_pv = tracers%data(i)%tra_adv_pv
+    end do
+    rc = adv_do_oce_adv_tra(adv_b200_ctx, real(dt, c_double), int(n, c_int), td, where)
+    call check(rc, partit)
+    deallocate(td, hs, vs, ls)
+  end subroutine do_oce_adv_tra_b200_batch
+
+  !-----------------------------------------------------------------------------
+  ! error convention of the reference: message on rank 0 + par_ex(comm, mype, 1) -> MPI_ABORT
+  ! (src/oce_adv_tra_driver.F90:351-353, src/gen_modules_partitioning.F90:87-123)
+  !-----------------------------------------------------------------------------
+  subroutine check(rc, partit)
+    use MOD_PARTIT
+    use MOD_PARSUP
+    integer(c_int), intent(in) :: rc
+    type(t_partit), intent(inout) :: partit
+    character(kind=c_char), pointer :: msg(:)
+    integer :: k
+    if (rc == ADV_OK) return
+    call c_f_pointer(adv_last_error(), msg, [512])
+    if (partit%mype == 0) then
+       do k = 1, 512
+          if (msg(k) == c_null_char) exit
+       end do
+       write(*,*) 'fesom_adv_b200: ', msg(1:k-1)
+    end if
+    call par_ex(partit%MPI_COMM_FESOM, partit%mype, 1)
+  end subroutine check
+
+end module oce_adv_tra_b200
+
+!===============================================================================
+! The reference's seam, unchanged: same external procedure name and argument list as
+! src/oce_adv_tra_driver.F90:46.  One tracer per call, like the reference.
+!===============================================================================
+subroutine do_oce_adv_tra(dt, vel, w, wi, we, tr_num, dynamics, tracers, partit, mesh)
+  use MOD_MESH
+  use MOD_TRACER
+  use MOD_PARTIT
+  use MOD_PARSUP
+  use MOD_DYN
+  use oce_adv_tra_b200
+  implicit none
+  real(kind=WP),  intent(in),    target :: dt
+  integer,        intent(in)            :: tr_num
+  type(t_partit), intent(inout), target :: partit
+  type(t_mesh),   intent(in),    target :: mesh
+  type(t_tracer), intent(inout), target :: tracers
+  type(t_dyn),    intent(inout), target :: dynamics
+  real(kind=WP),  intent(in)            :: vel(2, mesh%nl-1, partit%myDim_elem2D+partit%eDim_elem2D)
+  real(kind=WP),  intent(in), target    :: W(mesh%nl,    partit%myDim_nod2D+partit%eDim_nod2D)
+  real(kind=WP),  intent(in), target    :: WI(mesh%nl,   partit%myDim_nod2D+partit%eDim_nod2D)
+  real(kind=WP),  intent(in), target    :: WE(mesh%nl,   partit%myDim_nod2D+partit%eDim_nod2D)
+#ifdef ENABLE_OPENACC
+  ! operands live in the enclosing `!$ACC DATA` region (fesom.F90:71-83 / fesom_module.F90:759-805)
+  !$ACC HOST_DATA USE_DEVICE(vel, W, WI, WE, mesh%helem, mesh%hnode, mesh%hnode_new, mesh%zbar_3d_n, mesh%Z_3d_n) &
+  !$ACC           USE_DEVICE(tracers%data(tr_num)%values, tracers%data(tr_num)%valuesAB) &
+  !$ACC           USE_DEVICE(tracers%work%edge_up_dn_grad, tracers%work%del_ttf_advhoriz, tracers%work%del_ttf_advvert)
+  call do_oce_adv_tra_b200_batch(dt, vel, W, WI, WE, tr_num, tr_num, dynamics, tracers, partit, mesh, .true.)
+  !$ACC END HOST_DATA
+#else
+  call do_oce_adv_tra_b200_batch(dt, vel, W, WI, WE, tr_num, tr_num, dynamics, tracers, partit, mesh, .false.)
+#endif
+end subroutine do_oce_adv_tra

@@ -8,7 +8,7 @@
  * PARITY UNPINNED: the reference cannot be compiled in this environment (no Fortran compiler,
  * no MPI) and ships no golden vector / known-answer test for this path.
  * The restatement is pinned only by invariants and by an independently written NumPy
- * restatement (tests/test_oracle_*.py).
+ * restatement (oracle/numpy_ref.py, tests/test_oracle_pinning.py, tests/test_multirank_cpu.py).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library.

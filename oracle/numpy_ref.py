@@ -1,0 +1,253 @@
+"""oracle/numpy_ref.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+A second, independently written restatement of the reference's tracer advection
+(src/oce_adv_tra_driver.F90:46-646, src/oce_adv_tra_hor.F90:64-834, src/oce_adv_tra_ver.F90:244-434,
+:635-695, src/oce_adv_tra_fct.F90:72-512) in vectorised NumPy: whole-array masks and
+``np.add.at`` scatters instead of the Fortran loops the C oracle (adv_oracle.c) transcribes.  It
+exists to pin the C oracle: two restatements written in different styles
+must agree to round-off.  Scatter order is kept serial (``np.add.at`` is unbuffered and processes
+indices in order; node 1 and node 2 of an edge are interleaved), so the agreement is in practice
+exact.
+
+Covers: hor UPW1 / MUSCL / MFCT, ver UPW1 / QR4C / CDIFF, lim FCT / none, use_wsplit = False,
+one rank.  Arrays are (column, level) = transposes of the Fortran shapes; levels are 1-based in
+masks (``lev``).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+R_EARTH = 6367500.0   # src/oce_modules.F90:29
+
+
+class NumpyAdv:
+    def __init__(self, mesh, state, nboundary_lay):
+        m = self.m = mesh
+        self.L, self.nl, self.N, self.Nh, self.E = m.L, m.nl, m.N, m.Nh, m.E
+        f = lambda t: np.asarray(t.detach().cpu().numpy() if hasattr(t, "detach") else t, dtype=np.float64)
+        self.uv, self.w, self.we = f(state.uv), f(state.w), f(state.w_e)
+        self.helem, self.hnode, self.hnode_new = f(state.helem), f(state.hnode), f(state.hnode_new)
+        self.zbar, self.Z = f(state.zbar_3d_n), f(state.Z_3d_n)
+        self.nb = np.asarray(nboundary_lay)
+        L = self.L
+        self.lev = np.arange(1, L + 1)[None, :]                     # layer index nz
+        self.n1 = m.edges[:, 0].astype(np.int64) - 1
+        self.n2 = m.edges[:, 1].astype(np.int64) - 1
+        self.el1 = m.edge_tri[:, 0].astype(np.int64) - 1
+        self.has2 = m.edge_tri[:, 1] > 0
+        self.el2 = np.where(self.has2, m.edge_tri[:, 1].astype(np.int64) - 1, 0)
+        nu1 = m.ulevels[self.el1][:, None]; nl1 = (m.nlevels[self.el1] - 1)[:, None]
+        nu2 = np.where(self.has2, m.ulevels[self.el2], 0)[:, None]
+        nl2 = np.where(self.has2, m.nlevels[self.el2] - 1, 0)[:, None]
+        nl12, nu12 = np.minimum(nl1, nl2), np.maximum(nu1, nu2)
+        lev = self.lev
+        # level ranges A-E of oce_adv_tra_hor.F90:127-160
+        A = (lev >= nu1) & (lev <= nu12 - 1)
+        B = (nu2 > 0) & (lev >= nu2) & (lev <= nu12 - 1)
+        Cc = (lev >= nu12) & (lev <= nl12)
+        D = (lev >= nl12 + 1) & (lev <= nl1)
+        Ee = (lev >= nl12 + 1) & (lev <= nl2)
+        self.use1, self.use2 = A | Cc | D, B | Cc | Ee
+        # scatter range of oce_adv_tra_driver.F90:154-156
+        lo = np.where(nu2 > 0, np.minimum(nu1, nu2), nu1)
+        self.scat = (lev >= lo) & (lev <= np.maximum(nl1, nl2))
+        uln = m.ulevels_nod2D[:, None]; nln = m.nlevels_nod2D[:, None]
+        self.nvalid = (lev >= uln) & (lev <= nln - 1)               # (Nh, L) valid layers of a node
+        self.uln, self.nln = uln, nln
+        a = R_EARTH * m.elem_cos[self.el1]
+        a = np.where(self.has2, 0.5 * (a + R_EARTH * m.elem_cos[self.el2]), a)
+        self.cx = m.edge_dxdy[:, 0] * a
+        self.cy = m.edge_dxdy[:, 1] * R_EARTH
+
+    # ------------------------------------------------------------------ horizontal
+    def volflux(self):
+        c = self.m.edge_cross_dxdy
+        u1, v1 = self.uv[self.el1, :, 0], self.uv[self.el1, :, 1]
+        u2, v2 = self.uv[self.el2, :, 0], self.uv[self.el2, :, 1]
+        f1 = (-v1 * c[:, 0:1] + u1 * c[:, 1:2]) * self.helem[self.el1]
+        f2 = (v2 * c[:, 2:3] - u2 * c[:, 3:4]) * self.helem[self.el2]
+        return np.where(self.use1 & self.use2, f1 + f2, np.where(self.use1, f1, np.where(self.use2, f2, 0.0)))
+
+    def hor_upw1(self, ttf, Q, flux_in):
+        t1, t2 = ttf[self.n1], ttf[self.n2]
+        new = -0.5 * (t1 * (Q + np.abs(Q)) + t2 * (Q - np.abs(Q))) - flux_in
+        return np.where(self.use1 | self.use2, new, flux_in)
+
+    def hor_ho(self, kind, ttf, grad, Q, num_ord, flux_in):
+        if kind == "UPW1":
+            return self.hor_upw1(ttf, Q, flux_in)
+        t1, t2 = ttf[self.n1], ttf[self.n2]
+        cx, cy = self.cx[:, None], self.cy[:, None]
+        d = 2.0 * (t2 - t1)
+        Tm2 = (d + cx * grad[:, :, 1] + cy * grad[:, :, 3]) / 6.0
+        Tm1 = (d + cx * grad[:, :, 0] + cy * grad[:, :, 2]) / 6.0
+        if kind == "MUSCL":                                              # c_lo, oce_adv_tra_hor.F90:411-412
+            Tm1 = Tm1 * np.where(self.nb[self.n1][:, None] - self.lev >= 0, 1.0, 0.0)
+            Tm2 = Tm2 * np.where(self.nb[self.n2][:, None] - self.lev >= 0, 1.0, 0.0)
+        Tmean1, Tmean2 = t1 + Tm1, t2 - Tm2
+        cHO = (Q + np.abs(Q)) * Tmean1 + (Q - np.abs(Q)) * Tmean2
+        new = -0.5 * (1.0 - num_ord) * cHO - Q * num_ord * 0.5 * (Tmean1 + Tmean2) - flux_in
+        return np.where(self.use1 | self.use2, new, flux_in)
+
+    def scatter_edges(self, acc, contrib):
+        """acc(n1) += c, acc(n2) -= c per edge in ascending order (oce_adv_tra_driver.F90:142-201)."""
+        c = np.where(self.scat, contrib, 0.0)
+        idx = np.stack([self.n1, self.n2], 1).ravel()
+        val = np.stack([c, -c], 1).reshape(-1, self.L)
+        np.add.at(acc, idx, val)
+
+    # ------------------------------------------------------------------ vertical (nl interfaces)
+    def _iface(self):
+        k = np.arange(1, self.nl + 1)[None, :]
+        return k, self.uln[: self.N], self.nln[: self.N]
+
+    def ver_upw1(self, w, ttf, flux_in):
+        N, L, nl = self.N, self.L, self.nl
+        k, nzmin, nzmax = self._iface()
+        t = np.zeros((N, nl + 1)); t[:, 1:L + 1] = ttf[:N]             # t[:, k] = ttf(k), t[:,0] unused
+        tk, tkm1 = t[:, 1:], t[:, :-1]
+        W, A = w[:N], self.m.area[:N]
+        out = flux_in.copy()
+        top = k == nzmin
+        out = np.where(top, -W * tk * A - out, out)
+        out = np.where(k == nzmax, 0.0 - out, out)
+        mid = (k >= nzmin + 1) & (k <= nzmax - 1)
+        out = np.where(mid, -0.5 * (tk * (W + np.abs(W)) + tkm1 * (W - np.abs(W))) * A - out, out)
+        return out
+
+    def ver_cdiff(self, w, ttf, flux_in):
+        N, L, nl = self.N, self.L, self.nl
+        k, nzmin, nzmax = self._iface()
+        t = np.zeros((N, nl + 1)); t[:, 1:L + 1] = ttf[:N]
+        tk, tkm1 = t[:, 1:], t[:, :-1]
+        W, A = w[:N], self.m.area[:N]
+        tv = np.where(k == nzmin, -W * tk * A, -(0.5 * (tkm1 + tk)) * W * A)
+        return np.where((k >= nzmin) & (k <= nzmax - 1), tv - flux_in, flux_in)
+
+    def ver_qr4c(self, w, ttf, num_ord, flux_in):
+        N, L, nl = self.N, self.L, self.nl
+        k, nzmin, nzmax = self._iface()
+        pad = lambda a: np.concatenate([np.zeros((N, 2)), a[:N, :L], np.zeros((N, 2))], 1)   # index k+1 -> level k
+        t, Z = pad(ttf), pad(self.Z)
+        g = lambda a, s: a[:, 2 + s: 2 + s + nl]                       # a(k+s) for k = 1..nl
+        t0, tm1, tm2, tp1 = g(t, 0), g(t, -1), g(t, -2), g(t, 1)
+        z0, zm1, zm2, zp1 = g(Z, 0), g(Z, -1), g(Z, -2), g(Z, 1)
+        W, A, zb = w[:N], self.m.area[:N], self.zbar[:N]
+        out = flux_in.copy()
+        out = np.where(k == nzmin, -t0 * W * A - out, out)
+        cen = -0.5 * (tm1 + t0) * W * A
+        out = np.where(k == nzmin + 1, cen - out, out)
+        out = np.where(k == nzmax - 1, cen - out, out)
+        out = np.where(k == nzmax, 0.0 - out, out)
+        inner = (k >= nzmin + 2) & (k <= nzmax - 2)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            qc = (tm1 - t0) / (zm1 - z0)
+            qu = (t0 - tp1) / (z0 - zp1)
+            qd = (tm2 - tm1) / (zm2 - zm1)
+            T1 = t0 + (2 * qc + qu) * (zb - z0) / 3.0
+            T2 = tm1 + (2 * qc + qd) * (zb - zm1) / 3.0
+            Tm = (W + np.abs(W)) * T1 + (W - np.abs(W)) * T2
+            val = (-0.5 * (1.0 - num_ord) * Tm - num_ord * (0.5 * (T1 + T2)) * W) * A - out
+        return np.where(inner, val, out)
+
+    def ver(self, kind, w, ttf, num_ord, flux_in):
+        if kind == "UPW1":
+            return self.ver_upw1(w, ttf, flux_in)
+        if kind == "QR4C":
+            return self.ver_qr4c(w, ttf, num_ord, flux_in)
+        if kind == "CDIFF":
+            return self.ver_cdiff(w, ttf, flux_in)
+        raise ValueError(kind)
+
+    # ------------------------------------------------------------------ FCT limiter
+    def fct(self, dt, ttf, lo, adf_h, adf_v):
+        m, N, L = self.m, self.N, self.L
+        big = 1.0e3
+        tmax, tmin = np.maximum(lo, ttf), np.minimum(lo, ttf)           # a1
+        en = m.elem2D_nodes.astype(np.int64) - 1
+        emask = (self.lev >= m.ulevels[:, None]) & (self.lev <= (m.nlevels - 1)[:, None])
+        amax = np.where(emask, np.maximum.reduce([tmax[en[:, j]] for j in range(3)]), -big)   # a2 (AUX)
+        amin = np.where(emask, np.minimum.reduce([tmin[en[:, j]] for j in range(3)]), big)
+        tvmax = np.full((N, L), -np.inf); tvmin = np.full((N, L), np.inf)
+        for j in range(m.nod_in_elem2D.shape[1]):                        # a3
+            have = (j < m.nod_in_elem2D_num[:N])[:, None]
+            el = np.where(have[:, 0], m.nod_in_elem2D[:N, j].astype(np.int64) - 1, 0)
+            tvmax = np.where(have, np.maximum(tvmax, amax[el]), tvmax)
+            tvmin = np.where(have, np.minimum(tvmin, amin[el]), tvmin)
+        nzmin, nzmax = self.uln[:N], self.nln[:N]
+        lev = self.lev
+        sh = lambda a, s, fill: np.concatenate([np.full((N, 1), fill), a, np.full((N, 1), fill)], 1)[:, 1 + s:1 + s + L]
+        inner = (lev >= nzmin + 1) & (lev <= nzmax - 2)
+        vmax = np.where(inner, np.maximum.reduce([sh(tvmax, -1, -np.inf), tvmax, sh(tvmax, 1, -np.inf)]), tvmax)
+        vmin = np.where(inner, np.minimum.reduce([sh(tvmin, -1, np.inf), tvmin, sh(tvmin, 1, np.inf)]), tvmin)
+        valid = self.nvalid[:N]
+        inc_max = np.where(valid, vmax - lo[:N], 0.0)
+        inc_min = np.where(valid, vmin - lo[:N], 0.0)
+        plus = np.zeros((self.Nh, L)); minus = np.zeros((self.Nh, L))
+        plus[:N] = np.where(valid, np.maximum(0.0, adf_v[:, :L]) + np.maximum(0.0, -adf_v[:, 1:L + 1]), 0.0)
+        minus[:N] = np.where(valid, np.minimum(0.0, adf_v[:, :L]) + np.minimum(0.0, -adf_v[:, 1:L + 1]), 0.0)
+        idx = np.stack([self.n1, self.n2], 1).ravel()
+        f = np.where(self.scat, adf_h, 0.0)
+        np.add.at(plus, idx, np.stack([np.maximum(0.0, f), np.maximum(0.0, -f)], 1).reshape(-1, L))
+        np.add.at(minus, idx, np.stack([np.minimum(0.0, f), np.minimum(0.0, -f)], 1).reshape(-1, L))
+        av, hn = m.areasvol[:N, :L], self.hnode_new[:N]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            Rp = np.where(valid, np.minimum(1.0, inc_max / (plus[:N] * dt / av / hn + 1e-16)), 0.0)
+            Rm = np.where(valid, np.minimum(1.0, inc_min / (minus[:N] * dt / av / hn - 1e-16)), 0.0)
+        # b3 vertical
+        k = np.arange(1, self.nl + 1)[None, :]
+        pk = np.concatenate([Rp, np.ones((N, 1))], 1); mk = np.concatenate([Rm, np.ones((N, 1))], 1)
+        pa = np.concatenate([np.ones((N, 1)), Rp], 1); ma = np.concatenate([np.ones((N, 1)), Rm], 1)   # layer k-1
+        pos = adf_v >= 0.0
+        ae_top = np.where(pos, np.minimum(1.0, pk), np.minimum(1.0, mk))
+        ae_mid = np.where(pos, np.minimum(np.minimum(1.0, ma), pk), np.minimum(np.minimum(1.0, pa), mk))
+        ae = np.where(k == nzmin, ae_top, np.where((k >= nzmin + 1) & (k <= nzmax - 1), ae_mid, 1.0))
+        adf_v = ae * adf_v
+        return Rp, Rm, adf_v
+
+    def limit_h(self, adf_h, Rp_all, Rm_all):
+        p1, m1, p2, m2 = Rp_all[self.n1], Rm_all[self.n1], Rp_all[self.n2], Rm_all[self.n2]
+        ae = np.where(adf_h >= 0.0, np.minimum(np.minimum(1.0, p1), m2), np.minimum(np.minimum(1.0, m1), p2))
+        return np.where(self.scat, ae * adf_h, adf_h)
+
+    # ------------------------------------------------------------------ driver
+    def do_oce_adv_tra(self, dt, tr, dttf_h, dttf_v):
+        """one tracer; accumulates into dttf_h / dttf_v (Nh, L) like the reference"""
+        m, N, L, nl = self.m, self.N, self.L, self.nl
+        f = lambda t: np.asarray(t.detach().cpu().numpy() if hasattr(t, "detach") else t, dtype=np.float64)
+        ttf, ttfAB, grad = f(tr.values), f(tr.valuesAB), f(tr.edge_up_dn_grad)
+        Q = self.volflux()
+        fct = tr.tra_adv_lim.strip() == "FCT"
+        zE, zV = np.zeros((self.E, L)), np.zeros((N, nl))
+        valid = self.nvalid[:N]
+        av = m.areasvol[:N, :L]
+        if fct:
+            flo_h = self.hor_upw1(ttf, Q, zE)
+            lo = np.zeros((self.Nh, L))
+            self.scatter_edges(lo, flo_h)
+            flo_v = self.ver_upw1(self.we, ttf, zV)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                lo_new = (ttf[:N] * self.hnode[:N] + (lo[:N] + (flo_v[:, :L] - flo_v[:, 1:L + 1])) * dt / av) / self.hnode_new[:N]
+            lo = np.where(self.nvalid, 0.0, 0.0)
+            lo[:N] = np.where(valid, lo_new, 0.0)
+            adf_h = self.hor_ho(tr.tra_adv_hor.strip(), ttfAB, grad, Q, tr.tra_adv_ph, flo_h)
+            adf_v = self.ver(tr.tra_adv_ver.strip(), self.w, ttfAB, tr.tra_adv_pv, flo_v)
+            Rp, Rm, adf_v = self.fct(dt, ttf, lo, adf_h, adf_v)
+            Rp_all = np.zeros((self.Nh, L)); Rm_all = np.zeros((self.Nh, L))
+            Rp_all[:N], Rm_all[:N] = Rp, Rm
+            adf_h = self.limit_h(adf_h, Rp_all, Rm_all)
+            dttf_v[:N] = np.where(valid, dttf_v[:N] - ttf[:N] * self.hnode[:N] + lo[:N] * self.hnode_new[:N], dttf_v[:N])
+            self.keep = dict(fct_LO=lo, fct_plus=Rp_all, fct_minus=Rm_all)
+        else:
+            adf_h = self.hor_ho(tr.tra_adv_hor.strip(), ttfAB, grad, Q, tr.tra_adv_ph, zE)
+            adf_v = self.ver(tr.tra_adv_ver.strip(), self.we, ttfAB, tr.tra_adv_pv, zV)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            dttf_v[:N] = np.where(valid, dttf_v[:N] + (adf_v[:, :L] - adf_v[:, 1:L + 1]) * dt / av, dttf_v[:N])
+        # U3: per edge, node 1 then node 2, addend (flux*dt)/areasvol(nz,node)
+        c = np.where(self.scat, adf_h, 0.0) * dt
+        idx = np.stack([self.n1, self.n2], 1).ravel()
+        a1, a2 = m.areasvol[self.n1, :L], m.areasvol[self.n2, :L]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            val = np.stack([np.where(self.scat, c / a1, 0.0), np.where(self.scat, -(c / a2), 0.0)], 1).reshape(-1, L)
+        np.add.at(dttf_h, idx, val)
+        return dttf_h, dttf_v
