@@ -131,7 +131,7 @@ struct adv_ctx {
     DevBuf<double> area, areasvol, Q;
     int nS = 0, nI = 0, nSH = 0;
     int pf_dist = 0;                          // L2 prefetch distance in CTAs (ADV_PF; 0 = off)
-    int g_lo = 6, g_k2 = 3, g_k3 = 3;         // gather batch sizes (tunable: ADV_G_LO / ADV_G_K2 / ADV_G_K3)
+    int g_lo = 2, g_k2 = 1, g_k3 = 1;         // gather batch sizes (tunable: ADV_G_LO / ADV_G_K2 / ADV_G_K3)
     std::vector<Peer> rpeers, speers;
     int send_cols = 0;
     // state (ADV_HOST staging)
@@ -285,9 +285,9 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
     adv_ctx* c = new adv_ctx();
     c->device = device; c->max_tr = max_tracers; c->mype = d->mype; c->npes = std::max(1, d->npes);
     if (const char* v = getenv("ADV_PF")) c->pf_dist = std::max(0, atoi(v));
-    if (const char* v = getenv("ADV_G_LO")) c->g_lo = atoi(v) == 3 ? 3 : 6;
-    if (const char* v = getenv("ADV_G_K2")) c->g_k2 = atoi(v) == 6 ? 6 : 3;
-    if (const char* v = getenv("ADV_G_K3")) c->g_k3 = atoi(v) == 6 ? 6 : 3;
+    if (const char* v = getenv("ADV_G_LO")) c->g_lo = atoi(v);
+    if (const char* v = getenv("ADV_G_K2")) c->g_k2 = atoi(v);
+    if (const char* v = getenv("ADV_G_K3")) c->g_k3 = atoi(v);
 #define CUF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { delete c; return fail(ADV_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
     CUF(c->ne_ptr.upload(ne_ptr)); CUF(c->ne_ent.upload(ne_ent));
     CUF(c->node_lev.upload(node_lev)); CUF(c->node_rec.upload(node_rec)); CUF(c->ne_ell.upload(ne_ell));
@@ -482,14 +482,19 @@ int launch_phase(adv_ctx* c, Phase ph, int hor, int ver, bool q_stored, const Ch
     if (ph == PH_N1) {
 #define N1(V) if (ver == V) { const size_t smn = (size_t)n1_smem_arrays<V, TB>() * nthr * sizeof(double); \
                               if (c->g_lo == 6) k_node_lo<V, TB, 6><<<grid, nthr, smn, s>>>(m, b, r, dt); \
+                              else if (c->g_lo == 2) k_node_lo<V, TB, 2><<<grid, nthr, smn, s>>>(m, b, r, dt); \
                               else k_node_lo<V, TB, 3><<<grid, nthr, smn, s>>>(m, b, r, dt); }
         N1(VER_UPW1) N1(VER_QR4C) N1(VER_PPM) N1(VER_CDIFF)
 #undef N1
     } else if (ph == PH_K2) {
         if (c->g_k2 == 6) k_fct_bounds<TB, 6><<<grid, nthr, 2 * sm1, s>>>(m, b, r, dt);
+        else if (c->g_k2 == 2) k_fct_bounds<TB, 2><<<grid, nthr, 2 * sm1, s>>>(m, b, r, dt);
+        else if (c->g_k2 == 1) k_fct_bounds<TB, 1><<<grid, nthr, 2 * sm1, s>>>(m, b, r, dt);
         else k_fct_bounds<TB, 3><<<grid, nthr, 2 * sm1, s>>>(m, b, r, dt);
     } else if (ph == PH_K3) {
         if (c->g_k3 == 6) k_fct_update<TB, 6><<<grid, nthr, 0, s>>>(m, b, r, dt);
+        else if (c->g_k3 == 2) k_fct_update<TB, 2><<<grid, nthr, 0, s>>>(m, b, r, dt);
+        else if (c->g_k3 == 1) k_fct_update<TB, 1><<<grid, nthr, 0, s>>>(m, b, r, dt);
         else k_fct_update<TB, 3><<<grid, nthr, 0, s>>>(m, b, r, dt);
     } else {
 #define HV(H, V) if (hor == H && ver == V) k_nofct<H, V, TB><<<grid, nthr, sm1, s>>>(m, b, r, dt);

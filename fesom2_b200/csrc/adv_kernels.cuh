@@ -39,17 +39,20 @@ enum { HOR_UPW1 = 0, HOR_MUSCL = 1, HOR_MFCT = 2 };
 enum { VER_UPW1 = 0, VER_QR4C = 1, VER_PPM = 2, VER_CDIFF = 3 };
 
 constexpr int kBlock = 256;
+// minimum resident CTAs per SM (register caps): measured on B200, see DESIGN.md section 4 --
+// occupancy beats register-resident batching: 4-5 CTAs of 7 warps with a few spilled words run
+// 20-30 % faster than 2 CTAs without spills (gpurun_out/exp_mb*.log, profiles/r1_tuning.md)
 #ifndef ADV_E1_MINB
 #define ADV_E1_MINB 4
 #endif
 #ifndef ADV_N1_MINB
-#define ADV_N1_MINB 2
+#define ADV_N1_MINB 5
 #endif
 #ifndef ADV_K2_MINB
-#define ADV_K2_MINB 2
+#define ADV_K2_MINB 4
 #endif
 #ifndef ADV_K3_MINB
-#define ADV_K3_MINB 2
+#define ADV_K3_MINB 4
 #endif
 
 struct MeshDev {
