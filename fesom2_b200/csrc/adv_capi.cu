@@ -4,7 +4,7 @@
 // There is deliberately no CPU path in this file: every entry point needs a CUDA device.
 #include "../../include/fesom_adv_b200.h"
 #include "adv_kernels.cuh"
-#include "adv_staged.cuh"
+#include "adv_pipe.cuh"
 
 #include <nccl.h>   // types only: the library is resolved at run time (see NcclApi)
 #include <dlfcn.h>
@@ -133,11 +133,12 @@ struct adv_ctx {
     int nS = 0, nI = 0, nSH = 0;
     int pf_dist = 0;                          // L2 prefetch distance in CTAs (ADV_PF; 0 = off)
     int g_lo = 2, g_k2 = 1, g_k3 = 1;         // gather batch sizes (tunable: ADV_G_LO / ADV_G_K2 / ADV_G_K3)
-    // shared-memory staged kernels (adv_staged.cuh): bit 0 E1, 1 N1, 2 K2, 3 K3 (ADV_STAGED, default all)
-    int staged = 15;
-    int cpb_s = 1;                            // columns per CTA of the staged kernels
+    // pipelined multi-group kernels (adv_pipe.cuh): bit 0 E1, 1 N1, 2 K2, 3 K3 (ADV_PIPE)
+    int pipe = 15;
+    int e1_ng = 8, e1_depth = 3;              // edge groups per CTA / cp.async stages (ADV_E1_NG, ADV_E1_D)
+    int nd_ng = 8;                            // node groups per CTA (ADV_ND_NG)
+    int k3_depth = 1;                         // stages of the pipelined node kernels (ADV_K3_D)
     int max_smem_optin = 0;
-    int sr_max[5][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}};   // per range id: max distinct node / edge columns per CTA
     std::vector<Peer> rpeers, speers;
     int send_cols = 0;
     // state (ADV_HOST staging)
@@ -170,27 +171,6 @@ static int parse_scheme(const char* s, const char* const* names, const int* code
     for (int i = 0; i < n; ++i)
         if (strcmp(buf, names[i]) == 0) return codes[i];
     return -1;
-}
-
-// upper bounds of the distinct node / edge columns one CTA of `cpb` consecutive range entries
-// touches (sizes the shared-memory slots of the staged node kernels)
-static void range_max_distinct(const std::vector<int>& ne_ptr, const std::vector<int4>& ne_ent, const int* list, int begin,
-                               int count, int cpb, int out[2])
-{
-    std::vector<int> nodes, edges;
-    size_t mn = 1, me = 1;
-    for (int k0 = 0; k0 < count; k0 += cpb) {
-        nodes.clear(); edges.clear();
-        for (int k = k0; k < std::min(count, k0 + cpb); ++k) {
-            const int n = list ? list[begin + k] : begin + k;
-            nodes.push_back(n);
-            for (int q = ne_ptr[n]; q < ne_ptr[n + 1]; ++q) { nodes.push_back(ne_ent[q].y); edges.push_back(ne_ent[q].x); }
-        }
-        std::sort(nodes.begin(), nodes.end()); std::sort(edges.begin(), edges.end());
-        mn = std::max<size_t>(mn, std::unique(nodes.begin(), nodes.end()) - nodes.begin());
-        me = std::max<size_t>(me, std::unique(edges.begin(), edges.end()) - edges.begin());
-    }
-    out[0] = (int)mn; out[1] = (int)me;
 }
 
 enum RangeId { R_ALL = 0, R_S, R_I, R_SH, R_ALLH };
@@ -317,9 +297,11 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
     if (const char* v = getenv("ADV_G_LO")) c->g_lo = atoi(v);
     if (const char* v = getenv("ADV_G_K2")) c->g_k2 = atoi(v);
     if (const char* v = getenv("ADV_G_K3")) c->g_k3 = atoi(v);
-    if (const char* v = getenv("ADV_STAGED")) c->staged = atoi(v);
-    c->cpb_s = std::max(1, std::min(kBlock / L, 8));
-    if (const char* v = getenv("ADV_CPB_S")) c->cpb_s = std::max(1, std::min(kBlock / L, atoi(v)));
+    if (const char* v = getenv("ADV_PIPE")) c->pipe = atoi(v);
+    if (const char* v = getenv("ADV_E1_NG")) c->e1_ng = std::max(1, atoi(v));
+    if (const char* v = getenv("ADV_E1_D")) c->e1_depth = std::max(2, std::min(4, atoi(v)));
+    if (const char* v = getenv("ADV_ND_NG")) c->nd_ng = std::max(1, atoi(v));
+    if (const char* v = getenv("ADV_K3_D")) c->k3_depth = atoi(v) >= 2 ? 2 : 1;
     cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
 #define CUF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { delete c; return fail(ADV_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
     CUF(c->ne_ptr.upload(ne_ptr)); CUF(c->ne_ent.upload(ne_ent));
@@ -369,12 +351,8 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
         SH = S;
         for (int n = N; n < Nh; ++n) SH.push_back(n);
         c->nS = (int)S.size(); c->nI = (int)I.size(); c->nSH = (int)SH.size();
-        range_max_distinct(ne_ptr, ne_ent, S.data(), 0, c->nS, c->cpb_s, c->sr_max[R_S]);
-        range_max_distinct(ne_ptr, ne_ent, I.data(), 0, c->nI, c->cpb_s, c->sr_max[R_I]);
-        range_max_distinct(ne_ptr, ne_ent, SH.data(), 0, c->nSH, c->cpb_s, c->sr_max[R_SH]);
         CUF(c->list_S.upload(S)); CUF(c->list_I.upload(I)); CUF(c->list_SH.upload(SH)); CUF(c->slist.upload(sl));
     }
-    range_max_distinct(ne_ptr, ne_ent, nullptr, 0, N, c->cpb_s, c->sr_max[R_ALL]);
     c->slots.resize(max_tracers);
     c->trloc.resize(max_tracers);
     CUF(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
@@ -519,14 +497,13 @@ static NodeRange node_range(const adv_ctx* c, int rid, int cpb)
     }
 }
 
-// the staged kernels need 16-byte aligned field pointers (cp.async.bulk); anything else runs on the
-// register-gather kernels
+// the pipelined kernels copy 16-byte cells from the caller's edge_up_dn_grad / uv (cp.async needs the
+// alignment); anything else runs on the register-gather kernels
 template <int TB>
 static bool chunk_aligned(const MeshDev& m, const Chunk<TB>& b)
 {
-    uintptr_t x = (uintptr_t)m.uv | (uintptr_t)m.helem | (uintptr_t)m.w | (uintptr_t)m.we | (uintptr_t)m.hnode |
-                  (uintptr_t)m.hnode_new | (uintptr_t)m.zbar3d | (uintptr_t)m.Z3d | (uintptr_t)m.area | (uintptr_t)m.areasvol;
-    for (int t = 0; t < TB; ++t) x |= (uintptr_t)b.ttf[t] | (uintptr_t)b.ttfAB[t] | (uintptr_t)b.grad[t];
+    uintptr_t x = (uintptr_t)m.uv;
+    for (int t = 0; t < TB; ++t) x |= (uintptr_t)b.grad[t];
     return (x & 15u) == 0;
 }
 
@@ -535,100 +512,85 @@ int launch_phase(adv_ctx* c, Phase ph, int hor, int ver, bool q_stored, const Ch
 {
     const MeshDev& m = c->m;
     cudaStream_t s = c->s_comp;
-    const bool aligned = chunk_aligned<TB>(m, b);
     cudaError_t se = cudaSuccess;
+    bool piped = false;
+    int grid = 0, nthr = 0;
     if (ph == PH_E1) {
-        bool staged = (c->staged & 1) && aligned;
-        const int epb_s = c->cpb_s;
-        if (staged) {
-            const int grid = nblocks(m.E, epb_s), nthr = epb_s * m.L;
-            bool done = false;
-#define E1S(H, Q) if (!done && hor == H && (q_stored ? 1 : 0) == Q) { \
-                const size_t sm = e1_layout(m.L, epb_s, TB, H, Q).total; \
+        const int epb = cols_per_block(m.L);
+        nthr = epb * m.L;
+        if ((c->pipe & 1) && chunk_aligned<TB>(m, b)) {
+            const int ng = std::max(1, std::min(c->e1_ng, nthr / epb));
+            const int nge = epb * ng, D = c->e1_depth;
+            grid = nblocks(m.E, nge);
+#define E1P(H, Q, DD) if (!piped && hor == H && (q_stored ? 1 : 0) == Q && D == DD) { \
+                const size_t sm = e1p_smem_bytes<H, TB, Q>(nge, nthr, DD); \
                 if ((int)sm <= c->max_smem_optin) { \
-                    se = smem_optin(k_edge_flux_s<H, TB, Q>, sm); \
-                    if (se == cudaSuccess) k_edge_flux_s<H, TB, Q><<<grid, nthr, sm, s>>>(m, b, epb_s); \
-                    done = true; } }
-            E1S(HOR_UPW1, 0) E1S(HOR_UPW1, 1) E1S(HOR_MUSCL, 0) E1S(HOR_MUSCL, 1) E1S(HOR_MFCT, 0) E1S(HOR_MFCT, 1)
-#undef E1S
-            staged = done;
+                    se = smem_optin(k_edge_flux_p<H, TB, Q, DD>, sm); \
+                    if (se == cudaSuccess) k_edge_flux_p<H, TB, Q, DD><<<grid, nthr, sm, s>>>(m, b, epb, ng); \
+                    piped = true; } }
+#define E1PD(H, Q) E1P(H, Q, 2) E1P(H, Q, 3) E1P(H, Q, 4)
+            E1PD(HOR_UPW1, 0) E1PD(HOR_UPW1, 1) E1PD(HOR_MUSCL, 0) E1PD(HOR_MUSCL, 1) E1PD(HOR_MFCT, 0) E1PD(HOR_MFCT, 1)
+#undef E1PD
+#undef E1P
         }
-        if (!staged) {
-            const int epb = cols_per_block(m.L), grid = nblocks(m.E, epb), nthr = epb * m.L;
+        if (!piped) {
+            grid = nblocks(m.E, epb);
 #define E1(H) if (hor == H) { if (q_stored) k_edge_flux<H, TB, 1><<<grid, nthr, 0, s>>>(m, b, epb, c->pf_dist); \
                               else k_edge_flux<H, TB, 0><<<grid, nthr, 0, s>>>(m, b, epb, c->pf_dist); }
             E1(HOR_UPW1) E1(HOR_MUSCL) E1(HOR_MFCT)
 #undef E1
         }
-        ++c->launches;
-        if (se != cudaSuccess) return fail(ADV_ECUDA, std::string("k_edge_flux_s attributes: ") + cudaGetErrorString(se));
-        if (cudaError_t e = cudaGetLastError()) return fail(ADV_ECUDA, std::string("launch k_edge_flux: ") + cudaGetErrorString(e));
-        return ADV_OK;
-    }
-    const int bit = ph == PH_N1 ? 2 : ph == PH_K2 ? 4 : ph == PH_K3 ? 8 : 0;
-    bool staged = (c->staged & bit) && aligned && rid != R_ALLH;
-    if (staged) {
-        StageRange sr{node_range(c, rid, c->cpb_s), c->sr_max[rid][0], c->sr_max[rid][1]};
-        if (sr.r.count <= 0) return ADV_OK;
-        const int grid = nblocks(sr.r.count, sr.r.cpb), nthr = sr.r.cpb * m.L;
-        bool done = false;
-        if (ph == PH_N1) {
-#define N1S(V) if (!done && ver == V) { const size_t sm = n1_layout<V, TB>(m.L, m.nl, sr.r.cpb, m.ell_w, sr.ns_max, sr.es_max).total; \
-                if ((int)sm <= c->max_smem_optin) { se = smem_optin(k_node_lo_s<V, TB>, sm); \
-                    if (se == cudaSuccess) k_node_lo_s<V, TB><<<grid, nthr, sm, s>>>(m, b, sr, dt); done = true; } }
-            N1S(VER_UPW1) N1S(VER_QR4C) N1S(VER_PPM) N1S(VER_CDIFF)
-#undef N1S
-        } else if (ph == PH_K2) {
-            const size_t sm = k2_layout<TB>(m.L, sr.r.cpb, m.ell_w, sr.ns_max, sr.es_max).total;
+    } else {
+        const NodeRange r = node_range(c, rid, cols_per_block(m.L));
+        if (r.count <= 0) return ADV_OK;
+        nthr = r.cpb * m.L;
+        const int ng = std::max(1, c->nd_ng), cn = r.cpb * ng;
+        const size_t sm1 = (size_t)TB * nthr * sizeof(double);
+        if (ph == PH_K3 && (c->pipe & 8)) {
+            const int D = c->k3_depth;
+            const size_t sm = k3p_smem_bytes<TB>(cn, m.ell_w, nthr, D);
             if ((int)sm <= c->max_smem_optin) {
-                se = smem_optin(k_fct_bounds_s<TB>, sm);
-                if (se == cudaSuccess) k_fct_bounds_s<TB><<<grid, nthr, sm, s>>>(m, b, sr, dt);
-                done = true;
-            }
-        } else {
-            const size_t sm = k3_layout<TB>(m.L, sr.r.cpb, m.ell_w, sr.ns_max, sr.es_max).total;
-            if ((int)sm <= c->max_smem_optin) {
-                se = smem_optin(k_fct_update_s<TB>, sm);
-                if (se == cudaSuccess) k_fct_update_s<TB><<<grid, nthr, sm, s>>>(m, b, sr, dt);
-                done = true;
+                grid = nblocks(r.count, cn);
+                if (D == 2) { se = smem_optin(k_fct_update_p<TB, 2>, sm); if (se == cudaSuccess) k_fct_update_p<TB, 2><<<grid, nthr, sm, s>>>(m, b, r, ng, dt); }
+                else { se = smem_optin(k_fct_update_p<TB, 1>, sm); if (se == cudaSuccess) k_fct_update_p<TB, 1><<<grid, nthr, sm, s>>>(m, b, r, ng, dt); }
+                piped = true;
             }
         }
-        staged = done;
-        if (se != cudaSuccess) return fail(ADV_ECUDA, std::string("staged kernel attributes: ") + cudaGetErrorString(se));
-    }
-    const NodeRange r = node_range(c, rid, cols_per_block(m.L));
-    if (r.count <= 0) return ADV_OK;
-    const int grid = nblocks(r.count, r.cpb), nthr = r.cpb * m.L;
-    const size_t sm1 = (size_t)TB * nthr * sizeof(double);
-    if (staged) {
-    } else if (ph == PH_N1) {
+        if (piped) {
+        } else if (ph == PH_N1) {
+            grid = nblocks(r.count, r.cpb);
 #define N1(V) if (ver == V) { const size_t smn = (size_t)n1_smem_arrays<V, TB>() * nthr * sizeof(double); \
                               if (c->g_lo == 6) k_node_lo<V, TB, 6><<<grid, nthr, smn, s>>>(m, b, r, dt); \
                               else if (c->g_lo == 2) k_node_lo<V, TB, 2><<<grid, nthr, smn, s>>>(m, b, r, dt); \
                               else k_node_lo<V, TB, 3><<<grid, nthr, smn, s>>>(m, b, r, dt); }
-        N1(VER_UPW1) N1(VER_QR4C) N1(VER_PPM) N1(VER_CDIFF)
+            N1(VER_UPW1) N1(VER_QR4C) N1(VER_PPM) N1(VER_CDIFF)
 #undef N1
-    } else if (ph == PH_K2) {
-        if (c->g_k2 == 6) k_fct_bounds<TB, 6><<<grid, nthr, 2 * sm1, s>>>(m, b, r, dt);
-        else if (c->g_k2 == 2) k_fct_bounds<TB, 2><<<grid, nthr, 2 * sm1, s>>>(m, b, r, dt);
-        else if (c->g_k2 == 1) k_fct_bounds<TB, 1><<<grid, nthr, 2 * sm1, s>>>(m, b, r, dt);
-        else k_fct_bounds<TB, 3><<<grid, nthr, 2 * sm1, s>>>(m, b, r, dt);
-    } else if (ph == PH_K3) {
-        if (c->g_k3 == 6) k_fct_update<TB, 6><<<grid, nthr, 0, s>>>(m, b, r, dt);
-        else if (c->g_k3 == 2) k_fct_update<TB, 2><<<grid, nthr, 0, s>>>(m, b, r, dt);
-        else if (c->g_k3 == 1) k_fct_update<TB, 1><<<grid, nthr, 0, s>>>(m, b, r, dt);
-        else k_fct_update<TB, 3><<<grid, nthr, 0, s>>>(m, b, r, dt);
-    } else {
+        } else if (ph == PH_K2) {
+            grid = nblocks(r.count, r.cpb);
+            if (c->g_k2 == 6) k_fct_bounds<TB, 6><<<grid, nthr, 2 * sm1, s>>>(m, b, r, dt);
+            else if (c->g_k2 == 2) k_fct_bounds<TB, 2><<<grid, nthr, 2 * sm1, s>>>(m, b, r, dt);
+            else if (c->g_k2 == 1) k_fct_bounds<TB, 1><<<grid, nthr, 2 * sm1, s>>>(m, b, r, dt);
+            else k_fct_bounds<TB, 3><<<grid, nthr, 2 * sm1, s>>>(m, b, r, dt);
+        } else if (ph == PH_K3) {
+            grid = nblocks(r.count, r.cpb);
+            if (c->g_k3 == 6) k_fct_update<TB, 6><<<grid, nthr, 0, s>>>(m, b, r, dt);
+            else if (c->g_k3 == 2) k_fct_update<TB, 2><<<grid, nthr, 0, s>>>(m, b, r, dt);
+            else if (c->g_k3 == 1) k_fct_update<TB, 1><<<grid, nthr, 0, s>>>(m, b, r, dt);
+            else k_fct_update<TB, 3><<<grid, nthr, 0, s>>>(m, b, r, dt);
+        } else {
+            grid = nblocks(r.count, r.cpb);
 #define HV(H, V) if (hor == H && ver == V) k_nofct<H, V, TB><<<grid, nthr, sm1, s>>>(m, b, r, dt);
-        HV(HOR_UPW1, VER_UPW1) HV(HOR_UPW1, VER_QR4C) HV(HOR_UPW1, VER_PPM) HV(HOR_UPW1, VER_CDIFF)
-        HV(HOR_MUSCL, VER_UPW1) HV(HOR_MUSCL, VER_QR4C) HV(HOR_MUSCL, VER_PPM) HV(HOR_MUSCL, VER_CDIFF)
-        HV(HOR_MFCT, VER_UPW1) HV(HOR_MFCT, VER_QR4C) HV(HOR_MFCT, VER_PPM) HV(HOR_MFCT, VER_CDIFF)
+            HV(HOR_UPW1, VER_UPW1) HV(HOR_UPW1, VER_QR4C) HV(HOR_UPW1, VER_PPM) HV(HOR_UPW1, VER_CDIFF)
+            HV(HOR_MUSCL, VER_UPW1) HV(HOR_MUSCL, VER_QR4C) HV(HOR_MUSCL, VER_PPM) HV(HOR_MUSCL, VER_CDIFF)
+            HV(HOR_MFCT, VER_UPW1) HV(HOR_MFCT, VER_QR4C) HV(HOR_MFCT, VER_PPM) HV(HOR_MFCT, VER_CDIFF)
 #undef HV
+        }
     }
     ++c->launches;
+    static const char* names[] = {"k_edge_flux", "k_node_lo", "k_fct_bounds", "k_fct_update", "k_nofct"};
+    if (se != cudaSuccess) return fail(ADV_ECUDA, std::string(names[ph]) + "_p attributes: " + cudaGetErrorString(se));
     if (cudaError_t e = cudaGetLastError()) {
-        static const char* names[] = {"k_edge_flux", "k_node_lo", "k_fct_bounds", "k_fct_update", "k_nofct"};
-        return fail(ADV_ECUDA, std::string("launch ") + names[ph] + (staged ? "_s" : "") + " (grid " + std::to_string(grid) + ", block " + std::to_string(nthr) +
+        return fail(ADV_ECUDA, std::string("launch ") + names[ph] + (piped ? "_p" : "") + " (grid " + std::to_string(grid) + ", block " + std::to_string(nthr) +
                                    ", hor " + std::to_string(hor) + ", ver " + std::to_string(ver) + ", tb " + std::to_string(TB) + "): " + cudaGetErrorString(e));
     }
     return ADV_OK;
