@@ -5,6 +5,8 @@
 #include "../../include/fesom_adv_b200.h"
 #include "adv_kernels.cuh"
 #include "adv_pipe.cuh"
+#include "adv_slot.cuh"
+#include "adv_lean.cuh"
 
 #include <nccl.h>   // types only: the library is resolved at run time (see NcclApi)
 #include <dlfcn.h>
@@ -129,15 +131,20 @@ struct adv_ctx {
     DevBuf<int4> ne_ell;
     DevBuf<double4> edge_cross;
     DevBuf<double2> edge_c;
-    DevBuf<double> area, areasvol, Q;
+    DevBuf<double> area, areasvol, r_areasvol, Q;
     int nS = 0, nI = 0, nSH = 0;
     int pf_dist = 0;                          // L2 prefetch distance in CTAs (ADV_PF; 0 = off)
-    int g_lo = 2, g_k2 = 1, g_k3 = 1;         // gather batch sizes (tunable: ADV_G_LO / ADV_G_K2 / ADV_G_K3)
+    int g_lo = 2, g_k2 = 1, g_k3 = 2;         // gather batch sizes (tunable: ADV_G_LO / ADV_G_K2 / ADV_G_K3)
     // pipelined multi-group kernels (adv_pipe.cuh): bit 0 E1, 1 N1, 2 K2, 3 K3 (ADV_PIPE)
-    int pipe = 15;
-    int e1_ng = 8, e1_depth = 3;              // edge groups per CTA / cp.async stages (ADV_E1_NG, ADV_E1_D)
+    int pipe = 17;
+    int e1_il = 0;                            // grid-strided group assignment of the bulk edge kernel (ADV_E1_IL)
+    int e1_ng = 8, e1_depth = 2;              // edge groups per CTA / cp.async stages (ADV_E1_NG, ADV_E1_D)
     int nd_ng = 8;                            // node groups per CTA (ADV_ND_NG)
     int k3_depth = 1;                         // stages of the pipelined node kernels (ADV_K3_D)
+    int slot = 0;                            // slot-parallel node kernels (adv_slot.cuh): bit 1 N1, 2 K2, 3 K3 (ADV_SLOT)
+    int lean = 0, lean_g = 3;                // lean node kernels (adv_lean.cuh): bit 1 N1, 2 K2, 3 K3 (ADV_LEAN, ADV_LEAN_G)
+    int force_tb1 = 0;                        // experiments: one tracer per chunk (ADV_TB1)
+    int slot_s = 0;                           // slot lanes per CTA, 0 = min(ell_w, kSlotBlock / L) (ADV_SLOT_S)
     int max_smem_optin = 0;
     std::vector<Peer> rpeers, speers;
     int send_cols = 0;
@@ -299,9 +306,15 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
     if (const char* v = getenv("ADV_G_K3")) c->g_k3 = atoi(v);
     if (const char* v = getenv("ADV_PIPE")) c->pipe = atoi(v);
     if (const char* v = getenv("ADV_E1_NG")) c->e1_ng = std::max(1, atoi(v));
+    if (const char* v = getenv("ADV_E1_IL")) c->e1_il = atoi(v) ? 1 : 0;
     if (const char* v = getenv("ADV_E1_D")) c->e1_depth = std::max(2, std::min(4, atoi(v)));
     if (const char* v = getenv("ADV_ND_NG")) c->nd_ng = std::max(1, atoi(v));
     if (const char* v = getenv("ADV_K3_D")) c->k3_depth = atoi(v) >= 2 ? 2 : 1;
+    if (const char* v = getenv("ADV_TB1")) c->force_tb1 = atoi(v);
+    if (const char* v = getenv("ADV_LEAN")) c->lean = atoi(v);
+    if (const char* v = getenv("ADV_LEAN_G")) c->lean_g = atoi(v);
+    if (const char* v = getenv("ADV_SLOT")) c->slot = atoi(v);
+    if (const char* v = getenv("ADV_SLOT_S")) c->slot_s = std::max(0, atoi(v));
     cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
 #define CUF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { delete c; return fail(ADV_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
     CUF(c->ne_ptr.upload(ne_ptr)); CUF(c->ne_ent.upload(ne_ent));
@@ -316,6 +329,8 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
         CUF(c->area.upload(tmp));
         tmp.assign(d->areasvol, d->areasvol + (size_t)nl * Nh);
         CUF(c->areasvol.upload(tmp));
+        for (double& x : tmp) x = 1.0 / x;                 // IEEE division on the host == the device's 1.0 / av
+        CUF(c->r_areasvol.upload(tmp));
     }
     CUF(c->Q.alloc((size_t)L * E));
 
@@ -370,7 +385,7 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
     m.node_lev = c->node_lev.p; m.node_rec = c->node_rec.p; m.ne_ell = c->ne_ell.p; m.ell_w = ell_w;
     m.edge_meta = c->edge_meta.p; m.edge_el = c->edge_el.p; m.edge_lev = c->edge_lev.p;
     m.edge_cross = c->edge_cross.p; m.edge_c = c->edge_c.p; m.nboundary_lay = c->nboundary_lay.p;
-    m.area = c->area.p; m.areasvol = c->areasvol.p; m.Q = c->Q.p;
+    m.area = c->area.p; m.areasvol = c->areasvol.p; m.r_areasvol = c->r_areasvol.p; m.Q = c->Q.p;
     *out = c;
     return ADV_OK;
 }
@@ -528,6 +543,16 @@ int launch_phase(adv_ctx* c, Phase ph, int hor, int ver, bool q_stored, const Ch
                     se = smem_optin(k_edge_flux_p<H, TB, Q, DD>, sm); \
                     if (se == cudaSuccess) k_edge_flux_p<H, TB, Q, DD><<<grid, nthr, sm, s>>>(m, b, epb, ng); \
                     piped = true; } }
+#define E1B(H, Q, DD) if (!piped && (c->pipe & 16) && hor == H && (q_stored ? 1 : 0) == Q && D == DD) { \
+                const size_t sm = e1b_smem_bytes<TB, Q>(nge, nthr, DD); \
+                if ((int)sm <= c->max_smem_optin) { \
+                    se = smem_optin(k_edge_flux_b<H, TB, Q, DD>, sm); \
+                    if (se == cudaSuccess) k_edge_flux_b<H, TB, Q, DD><<<grid, nthr, sm, s>>>(m, b, epb, ng, c->e1_il); \
+                    piped = true; } }
+#define E1BD(H, Q) E1B(H, Q, 2) E1B(H, Q, 3) E1B(H, Q, 4)
+            E1BD(HOR_MUSCL, 0) E1BD(HOR_MUSCL, 1) E1BD(HOR_MFCT, 0) E1BD(HOR_MFCT, 1)
+#undef E1BD
+#undef E1B
 #define E1PD(H, Q) E1P(H, Q, 2) E1P(H, Q, 3) E1P(H, Q, 4)
             E1PD(HOR_UPW1, 0) E1PD(HOR_UPW1, 1) E1PD(HOR_MUSCL, 0) E1PD(HOR_MUSCL, 1) E1PD(HOR_MFCT, 0) E1PD(HOR_MFCT, 1)
 #undef E1PD
@@ -546,7 +571,19 @@ int launch_phase(adv_ctx* c, Phase ph, int hor, int ver, bool q_stored, const Ch
         nthr = r.cpb * m.L;
         const int ng = std::max(1, c->nd_ng), cn = r.cpb * ng;
         const size_t sm1 = (size_t)TB * nthr * sizeof(double);
-        if (ph == PH_K3 && (c->pipe & 8)) {
+        const int S = std::max(1, std::min(c->slot_s > 0 ? c->slot_s : m.ell_w, kSlotBlock / m.L));
+        if (ph == PH_K3 && (c->lean & 8)) {
+            const size_t sm = lean_meta_bytes(cn, m.ell_w);
+            grid = nblocks(r.count, cn);
+            if (c->lean_g == 2) k_fct_update_l<TB, 2><<<grid, nthr, sm, s>>>(m, b, r, ng, dt);
+            else if (c->lean_g == 6) k_fct_update_l<TB, 6><<<grid, nthr, sm, s>>>(m, b, r, ng, dt);
+            else k_fct_update_l<TB, 3><<<grid, nthr, sm, s>>>(m, b, r, ng, dt);
+            piped = true;
+        } else if (ph == PH_K3 && (c->slot & 8)) {
+            grid = r.count; nthr = S * m.L;
+            k_fct_update_t<TB><<<grid, nthr, (size_t)m.ell_w * TB * m.L * sizeof(double), s>>>(m, b, r, S, dt);
+            piped = true;
+        } else if (ph == PH_K3 && (c->pipe & 8)) {
             const int D = c->k3_depth;
             const size_t sm = k3p_smem_bytes<TB>(cn, m.ell_w, nthr, D);
             if ((int)sm <= c->max_smem_optin) {
@@ -658,8 +695,8 @@ static int run_batch(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr
     std::vector<ChunkSel> chunks;
     for (auto& g : groups) {
         size_t i = 0;
-        for (; i + 2 <= g.idx.size(); i += 2) chunks.push_back(ChunkSel{g.fct, g.hor, g.ver, 2, {g.idx[i], g.idx[i + 1]}, 0});
-        if (i < g.idx.size()) chunks.push_back(ChunkSel{g.fct, g.hor, g.ver, 1, {g.idx[i], g.idx[i]}, 0});
+        for (; !c->force_tb1 && i + 2 <= g.idx.size(); i += 2) chunks.push_back(ChunkSel{g.fct, g.hor, g.ver, 2, {g.idx[i], g.idx[i + 1]}, 0});
+        for (; i < g.idx.size(); ++i) chunks.push_back(ChunkSel{g.fct, g.hor, g.ver, 1, {g.idx[i], g.idx[i]}, 0});
     }
     if (int rc = ensure_chunk_bufs(c, (int)chunks.size())) return rc;
     for (size_t k = 0; k < chunks.size(); ++k) {

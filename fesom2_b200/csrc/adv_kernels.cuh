@@ -74,6 +74,7 @@ struct MeshDev {
     const int*    nboundary_lay; // (Nh)
     const double* area;      // (nl,Nh)
     const double* areasvol;  // (nl,Nh)
+    const double* r_areasvol;  // (nl,Nh) RN(1/areasvol): the exact-division helper y of div_rcp, precomputed (static geometry)
     // state
     const double *uv, *helem;            // (2,L,T) (L,T)
     const double *w, *we, *wi;           // (nl,Nh)
@@ -274,6 +275,29 @@ __device__ __forceinline__ double ver_qr4c(const ColV& c, int k, double fin)
         const double zb = CZB(k);
         const double Tmean1 = t0 + div3((2 * qc + qu) * (zb - z0));
         const double Tmean2 = tm1 + div3((2 * qc + qd) * (zb - zm1));
+        const double w = CW(k);
+        const double Tmean = (w + fabs(w)) * Tmean1 + (w - fabs(w)) * Tmean2;
+        v = (-0.5 * (1.0 - c.num_ord) * Tmean - c.num_ord * (0.5 * (Tmean1 + Tmean2)) * w) * CA(k) - v;
+    }
+    return v;
+}
+
+// adv_tra_ver_qr4c with the three slopes of :417-419 taken from a per-column array: S(j) =
+// (ttf(j-1) - ttf(j)) / (Z(j-1) - Z(j)) for j in [nzmin+1, nzmax-1], so that qc = S(k), qu = S(k+1),
+// qd = S(k-1).  Every slope is evaluated once per column (by the thread of layer j) instead of three
+// times, with the correctly rounded division, hence bit-identical to ver_qr4c.
+__device__ __forceinline__ double ver_qr4c_s(const ColV& c, const double* S, int k, double fin)
+{
+    double v = fin;
+    if (k == c.nzmin) v = -CT(k) * CW(k) * CA(k) - v;
+    if (k == c.nzmin + 1) v = -0.5 * (CT(k - 1) + CT(k)) * CW(k) * CA(k) - v;
+    if (k == c.nzmax - 1) v = -0.5 * (CT(k - 1) + CT(k)) * CW(k) * CA(k) - v;
+    if (k == c.nzmax) v = 0.0 - v;
+    if (k >= c.nzmin + 2 && k <= c.nzmax - 2) {
+        const double qc = S[k - 1], qu = S[k], qd = S[k - 2];
+        const double zb = CZB(k);
+        const double Tmean1 = CT(k) + div3((2 * qc + qu) * (zb - CZ(k)));
+        const double Tmean2 = CT(k - 1) + div3((2 * qc + qd) * (zb - CZ(k - 1)));
         const double w = CW(k);
         const double Tmean = (w + fabs(w)) * Tmean1 + (w - fabs(w)) * Tmean2;
         v = (-0.5 * (1.0 - c.num_ord) * Tmean - c.num_ord * (0.5 * (Tmean1 + Tmean2)) * w) * CA(k) - v;
@@ -979,17 +1003,26 @@ __global__ void __launch_bounds__(kBlock, ADV_K3_MINB) k_fct_update(MeshDev m, C
 #pragma unroll
         for (int j = 0; j < G; ++j) {
             if (!in[j]) continue;
-            const bool second = (ent[j].z >> 16) & 1;
+            // fct :489-494: ae = min(1, R+/R- of edges(1,e), R-/R+ of edges(2,e)) by the sign of the flux;
+            // one (nearly warp-uniform) branch on which end this node is replaces four double selects
+            if (!((ent[j].z >> 16) & 1)) {                 // this node is edges(1,e)
 #pragma unroll
-            for (int t = 0; t < TB; ++t) {
-                const double ff = f[j][t];
-                const double p1 = second ? po[j][t] : pk[t], m1 = second ? mo[j][t] : mk[t];   // factors at edges(1,e)
-                const double p2 = second ? pk[t] : po[j][t], m2 = second ? mk[t] : mo[j][t];   // factors at edges(2,e)
-                double ae = 1.0;
-                if (ff >= 0.0) { ae = dmin(ae, p1); ae = dmin(ae, m2); }      // fct :489-491
-                else { ae = dmin(ae, m1); ae = dmin(ae, p2); }                // :493-494
-                const double term = div_rcp(ae * ff * dt, av, r_av);          // fct :497, driver :607,:620
-                dh[t] = second ? dh[t] - term : dh[t] + term;
+                for (int t = 0; t < TB; ++t) {
+                    const double ff = f[j][t];
+                    const bool pos = ff >= 0.0;
+                    const double A = pos ? pk[t] : mk[t], B = pos ? mo[j][t] : po[j][t];
+                    const double ae = dmin(dmin(1.0, A), B);
+                    dh[t] = dh[t] + div_rcp(ae * ff * dt, av, r_av);          // fct :497, driver :607
+                }
+            } else {                                       // this node is edges(2,e)
+#pragma unroll
+                for (int t = 0; t < TB; ++t) {
+                    const double ff = f[j][t];
+                    const bool pos = ff >= 0.0;
+                    const double A = pos ? po[j][t] : mo[j][t], B = pos ? mk[t] : pk[t];
+                    const double ae = dmin(dmin(1.0, A), B);
+                    dh[t] = dh[t] - div_rcp(ae * ff * dt, av, r_av);          // driver :620
+                }
             }
         }
         j0 += G;

@@ -21,7 +21,7 @@
 namespace adv {
 
 #ifndef ADV_E1P_MINB
-#define ADV_E1P_MINB 2
+#define ADV_E1P_MINB 4      // 4 CTAs of 7 warps per SM: measured best for the bulk edge kernel (profiles/r1_tuning.md)
 #endif
 #ifndef ADV_NDP_MINB
 #define ADV_NDP_MINB 2
@@ -212,6 +212,238 @@ __global__ void __launch_bounds__(kBlock, ADV_E1P_MINB) k_edge_flux_p(MeshDev m,
                 const double a1 = c8[(C::c_a1 + t) * nthr], a2 = c8[(C::c_a2 + t) * nthr];
                 const double flo = hor_lo(t1, t2, qp, qm);
                 out[t] = hor_ho<HOR>(a1, a2, q, qp, qm, ec, g12, g34, b.ph[t], clo1, clo2, flo);
+            }
+        }
+        stv<TB>(b.adf_h + (size_t)oe * TB, out);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// E1 (bulk): as k_edge_flux_p, but the contiguous streams of a group -- edge_up_dn_grad of the
+// group's epb consecutive edges (epb * L * 32 bytes per tracer, 64 % of the kernel's DRAM bytes)
+// -- are fetched by ONE bulk asynchronous copy each
+// (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier), issued by one elected thread.  Bulk
+// copies go through the TMA unit, not through the per-thread load/store path whose outstanding-miss
+// capacity the gather kernels saturate; only the genuine gathers (node columns of ttf/ttfAB,
+// element columns of uv/helem; mostly L1/L2 hits) stay per-thread cp.async cells.
+// Stage layout: [grad t=0 | grad t=1] in global order, then the cells [cell][thread].
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int cnt)
+{
+    asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(cnt));
+}
+__device__ __forceinline__ void mbar_expect(unsigned long long* b, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity)
+{
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
+                 ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned long long* b)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+
+#ifndef ADV_E1B_DIRECT
+#define ADV_E1B_DIRECT 1     // 1: ttf/ttfAB end values are loaded straight to registers in the compute phase (not staged)
+#endif
+template <int TB, int QMODE>
+struct E1bCells {
+    static constexpr int n16 = (QMODE == 0 ? 2 : 0);
+    static constexpr int n8 = (ADV_E1B_DIRECT ? 0 : 4 * TB) + (QMODE == 0 ? 2 : 1);   // + he1, he2 (QMODE 0) or q (QMODE 1)
+    static constexpr int bytes = 16 * n16 + 8 * n8;     // per thread and stage
+    static constexpr int c_uv = 0;
+    static constexpr int c_t1 = 0, c_t2 = TB, c_a1 = 2 * TB, c_a2 = 3 * TB, c_he = (ADV_E1B_DIRECT ? 0 : 4 * TB);
+};
+__host__ __device__ constexpr size_t align128(size_t x) { return (x + 127) & ~(size_t)127; }
+template <int TB, int QMODE>
+__host__ __device__ inline size_t e1b_bulk_bytes(int nthr) { return align128((size_t)nthr * 32 * TB); }
+template <int TB, int QMODE>
+__host__ __device__ inline size_t e1b_stage_bytes(int nthr) { return e1b_bulk_bytes<TB, QMODE>(nthr) + align128((size_t)E1bCells<TB, QMODE>::bytes * nthr); }
+template <int TB, int QMODE>
+__host__ __device__ inline size_t e1b_smem_bytes(int nge, int nthr, int D)
+{
+    return align128(e1p_meta_bytes(nge)) + (size_t)D * e1b_stage_bytes<TB, QMODE>(nthr) + 64;
+}
+
+template <int HOR, int TB, int QMODE, int D>
+__global__ void __launch_bounds__(kBlock, ADV_E1P_MINB) k_edge_flux_b(MeshDev m, Chunk<TB> b, int epb, int ng, int il)
+{
+    static_assert(HOR != HOR_UPW1, "the bulk variant stages edge_up_dn_grad");
+    using C = E1bCells<TB, QMODE>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int L = m.L, nthr = blockDim.x, tid = threadIdx.x;
+    const int nge = epb * ng;
+    // group i of this CTA: consecutive groups (il = 0) or grid-strided (il = 1: at any time the resident
+    // CTAs then work on one dense window of the edge arrays, which keeps DRAM pages open longer)
+    const int g0 = il ? (int)blockIdx.x : (int)blockIdx.x * ng, gs = il ? (int)gridDim.x : 1;
+    const int ngroups = (m.E + epb - 1) / epb;
+    int4* s_em = reinterpret_cast<int4*>(smem_raw);
+    double2* s_cr = reinterpret_cast<double2*>(s_em + nge);
+    double2* s_ec = s_cr + 2 * nge;
+    int2* s_nb = reinterpret_cast<int2*>(s_ec + nge);
+    unsigned* s_lv = reinterpret_cast<unsigned*>(s_nb + nge);
+    unsigned char* s_stage = smem_raw + align128(e1p_meta_bytes(nge));
+    const unsigned stage_bytes = (unsigned)e1b_stage_bytes<TB, QMODE>(nthr);
+    const unsigned bulk_bytes = (unsigned)e1b_bulk_bytes<TB, QMODE>(nthr);
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(s_stage + (size_t)D * stage_bytes);
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < D; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < nge; i += nthr) {
+        const int gi = i / epb;
+        const int e = (g0 + gi * gs) * epb + (i - gi * epb);
+        if (e < m.E) {
+            const int4 em = __ldg(&m.edge_meta[e]);
+            s_em[i] = em;
+            s_lv[i] = __ldg(reinterpret_cast<const unsigned*>(m.edge_lev) + e);
+            const double2* cr = reinterpret_cast<const double2*>(&m.edge_cross[e]);
+            s_cr[2 * i] = __ldg(cr); s_cr[2 * i + 1] = __ldg(cr + 1);
+            s_ec[i] = __ldg(&m.edge_c[e]);
+            if (HOR == HOR_MUSCL) s_nb[i] = make_int2(__ldg(&m.nboundary_lay[em.x]), __ldg(&m.nboundary_lay[em.y]));
+        }
+    }
+    __syncthreads();
+    const ColThread c = col_thread(m);
+    const int nz0 = c.nz0, nz = nz0 + 1;
+    int ngrp = 0;                                             // groups of this CTA that exist
+    for (; ngrp < ng && g0 + ngrp * gs < ngroups; ++ngrp) {}
+    const unsigned sb0 = smem_u32(s_stage);
+    const unsigned o16 = bulk_bytes + (unsigned)tid * 16u, o8 = bulk_bytes + (unsigned)C::n16 * 16u * nthr + (unsigned)tid * 8u;
+    const unsigned st16 = 16u * nthr, st8 = 8u * nthr;
+    const unsigned colw = (unsigned)L * 32u;          // bytes of one edge column of edge_up_dn_grad
+
+    auto issue = [&](int i) {
+        if (i < ngrp) {
+            const unsigned sb = sb0 + (unsigned)(i % D) * stage_bytes;
+            const int eg = (g0 + i * gs) * epb;                // first edge of the group
+            if (tid == 0) {                                    // the contiguous streams of the group: bulk copies
+                const int ne = min(epb, m.E - eg);             // edges of this group
+                const size_t ecol = (size_t)eg * L;
+                const unsigned gb = (unsigned)ne * colw;
+                mbar_expect(&full[i % D], gb * TB);
+#pragma unroll
+                for (int t = 0; t < TB; ++t) bulk_g2s(sb + (unsigned)t * epb * colw, b.grad[t] + ecol * 4, gb, &full[i % D]);
+            }
+            const int li = i * epb + c.g;
+            if (eg + c.g < m.E) {
+                const int4 em = s_em[li];
+                const unsigned lvw = s_lv[li];
+                const int nu1 = lvw & 0xff, nl1 = (lvw >> 8) & 0xff, nu2 = (lvw >> 16) & 0xff, nl2 = lvw >> 24;
+                const int lo = nu2 > 0 ? min(nu1, nu2) : nu1, hi = max(nl1, nl2);
+                const unsigned o1 = (unsigned)em.x * L + nz0, o2 = (unsigned)em.y * L + nz0;
+                if (nz >= lo && nz <= hi) {
+                    if (!ADV_E1B_DIRECT) {
+#pragma unroll
+                        for (int t = 0; t < TB; ++t) {
+                            cpa8(sb + o8 + (C::c_t1 + t) * st8, &b.ttf[t][o1]);
+                            cpa8(sb + o8 + (C::c_t2 + t) * st8, &b.ttf[t][o2]);
+                            cpa8(sb + o8 + (C::c_a1 + t) * st8, &b.ttfAB[t][o1]);
+                            cpa8(sb + o8 + (C::c_a2 + t) * st8, &b.ttfAB[t][o2]);
+                        }
+                    }
+                    if (QMODE == 1) cpa8(sb + o8 + C::c_he * st8, &m.Q[(unsigned)(eg + c.g) * L + nz0]);
+                }
+                if (QMODE == 0) {
+                    bool use1, use2;
+                    edge_use(make_uchar4(nu1, nl1, nu2, nl2), nz, use1, use2);
+                    if (use1) {
+                        const unsigned o = (unsigned)em.z * L + nz0;
+                        cpa16(sb + (C::c_uv + 0) * st16 + o16, m.uv + (size_t)o * 2);
+                        cpa8(sb + o8 + (C::c_he + 0) * st8, &m.helem[o]);
+                    }
+                    if (use2) {
+                        const unsigned o = (unsigned)em.w * L + nz0;
+                        cpa16(sb + (C::c_uv + 1) * st16 + o16, m.uv + (size_t)o * 2);
+                        cpa8(sb + o8 + (C::c_he + 1) * st8, &m.helem[o]);
+                    }
+                }
+            }
+        }
+        cpa_commit();
+    };
+
+#pragma unroll
+    for (int s = 0; s < D - 1; ++s) issue(s);
+    for (int i = 0; i < ngrp; ++i) {
+        // everybody is done with group i-1, whose stage the copies of group i+D-1 overwrite
+        __syncthreads();
+        if (tid == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(i + D - 1);
+        cpa_wait<D - 1>();
+        mbar_wait(&full[i % D], (unsigned)((i / D) & 1));
+        const int li = i * epb + c.g;
+        const int e = (g0 + i * gs) * epb + c.g;
+        if (e >= m.E) continue;
+        const unsigned lvw = s_lv[li];
+        const int nu1 = lvw & 0xff, nl1 = (lvw >> 8) & 0xff, nu2 = (lvw >> 16) & 0xff, nl2 = lvw >> 24;
+        const int lo = nu2 > 0 ? min(nu1, nu2) : nu1, hi = max(nl1, nl2);
+        const bool inr = nz >= lo && nz <= hi;
+        const unsigned oe = (unsigned)e * L + nz0;
+        const unsigned char* sp = s_stage + (size_t)(i % D) * stage_bytes;
+        const double2* c16 = reinterpret_cast<const double2*>(sp + bulk_bytes) + tid;
+        const double* c8 = reinterpret_cast<const double*>(sp + bulk_bytes + (size_t)C::n16 * 16 * nthr) + tid;
+        double t1[TB], t2[TB], a1[TB], a2[TB];
+        if (inr) {
+            if (ADV_E1B_DIRECT) {
+                const int4 em = s_em[li];
+                const unsigned o1 = (unsigned)em.x * L + nz0, o2 = (unsigned)em.y * L + nz0;
+#pragma unroll
+                for (int t = 0; t < TB; ++t) {
+                    t1[t] = __ldg(&b.ttf[t][o1]); t2[t] = __ldg(&b.ttf[t][o2]);
+                    a1[t] = __ldg(&b.ttfAB[t][o1]); a2[t] = __ldg(&b.ttfAB[t][o2]);
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < TB; ++t) {
+                    t1[t] = c8[(C::c_t1 + t) * nthr]; t2[t] = c8[(C::c_t2 + t) * nthr];
+                    a1[t] = c8[(C::c_a1 + t) * nthr]; a2[t] = c8[(C::c_a2 + t) * nthr];
+                }
+            }
+        }
+        double q = 0.0;
+        if (QMODE == 0) {
+            bool use1, use2;
+            edge_use(make_uchar4(nu1, nl1, nu2, nl2), nz, use1, use2);
+            const double2 cr12 = s_cr[2 * li], cr34 = s_cr[2 * li + 1];
+            double v1 = 0.0, v2 = 0.0;
+            // Q(nz,e): vflux of oce_adv_tra_hor.F90:170,190,211-212,226,242
+            if (use1) {
+                const double2 uv1 = c16[(C::c_uv + 0) * nthr];
+                v1 = (-uv1.y * cr12.x + uv1.x * cr12.y) * c8[(C::c_he + 0) * nthr];
+            }
+            if (use2) {
+                const double2 uv2 = c16[(C::c_uv + 1) * nthr];
+                v2 = (uv2.y * cr34.x - uv2.x * cr34.y) * c8[(C::c_he + 1) * nthr];
+            }
+            if (use1 && use2) q = v1 + v2;
+            else if (use1) q = v1;
+            else if (use2) q = v2;
+            m.Q[oe] = q;
+        } else if (inr) q = c8[C::c_he * nthr];
+        double out[TB];
+#pragma unroll
+        for (int t = 0; t < TB; ++t) out[t] = 0.0;
+        if (inr) {
+            const double2 ec = s_ec[li];
+            double clo1 = 1.0, clo2 = 1.0;
+            if (HOR == HOR_MUSCL) {
+                const int2 nb = s_nb[li];
+                clo1 = (nb.x - nz >= 0) ? 1.0 : 0.0;   // oce_adv_tra_hor.F90:411-412
+                clo2 = (nb.y - nz >= 0) ? 1.0 : 0.0;
+            }
+            const double aq = fabs(q), qp = q + aq, qm = q - aq;
+#pragma unroll
+            for (int t = 0; t < TB; ++t) {
+                const double2* gp = reinterpret_cast<const double2*>(sp + (size_t)t * epb * colw) + (size_t)tid * 2;
+                const double2 g12 = gp[0], g34 = gp[1];
+                const double flo = hor_lo(t1[t], t2[t], qp, qm);
+                out[t] = hor_ho<HOR>(a1[t], a2[t], q, qp, qm, ec, g12, g34, b.ph[t], clo1, clo2, flo);
             }
         }
         stv<TB>(b.adf_h + (size_t)oe * TB, out);
