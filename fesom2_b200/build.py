@@ -6,7 +6,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "adv_capi.cu")
-DEPS = [SRC, os.path.join(_HERE, "csrc", "adv_kernels.cuh"), os.path.join(_HERE, "csrc", "adv_pipe.cuh"), os.path.join(_HERE, "csrc", "adv_slot.cuh"), os.path.join(_HERE, "csrc", "adv_lean.cuh"),
+DEPS = [SRC, os.path.join(_HERE, "csrc", "adv_kernels.cuh"), os.path.join(_HERE, "csrc", "adv_pipe.cuh"),
         os.path.join(_HERE, "..", "include", "fesom_adv_b200.h")]
 OUT = os.path.join(_HERE, "libfesom_adv_b200.so")
 

@@ -5,8 +5,6 @@
 #include "../../include/fesom_adv_b200.h"
 #include "adv_kernels.cuh"
 #include "adv_pipe.cuh"
-#include "adv_slot.cuh"
-#include "adv_lean.cuh"
 
 #include <nccl.h>   // types only: the library is resolved at run time (see NcclApi)
 #include <dlfcn.h>
@@ -134,17 +132,10 @@ struct adv_ctx {
     DevBuf<double> area, areasvol, r_areasvol, Q;
     int nS = 0, nI = 0, nSH = 0;
     int pf_dist = 0;                          // L2 prefetch distance in CTAs (ADV_PF; 0 = off)
-    int g_lo = 2, g_k2 = 1, g_k3 = 2;         // gather batch sizes (tunable: ADV_G_LO / ADV_G_K2 / ADV_G_K3)
-    // pipelined multi-group kernels (adv_pipe.cuh): bit 0 E1, 1 N1, 2 K2, 3 K3 (ADV_PIPE)
-    int pipe = 17;
-    int e1_il = 0;                            // grid-strided group assignment of the bulk edge kernel (ADV_E1_IL)
-    int e1_ng = 8, e1_depth = 2;              // edge groups per CTA / cp.async stages (ADV_E1_NG, ADV_E1_D)
-    int nd_ng = 8;                            // node groups per CTA (ADV_ND_NG)
-    int k3_depth = 1;                         // stages of the pipelined node kernels (ADV_K3_D)
-    int slot = 0;                            // slot-parallel node kernels (adv_slot.cuh): bit 1 N1, 2 K2, 3 K3 (ADV_SLOT)
-    int lean = 0, lean_g = 3;                // lean node kernels (adv_lean.cuh): bit 1 N1, 2 K2, 3 K3 (ADV_LEAN, ADV_LEAN_G)
+    int g_lo = 3, g_k2 = 2, g_k3 = 2;         // gather batch sizes (tunable: ADV_G_LO / ADV_G_K2 / ADV_G_K3)
+    int bulk = 1;                             // bulk-copy edge kernel (adv_pipe.cuh); 0 = register-gather k_edge_flux (ADV_BULK)
+    int e1_ng = 8, e1_depth = 2, e1_il = 0;   // edge groups per CTA / stages / grid-strided groups (ADV_E1_NG, ADV_E1_D, ADV_E1_IL)
     int force_tb1 = 0;                        // experiments: one tracer per chunk (ADV_TB1)
-    int slot_s = 0;                           // slot lanes per CTA, 0 = min(ell_w, kSlotBlock / L) (ADV_SLOT_S)
     int max_smem_optin = 0;
     std::vector<Peer> rpeers, speers;
     int send_cols = 0;
@@ -304,17 +295,11 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
     if (const char* v = getenv("ADV_G_LO")) c->g_lo = atoi(v);
     if (const char* v = getenv("ADV_G_K2")) c->g_k2 = atoi(v);
     if (const char* v = getenv("ADV_G_K3")) c->g_k3 = atoi(v);
-    if (const char* v = getenv("ADV_PIPE")) c->pipe = atoi(v);
+    if (const char* v = getenv("ADV_BULK")) c->bulk = atoi(v);
     if (const char* v = getenv("ADV_E1_NG")) c->e1_ng = std::max(1, atoi(v));
     if (const char* v = getenv("ADV_E1_IL")) c->e1_il = atoi(v) ? 1 : 0;
     if (const char* v = getenv("ADV_E1_D")) c->e1_depth = std::max(2, std::min(4, atoi(v)));
-    if (const char* v = getenv("ADV_ND_NG")) c->nd_ng = std::max(1, atoi(v));
-    if (const char* v = getenv("ADV_K3_D")) c->k3_depth = atoi(v) >= 2 ? 2 : 1;
     if (const char* v = getenv("ADV_TB1")) c->force_tb1 = atoi(v);
-    if (const char* v = getenv("ADV_LEAN")) c->lean = atoi(v);
-    if (const char* v = getenv("ADV_LEAN_G")) c->lean_g = atoi(v);
-    if (const char* v = getenv("ADV_SLOT")) c->slot = atoi(v);
-    if (const char* v = getenv("ADV_SLOT_S")) c->slot_s = std::max(0, atoi(v));
     cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
 #define CUF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { delete c; return fail(ADV_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
     CUF(c->ne_ptr.upload(ne_ptr)); CUF(c->ne_ent.upload(ne_ent));
@@ -533,17 +518,11 @@ int launch_phase(adv_ctx* c, Phase ph, int hor, int ver, bool q_stored, const Ch
     if (ph == PH_E1) {
         const int epb = cols_per_block(m.L);
         nthr = epb * m.L;
-        if ((c->pipe & 1) && chunk_aligned<TB>(m, b)) {
+        if (c->bulk && hor != HOR_UPW1 && chunk_aligned<TB>(m, b)) {
             const int ng = std::max(1, std::min(c->e1_ng, nthr / epb));
             const int nge = epb * ng, D = c->e1_depth;
             grid = nblocks(m.E, nge);
-#define E1P(H, Q, DD) if (!piped && hor == H && (q_stored ? 1 : 0) == Q && D == DD) { \
-                const size_t sm = e1p_smem_bytes<H, TB, Q>(nge, nthr, DD); \
-                if ((int)sm <= c->max_smem_optin) { \
-                    se = smem_optin(k_edge_flux_p<H, TB, Q, DD>, sm); \
-                    if (se == cudaSuccess) k_edge_flux_p<H, TB, Q, DD><<<grid, nthr, sm, s>>>(m, b, epb, ng); \
-                    piped = true; } }
-#define E1B(H, Q, DD) if (!piped && (c->pipe & 16) && hor == H && (q_stored ? 1 : 0) == Q && D == DD) { \
+#define E1B(H, Q, DD) if (!piped && hor == H && (q_stored ? 1 : 0) == Q && D == DD) { \
                 const size_t sm = e1b_smem_bytes<TB, Q>(nge, nthr, DD); \
                 if ((int)sm <= c->max_smem_optin) { \
                     se = smem_optin(k_edge_flux_b<H, TB, Q, DD>, sm); \
@@ -553,10 +532,6 @@ int launch_phase(adv_ctx* c, Phase ph, int hor, int ver, bool q_stored, const Ch
             E1BD(HOR_MUSCL, 0) E1BD(HOR_MUSCL, 1) E1BD(HOR_MFCT, 0) E1BD(HOR_MFCT, 1)
 #undef E1BD
 #undef E1B
-#define E1PD(H, Q) E1P(H, Q, 2) E1P(H, Q, 3) E1P(H, Q, 4)
-            E1PD(HOR_UPW1, 0) E1PD(HOR_UPW1, 1) E1PD(HOR_MUSCL, 0) E1PD(HOR_MUSCL, 1) E1PD(HOR_MFCT, 0) E1PD(HOR_MFCT, 1)
-#undef E1PD
-#undef E1P
         }
         if (!piped) {
             grid = nblocks(m.E, epb);
@@ -569,32 +544,8 @@ int launch_phase(adv_ctx* c, Phase ph, int hor, int ver, bool q_stored, const Ch
         const NodeRange r = node_range(c, rid, cols_per_block(m.L));
         if (r.count <= 0) return ADV_OK;
         nthr = r.cpb * m.L;
-        const int ng = std::max(1, c->nd_ng), cn = r.cpb * ng;
         const size_t sm1 = (size_t)TB * nthr * sizeof(double);
-        const int S = std::max(1, std::min(c->slot_s > 0 ? c->slot_s : m.ell_w, kSlotBlock / m.L));
-        if (ph == PH_K3 && (c->lean & 8)) {
-            const size_t sm = lean_meta_bytes(cn, m.ell_w);
-            grid = nblocks(r.count, cn);
-            if (c->lean_g == 2) k_fct_update_l<TB, 2><<<grid, nthr, sm, s>>>(m, b, r, ng, dt);
-            else if (c->lean_g == 6) k_fct_update_l<TB, 6><<<grid, nthr, sm, s>>>(m, b, r, ng, dt);
-            else k_fct_update_l<TB, 3><<<grid, nthr, sm, s>>>(m, b, r, ng, dt);
-            piped = true;
-        } else if (ph == PH_K3 && (c->slot & 8)) {
-            grid = r.count; nthr = S * m.L;
-            k_fct_update_t<TB><<<grid, nthr, (size_t)m.ell_w * TB * m.L * sizeof(double), s>>>(m, b, r, S, dt);
-            piped = true;
-        } else if (ph == PH_K3 && (c->pipe & 8)) {
-            const int D = c->k3_depth;
-            const size_t sm = k3p_smem_bytes<TB>(cn, m.ell_w, nthr, D);
-            if ((int)sm <= c->max_smem_optin) {
-                grid = nblocks(r.count, cn);
-                if (D == 2) { se = smem_optin(k_fct_update_p<TB, 2>, sm); if (se == cudaSuccess) k_fct_update_p<TB, 2><<<grid, nthr, sm, s>>>(m, b, r, ng, dt); }
-                else { se = smem_optin(k_fct_update_p<TB, 1>, sm); if (se == cudaSuccess) k_fct_update_p<TB, 1><<<grid, nthr, sm, s>>>(m, b, r, ng, dt); }
-                piped = true;
-            }
-        }
-        if (piped) {
-        } else if (ph == PH_N1) {
+        if (ph == PH_N1) {
             grid = nblocks(r.count, r.cpb);
 #define N1(V) if (ver == V) { const size_t smn = (size_t)n1_smem_arrays<V, TB>() * nthr * sizeof(double); \
                               if (c->g_lo == 6) k_node_lo<V, TB, 6><<<grid, nthr, smn, s>>>(m, b, r, dt); \

@@ -42,6 +42,33 @@ constexpr int kBlock = 256;
 // minimum resident CTAs per SM (register caps): measured on B200, see DESIGN.md section 4 --
 // occupancy beats register-resident batching: 4-5 CTAs of 7 warps with a few spilled words run
 // 20-30 % faster than 2 CTAs without spills (gpurun_out/exp_mb*.log, profiles/r1_tuning.md)
+// Register budgets of the node kernels.  The CTAs are cpb * L threads (210 for L = 70, i.e. 7 warps): a
+// cap of 72 registers still fits 4 CTAs per SM there (65536 / (224 * 72)), 56 fits 5, and the 8 extra
+// registers over the __launch_bounds__(256, n) caps remove most of the spills (profiles/r1_tuning.md).
+#ifndef ADV_N1_REGS
+#define ADV_N1_REGS 56
+#endif
+#ifndef ADV_K2_REGS
+#define ADV_K2_REGS 72
+#endif
+#ifndef ADV_K3_REGS
+#define ADV_K3_REGS 72
+#endif
+#if ADV_N1_REGS > 0
+#define ADV_N1_BOUNDS __maxnreg__(ADV_N1_REGS)
+#else
+#define ADV_N1_BOUNDS __launch_bounds__(kBlock, ADV_N1_MINB)
+#endif
+#if ADV_K2_REGS > 0
+#define ADV_K2_BOUNDS __maxnreg__(ADV_K2_REGS)
+#else
+#define ADV_K2_BOUNDS __launch_bounds__(kBlock, ADV_K2_MINB)
+#endif
+#if ADV_K3_REGS > 0
+#define ADV_K3_BOUNDS __maxnreg__(ADV_K3_REGS)
+#else
+#define ADV_K3_BOUNDS __launch_bounds__(kBlock, ADV_K3_MINB)
+#endif
 #ifndef ADV_E1_MINB
 #define ADV_E1_MINB 4
 #endif
@@ -138,11 +165,31 @@ template <> __device__ __forceinline__ void stv<2>(double* __restrict__ p, const
 // {plus, minus} pairs of the TB tracers at p
 template <int TB> __device__ __forceinline__ void ldpm(const double* __restrict__ p, double (&pl)[TB], double (&mi)[TB])
 {
+#ifndef ADV_NO_LDG256
+    if (TB == 2) {   // the {R+,R-} pairs of both tracers are one 32-byte record: a single 256-bit load (sm_100: LDG.E.256)
+        double a, b, c, d;
+        asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+        pl[0] = a; mi[0] = b; pl[TB - 1] = c; mi[TB - 1] = d;
+        return;
+    }
+#endif
 #pragma unroll
     for (int t = 0; t < TB; ++t) {
         const double2 v = __ldg(reinterpret_cast<const double2*>(p) + t);
         pl[t] = v.x; mi[t] = v.y;
     }
+}
+// store TB {a, b} pairs at p (32-byte aligned for TB = 2: one 256-bit store)
+template <int TB> __device__ __forceinline__ void stpm(double* __restrict__ p, const double (&a)[TB], const double (&b)[TB])
+{
+#ifndef ADV_NO_LDG256
+    if (TB == 2) {
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a[0]), "d"(b[0]), "d"(a[TB - 1]), "d"(b[TB - 1]) : "memory");
+        return;
+    }
+#endif
+#pragma unroll
+    for (int t = 0; t < TB; ++t) reinterpret_cast<double2*>(p)[t] = make_double2(a[t], b[t]);
 }
 
 // Correctly rounded x / b from y = RN(1/b): q0 = x*y is refined twice with exact FMA residuals
@@ -590,7 +637,7 @@ template <int VER, int TB>
 __host__ __device__ constexpr int n1_smem_arrays() { return 3 * TB + 5 + (VER == VER_PPM ? 2 : 0); }
 
 template <int VER, int TB, int G>
-__global__ void __launch_bounds__(kBlock, ADV_N1_MINB) k_node_lo(MeshDev m, Chunk<TB> b, NodeRange r, double dt)
+__global__ void ADV_N1_BOUNDS k_node_lo(MeshDev m, Chunk<TB> b, NodeRange r, double dt)
 {
     extern __shared__ double sm[];      // n1_smem_arrays() arrays of [nthr]; element g*L+nz0 == threadIdx.x
     const int L = m.L, nl = m.nl, nthr = blockDim.x, tid = threadIdx.x;
@@ -810,7 +857,7 @@ __global__ void __launch_bounds__(128) k_vert_impl(MeshDev m, double* __restrict
 // Output: pm = {R+, R-} per tracer.
 // ----------------------------------------------------------------------------------------------
 template <int TB, int G>
-__global__ void __launch_bounds__(kBlock, ADV_K2_MINB) k_fct_bounds(MeshDev m, Chunk<TB> b, NodeRange r, double dt)
+__global__ void ADV_K2_BOUNDS k_fct_bounds(MeshDev m, Chunk<TB> b, NodeRange r, double dt)
 {
     extern __shared__ double sm[];  // [2*TB][blockDim]: tvert_max, tvert_min
     const int L = m.L, nl = m.nl;
@@ -904,7 +951,7 @@ __global__ void __launch_bounds__(kBlock, ADV_K2_MINB) k_fct_bounds(MeshDev m, C
     if (!valid) return;
     const double r_av = 1.0 / av, r_hnn = 1.0 / hnn;
     const bool edge_layer = (nz == th.nzmin) || (nz == th.nzmax - 1);   // :233-234, :245-247
-    double* out = b.pm + (size_t)oL * TB * 2;
+    double rp[TB], rm[TB];
 #pragma unroll
     for (int t = 0; t < TB; ++t) {
         double vmax = tmax[t], vmin = tmin[t];
@@ -917,8 +964,9 @@ __global__ void __launch_bounds__(kBlock, ADV_K2_MINB) k_fct_bounds(MeshDev m, C
         const double inc_max = vmax - lo_n[t], inc_min = vmin - lo_n[t];
         const double fp = div_rcp(div_rcp(pp[t] * dt, av, r_av), hnn, r_hnn) + 1e-16;   // b2 :399
         const double fm = div_rcp(div_rcp(pn[t] * dt, av, r_av), hnn, r_hnn) - 1e-16;   // :401
-        reinterpret_cast<double2*>(out)[t] = make_double2(dmin(1.0, inc_max / fp), dmin(1.0, inc_min / fm));
+        rp[t] = dmin(1.0, inc_max / fp); rm[t] = dmin(1.0, inc_min / fm);
     }
+    stpm<TB>(b.pm + (size_t)oL * TB * 2, rp, rm);
 }
 
 // limited vertical antidiffusive flux at interface k of a column (oce_adv_tra_fct.F90:425-455):
@@ -941,7 +989,7 @@ __device__ __forceinline__ double limit_v(double f, int k, int nzmin, int nzmax,
 //   reference: oce_adv_tra_fct.F90:425-500 (b3), oce_adv_tra_driver.F90:529-633 (U1-U3)
 // ----------------------------------------------------------------------------------------------
 template <int TB, int G>
-__global__ void __launch_bounds__(kBlock, ADV_K3_MINB) k_fct_update(MeshDev m, Chunk<TB> b, NodeRange r, double dt)
+__global__ void ADV_K3_BOUNDS k_fct_update(MeshDev m, Chunk<TB> b, NodeRange r, double dt)
 {
     const int L = m.L, nl = m.nl;
     const NodeThread th = node_thread(m, r);
