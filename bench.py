@@ -288,10 +288,18 @@ def main():
         # per-rank algorithmic bytes over the max-over-ranks step time (includes exposed halo waits)
         roof["achieved"] = alg / (ms_per_step * 1e-3) / 1e9
     roof["frac"] = roof["achieved"] / peak
+    # measured DRAM bytes of the same step from the committed `ncu --set full` capture
+    # (tools/ncu_traffic.py -> profiles/traffic_latest.json; per launch, like `achieved`)
     traffic_file = os.path.join(ROOT, "profiles", "traffic_latest.json")
-    if os.path.exists(traffic_file):
+    if os.path.exists(traffic_file) and world == 1 and args.workload == "cfg4" and ntr == 2:
         try:
-            roof["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_step")
+            tj = json.load(open(traffic_file))
+            roof["traffic"] = tj.get("dram_bytes_per_step")
+            roof["traffic_source"] = "profiles/traffic_latest.json (" + os.path.basename(tj.get("report", "ncu")) + ")"
+            if "kernel_ms" in roof:
+                roof["kernel_dram_gbs"] = {
+                    k: (v["dram_read_bytes"] + v["dram_write_bytes"]) / (roof["kernel_ms"].get(k, float("nan")) * 1e-3) / 1e9
+                    for k, v in tj.get("kernels", {}).items() if k in roof["kernel_ms"]}
         except Exception:
             pass
 

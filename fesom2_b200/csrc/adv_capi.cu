@@ -423,6 +423,11 @@ int adv_ctx_set_state(adv_ctx_t* c, const adv_state_desc_t* st, int where)
     if (st->use_wsplit && !st->w_i) return fail(ADV_EINVAL, "use_wsplit needs w_i");
     if (where == ADV_DEVICE) {
         m.uv = st->uv; m.helem = st->helem; m.w = st->w; m.we = st->w_e; m.wi = st->w_i;
+        if ((uintptr_t)st->uv & 15u) {       // the kernels read (u,v) pairs as 16-byte words: stage an aligned copy
+            if (c->uv.n != 2 * L * T) CU(c->uv.alloc(2 * L * T, false));
+            CU(cudaMemcpyAsync(c->uv.p, st->uv, 2 * L * T * sizeof(double), cudaMemcpyDeviceToDevice, c->s_comp));
+            m.uv = c->uv.p;
+        }
         m.hnode = st->hnode; m.hnode_new = st->hnode_new; m.zbar3d = st->zbar_3d_n; m.Z3d = st->Z_3d_n;
     } else {
         struct { DevBuf<double>* b; const double* src; size_t n; const double** dst; } cp[] = {
@@ -760,6 +765,13 @@ static int do_adv(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr, i
         if (where == ADV_DEVICE) {
             p.ttf[i] = tr[i].values; p.ttfAB[i] = tr[i].valuesAB; p.grad[i] = tr[i].edge_up_dn_grad;
             p.dh[i] = tr[i].del_ttf_advhoriz; p.dv[i] = tr[i].del_ttf_advvert;
+            if (tr[i].edge_up_dn_grad && ((uintptr_t)tr[i].edge_up_dn_grad & 15u)) {
+                // edge_up_dn_grad(1:4,nz,e) is read as 16-byte words / bulk copies: stage an aligned copy
+                Slot& s = c->slots[i];
+                if (s.grad.n != 4 * nLE) CU(s.grad.alloc(4 * nLE, false));
+                CU(cudaMemcpyAsync(s.grad.p, tr[i].edge_up_dn_grad, 4 * nLE * 8, cudaMemcpyDeviceToDevice, c->s_comp));
+                p.grad[i] = s.grad.p;
+            }
         } else {
             Slot& s = c->slots[i];
             if (s.ttf.n != nLN) { CU(s.ttf.alloc(nLN, false)); CU(s.ttfAB.alloc(nLN, false)); CU(s.dh.alloc(nLN, false)); CU(s.dv.alloc(nLN, false)); }

@@ -21,7 +21,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FESOM_ADV_LIB") or os.path.join(_HERE, "libfesom_adv_b200.so")   # override: tuning builds only
 
 ADV_HOST, ADV_DEVICE = 0, 1
-ADV_ESCHEME = -3
+ADV_OK, ADV_EINVAL, ADV_ECUDA, ADV_ESCHEME, ADV_ENCCL, ADV_ESTATE = 0, -1, -2, -3, -4, -5   # include/fesom_adv_b200.h:32-37
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int32)

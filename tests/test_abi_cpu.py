@@ -1,0 +1,67 @@
+"""not-gpu: the C-ABI library builds for sm_100a, loads, and exports every entry point that
+include/fesom_adv_b200.h declares; without a CUDA device the product path fails loudly (there is no
+CPU fallback and nothing under oracle/ is reachable from the library)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "fesom_adv_b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(adv_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from fesom2_b200.build import build_library
+    return ctypes.CDLL(build_library())
+
+
+def test_header_and_driver_agree():
+    from fesom2_b200 import driver
+    assert sorted(driver.EXPORTS) == _declared()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    for name in _declared():
+        assert hasattr(lib, name), name
+
+
+def test_library_is_sm100a_only_and_uses_bulk_copies(lib):
+    """one architecture, and the Blackwell-era copy instructions are in the SASS (UBLKCP = cp.async.bulk,
+    LDGSTS = cp.async, 256-bit LDG)"""
+    from fesom2_b200.build import OUT
+    elf = subprocess.run(["cuobjdump", "-lelf", OUT], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", elf))
+    assert archs == {"sm_100a"}, archs
+    sass = subprocess.run(["cuobjdump", "-sass", OUT], capture_output=True, text=True).stdout
+    for mnemonic in ("UBLKCP", "LDGSTS", "LDG.E.ENL2.256", "SYNCS"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA" not in sass and "DMMA" not in sass      # no tensor cores on this path, by design
+
+
+def test_no_cuda_device_is_an_error_not_a_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from fesom2_b200 import driver, mesh as M
+    g = M.synth_mesh(12, 10, nl=8)
+    with pytest.raises(driver.AdvError) as ei:
+        driver.AdvB200(g, M.nboundary_lay(g), device=0, max_tracers=1)
+    assert ei.value.code == driver.ADV_ECUDA
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_product_package_does_not_import_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "fesom2_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".c", ".F90")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|#include\s+.*oracle", txt, flags=re.M), os.path.join(dirpath, f)

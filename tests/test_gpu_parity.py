@@ -143,3 +143,45 @@ def test_unknown_scheme_is_an_error(small_mesh):
     with pytest.raises(AdvError) as ei:
         run_cuda(small_mesh, st, trs, nb, dt)
     assert ei.value.code == ADV_ESCHEME
+
+
+@pytest.mark.parametrize("knobs", [{"ADV_BULK": "0"}, {"ADV_E1_D": "3", "ADV_E1_NG": "5"}, {"ADV_E1_D": "4", "ADV_E1_NG": "1"},
+                                   {"ADV_G_LO": "6", "ADV_G_K2": "6", "ADV_G_K3": "6"}, {"ADV_G_LO": "2", "ADV_G_K2": "1", "ADV_G_K3": "1"}])
+def test_kernel_variants_are_bit_identical(souf_mesh, monkeypatch, knobs):
+    """every launch configuration of the library (register-gather or bulk-copy edge kernel, pipeline
+    depth, groups per CTA, gather batch sizes) gives the same bits as the oracle-checked default"""
+    st, trs, nb, dt = make_case(souf_mesh, 3, "MFCT", "QR4C", "FCT")     # 3 tracers: one TB=2 and one TB=1 chunk
+    ora = run_oracle(souf_mesh, st, trs, nb, dt)
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    ctx, dh, dv = run_cuda(souf_mesh, st, trs, nb, dt)
+    _compare(souf_mesh, ctx, dh, dv, ora, 3, exact=True)
+    ctx.close()
+
+
+def test_unaligned_device_pointers_are_staged(small_mesh):
+    """edge_up_dn_grad / uv that are only 8-byte aligned cannot be read as 16-byte words or bulk-copied:
+    the library stages an aligned device copy, same result"""
+    from fesom2_b200.driver import AdvB200
+    from common import to_device
+    st, trs, nb, dt = make_case(small_mesh, 2, "MUSCL", "QR4C", "FCT")
+    ora = run_oracle(small_mesh, st, trs, nb, dt)
+    dev = torch.device("cuda:0")
+    st_d, trs_d = to_device(st, trs, dev)
+    for t in trs_d:                                                   # shift the gradients by one double
+        buf = torch.empty(t.edge_up_dn_grad.numel() + 1, dtype=torch.float64, device=dev)
+        view = buf[1:].view_as(t.edge_up_dn_grad)
+        view.copy_(t.edge_up_dn_grad)
+        assert view.data_ptr() % 16 == 8
+        t.edge_up_dn_grad = view
+    buf = torch.empty(st_d.uv.numel() + 1, dtype=torch.float64, device=dev)
+    uv = buf[1:].view_as(st_d.uv)
+    uv.copy_(st_d.uv)
+    st_d.uv = uv
+    ctx = AdvB200(small_mesh, nb, max_tracers=2)
+    ctx.set_state(st_d)
+    dh = [torch.zeros((small_mesh.Nh, small_mesh.L), dtype=torch.float64, device=dev) for _ in trs]
+    dv = [torch.zeros((small_mesh.Nh, small_mesh.L), dtype=torch.float64, device=dev) for _ in trs]
+    ctx.do_oce_adv_tra(dt, trs_d, dh, dv)
+    _compare(small_mesh, ctx, [x.cpu().numpy() for x in dh], [x.cpu().numpy() for x in dv], ora, 2)
+    ctx.close()
