@@ -131,7 +131,7 @@ struct adv_ctx {
     DevBuf<double2> edge_c;
     DevBuf<double> area, areasvol, r_areasvol, Q;
     int nS = 0, nI = 0, nSH = 0;
-    int pf_dist = 0;                          // L2 prefetch distance in CTAs (ADV_PF; 0 = off)
+    int pf_dist = 200;                        // L2 prefetch distance of the node kernels in CTAs (ADV_PF; 0 = off)
     int g_lo = 3, g_k2 = 2, g_k3 = 2;         // gather batch sizes (tunable: ADV_G_LO / ADV_G_K2 / ADV_G_K3)
     int bulk = 1;                             // bulk-copy edge kernel (adv_pipe.cuh); 0 = register-gather k_edge_flux (ADV_BULK)
     int e1_ng = 8, e1_depth = 2, e1_il = 0;   // edge groups per CTA / stages / grid-strided groups (ADV_E1_NG, ADV_E1_D, ADV_E1_IL)
@@ -494,11 +494,11 @@ static NodeRange node_range(const adv_ctx* c, int rid, int cpb)
 {
     const MeshDev& m = c->m;
     switch (rid) {
-    case R_S: return NodeRange{c->list_S.p, 0, c->nS, cpb};
-    case R_I: return NodeRange{c->list_I.p, 0, c->nI, cpb};
-    case R_SH: return NodeRange{c->list_SH.p, 0, c->nSH, cpb};
-    case R_ALLH: return NodeRange{nullptr, 0, m.Nh, cpb};
-    default: return NodeRange{nullptr, 0, m.N, cpb};
+    case R_S: return NodeRange{c->list_S.p, 0, c->nS, cpb, c->pf_dist};
+    case R_I: return NodeRange{c->list_I.p, 0, c->nI, cpb, c->pf_dist};
+    case R_SH: return NodeRange{c->list_SH.p, 0, c->nSH, cpb, c->pf_dist};
+    case R_ALLH: return NodeRange{nullptr, 0, m.Nh, cpb, c->pf_dist};
+    default: return NodeRange{nullptr, 0, m.N, cpb, c->pf_dist};
     }
 }
 
@@ -540,8 +540,8 @@ int launch_phase(adv_ctx* c, Phase ph, int hor, int ver, bool q_stored, const Ch
         }
         if (!piped) {
             grid = nblocks(m.E, epb);
-#define E1(H) if (hor == H) { if (q_stored) k_edge_flux<H, TB, 1><<<grid, nthr, 0, s>>>(m, b, epb, c->pf_dist); \
-                              else k_edge_flux<H, TB, 0><<<grid, nthr, 0, s>>>(m, b, epb, c->pf_dist); }
+#define E1(H) if (hor == H) { if (q_stored) k_edge_flux<H, TB, 1><<<grid, nthr, 0, s>>>(m, b, epb, 0); \
+                              else k_edge_flux<H, TB, 0><<<grid, nthr, 0, s>>>(m, b, epb, 0); }
             E1(HOR_UPW1) E1(HOR_MUSCL) E1(HOR_MFCT)
 #undef E1
         }
@@ -841,7 +841,7 @@ int adv_update_values(adv_ctx_t* c, int ntr, double* const* values, const double
     if (!c->state_set) return fail(ADV_ESTATE, "adv_ctx_set_state has not been called");
     CU(cudaSetDevice(c->device));
     const int cpb = cols_per_block(c->m.L);
-    const NodeRange rAll{nullptr, 0, c->m.N, cpb};
+    const NodeRange rAll{nullptr, 0, c->m.N, cpb, 0};
     for (int i = 0; i < ntr; ++i) {
         k_update_values<<<nblocks(c->m.N, cpb), cpb * c->m.L, 0, c->s_comp>>>(c->m, rAll, values[i], dh[i], dv[i]);
         ++c->launches;

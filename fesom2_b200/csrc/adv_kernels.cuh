@@ -39,6 +39,9 @@ enum { HOR_UPW1 = 0, HOR_MUSCL = 1, HOR_MFCT = 2 };
 enum { VER_UPW1 = 0, VER_QR4C = 1, VER_PPM = 2, VER_CDIFF = 3 };
 
 constexpr int kBlock = 256;
+#ifndef ADV_PF_OWN
+#define ADV_PF_OWN 4     // bit mask N1|K2|K3: also pull the next CTAs' own columns into L2 (helps K3 only: 1.37 -> 1.26 ms)
+#endif
 // minimum resident CTAs per SM (register caps): measured on B200, see DESIGN.md section 4 --
 // occupancy beats register-resident batching: 4-5 CTAs of 7 warps with a few spilled words run
 // 20-30 % faster than 2 CTAs without spills (gpurun_out/exp_mb*.log, profiles/r1_tuning.md)
@@ -128,6 +131,7 @@ struct NodeRange {
     const int* list;  // optional indirection (0-based node ids); nullptr = identity
     int begin, count;
     int cpb;          // columns per CTA
+    int pf;           // metadata prefetch distance in CTAs (0 = off)
 };
 
 __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
@@ -490,6 +494,20 @@ __device__ __forceinline__ NodeThread node_thread(const MeshDev& m, const NodeRa
 {
     NodeThread t;
     const ColThread c = col_thread(m);
+    // Metadata prefetch: every CTA starts with two dependent metadata loads (node_rec, then the ELL
+    // row) that nothing else overlaps (ncu: 11-15 % of the node kernels' stall samples).  Thread j < cpb
+    // pulls the record and the ELL row of column j of the CTA `pf` launches ahead into L2, so that
+    // those loads become L2 hits (1.30 / 1.21 / 1.43 -> 1.25 / 1.14 / 1.37 ms for N1 / K2 / K3).
+    if (r.pf > 0 && (int)threadIdx.x < r.cpb) {
+        const long long i = ((long long)blockIdx.x + r.pf) * r.cpb + threadIdx.x;
+        if (i < r.count) {
+            const int nf = r.list ? __ldg(&r.list[r.begin + i]) : r.begin + (int)i;
+            const char* row = reinterpret_cast<const char*>(m.ne_ell + (size_t)nf * m.ell_w);
+            l2_prefetch_line(&m.node_rec[nf]);
+            l2_prefetch_line(row);
+            l2_prefetch_line(row + m.ell_w * 16 - 1);
+        }
+    }
     t.nz0 = c.nz0;
     const int i = blockIdx.x * r.cpb + c.g;
     t.active = i < r.count;
@@ -503,6 +521,33 @@ __device__ __forceinline__ NodeThread node_thread(const MeshDev& m, const NodeRa
         t.self_lo = rec.y & 0xff; t.self_hi = (rec.y >> 8) & 0xff; t.deg = (rec.y >> 16) & 0xff;
     }
     return t;
+}
+
+// Own-column prefetch of the CTA `pf` launches ahead: thread 32 + a * cpb + j pulls column j of array a
+// into L2 with ONE bulk prefetch (cp.async.bulk.prefetch.L2, any length).
+struct PfArr { const void* base; unsigned col_bytes; };
+template <int NA>
+__device__ __forceinline__ void prefetch_own_columns(const NodeRange& r, const PfArr (&arr)[NA])
+{
+    const int k = (int)threadIdx.x - 32;                  // warp 1 onwards: warp 0 does the metadata
+    if (r.pf <= 0 || k < 0) return;
+    int a, nf, rows;
+    if (r.list == nullptr) {                              // consecutive nodes: the cpb columns are one block
+        if (k >= NA) return;
+        const long long i0 = ((long long)blockIdx.x + r.pf) * r.cpb;
+        if (i0 >= r.count) return;
+        a = k; nf = r.begin + (int)i0; rows = min(r.cpb, r.count - (int)i0);
+    } else {                                              // list range: one column per thread
+        if (k >= NA * r.cpb) return;
+        a = k / r.cpb;
+        const long long i = ((long long)blockIdx.x + r.pf) * r.cpb + (k - a * r.cpb);
+        if (i >= r.count) return;
+        nf = __ldg(&r.list[r.begin + i]); rows = 1;
+    }
+    const void* base = arr[0].base; unsigned cb = arr[0].col_bytes;
+#pragma unroll
+    for (int q = 1; q < NA; ++q) if (a == q) { base = arr[q].base; cb = arr[q].col_bytes; }
+    l2_prefetch(reinterpret_cast<const char*>(base) + (size_t)nf * cb, (unsigned)rows * cb);
 }
 
 // an empty gather slot: lo = 255 > hi = 0, never in range (nl <= 255)
@@ -642,6 +687,16 @@ __global__ void ADV_N1_BOUNDS k_node_lo(MeshDev m, Chunk<TB> b, NodeRange r, dou
     extern __shared__ double sm[];      // n1_smem_arrays() arrays of [nthr]; element g*L+nz0 == threadIdx.x
     const int L = m.L, nl = m.nl, nthr = blockDim.x, tid = threadIdx.x;
     const NodeThread th = node_thread(m, r);
+    if (ADV_PF_OWN & 1) {
+        PfArr pa[2 * TB + 8];
+#pragma unroll
+        for (int t = 0; t < TB; ++t) { pa[2 * t] = PfArr{b.ttf[t], (unsigned)L * 8u}; pa[2 * t + 1] = PfArr{b.ttfAB[t], (unsigned)L * 8u}; }
+        pa[2 * TB + 0] = PfArr{m.hnode, (unsigned)L * 8u}; pa[2 * TB + 1] = PfArr{m.hnode_new, (unsigned)L * 8u};
+        pa[2 * TB + 2] = PfArr{m.Z3d, (unsigned)L * 8u}; pa[2 * TB + 3] = PfArr{m.zbar3d, (unsigned)nl * 8u};
+        pa[2 * TB + 4] = PfArr{m.w, (unsigned)nl * 8u}; pa[2 * TB + 5] = PfArr{m.we, (unsigned)nl * 8u};
+        pa[2 * TB + 6] = PfArr{m.area, (unsigned)nl * 8u}; pa[2 * TB + 7] = PfArr{m.areasvol, (unsigned)nl * 8u};
+        prefetch_own_columns(r, pa);
+    }
     const int n = th.n, nz0 = th.nz0, nz = nz0 + 1, nzmin = th.nzmin, nzmax = th.nzmax;
     const bool active = th.active;
     const bool valid = active && nz >= nzmin && nz <= nzmax - 1;
@@ -862,6 +917,14 @@ __global__ void ADV_K2_BOUNDS k_fct_bounds(MeshDev m, Chunk<TB> b, NodeRange r, 
     extern __shared__ double sm[];  // [2*TB][blockDim]: tvert_max, tvert_min
     const int L = m.L, nl = m.nl;
     const NodeThread th = node_thread(m, r);
+    if (ADV_PF_OWN & 2) {
+        PfArr pa[TB + 4];
+#pragma unroll
+        for (int t = 0; t < TB; ++t) pa[t] = PfArr{b.ttf[t], (unsigned)L * 8u};
+        pa[TB + 0] = PfArr{b.lo, (unsigned)L * TB * 8u}; pa[TB + 1] = PfArr{b.adf_v, (unsigned)nl * TB * 8u};
+        pa[TB + 2] = PfArr{m.areasvol, (unsigned)nl * 8u}; pa[TB + 3] = PfArr{m.hnode_new, (unsigned)L * 8u};
+        prefetch_own_columns(r, pa);
+    }
     const int n = th.n, nz0 = th.nz0, nz = nz0 + 1;
     const bool valid = th.active && nz >= th.nzmin && nz <= th.nzmax - 1;
     const unsigned oL = (unsigned)n * L + nz0;
@@ -993,6 +1056,18 @@ __global__ void ADV_K3_BOUNDS k_fct_update(MeshDev m, Chunk<TB> b, NodeRange r, 
 {
     const int L = m.L, nl = m.nl;
     const NodeThread th = node_thread(m, r);
+    if (ADV_PF_OWN & 4) {
+        PfArr pa[3 * TB + 6];
+#pragma unroll
+        for (int t = 0; t < TB; ++t) {
+            pa[3 * t] = PfArr{b.dttf_h[t], (unsigned)L * 8u}; pa[3 * t + 1] = PfArr{b.dttf_v[t], (unsigned)L * 8u};
+            pa[3 * t + 2] = PfArr{b.ttf[t], (unsigned)L * 8u};
+        }
+        pa[3 * TB + 0] = PfArr{b.pm, (unsigned)L * TB * 16u}; pa[3 * TB + 1] = PfArr{b.adf_v, (unsigned)nl * TB * 8u};
+        pa[3 * TB + 2] = PfArr{b.lo, (unsigned)L * TB * 8u}; pa[3 * TB + 3] = PfArr{m.areasvol, (unsigned)nl * 8u};
+        pa[3 * TB + 4] = PfArr{m.hnode, (unsigned)L * 8u}; pa[3 * TB + 5] = PfArr{m.hnode_new, (unsigned)L * 8u};
+        prefetch_own_columns(r, pa);
+    }
     const int n = th.n, nz0 = th.nz0, nz = nz0 + 1;
     const bool valid = th.active && nz >= th.nzmin && nz <= th.nzmax - 1;
     if (!valid) return;
