@@ -135,6 +135,7 @@ struct adv_ctx {
     int g_lo = 3, g_k2 = 2, g_k3 = 2;         // gather batch sizes (tunable: ADV_G_LO / ADV_G_K2 / ADV_G_K3)
     int bulk = 1;                             // bulk-copy edge kernel (adv_pipe.cuh); 0 = register-gather k_edge_flux (ADV_BULK)
     int e1_ng = 8, e1_depth = 2, e1_il = 0;   // edge groups per CTA / stages / grid-strided groups (ADV_E1_NG, ADV_E1_D, ADV_E1_IL)
+    int e1_pf = 100;                          // metadata prefetch distance of the bulk edge kernel in CTAs (ADV_E1_PF)
     int force_tb1 = 0;                        // experiments: one tracer per chunk (ADV_TB1)
     int max_smem_optin = 0;
     std::vector<Peer> rpeers, speers;
@@ -300,6 +301,7 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
     if (const char* v = getenv("ADV_E1_IL")) c->e1_il = atoi(v) ? 1 : 0;
     if (const char* v = getenv("ADV_E1_D")) c->e1_depth = std::max(2, std::min(4, atoi(v)));
     if (const char* v = getenv("ADV_TB1")) c->force_tb1 = atoi(v);
+    if (const char* v = getenv("ADV_E1_PF")) c->e1_pf = std::max(0, atoi(v));
     cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
 #define CUF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { delete c; return fail(ADV_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
     CUF(c->ne_ptr.upload(ne_ptr)); CUF(c->ne_ent.upload(ne_ent));
@@ -531,7 +533,7 @@ int launch_phase(adv_ctx* c, Phase ph, int hor, int ver, bool q_stored, const Ch
                 const size_t sm = e1b_smem_bytes<TB, Q>(nge, nthr, DD); \
                 if ((int)sm <= c->max_smem_optin) { \
                     se = smem_optin(k_edge_flux_b<H, TB, Q, DD>, sm); \
-                    if (se == cudaSuccess) k_edge_flux_b<H, TB, Q, DD><<<grid, nthr, sm, s>>>(m, b, epb, ng, c->e1_il); \
+                    if (se == cudaSuccess) k_edge_flux_b<H, TB, Q, DD><<<grid, nthr, sm, s>>>(m, b, epb, ng, c->e1_il, c->e1_pf); \
                     piped = true; } }
 #define E1BD(H, Q) E1B(H, Q, 2) E1B(H, Q, 3) E1B(H, Q, 4)
             E1BD(HOR_MUSCL, 0) E1BD(HOR_MUSCL, 1) E1BD(HOR_MFCT, 0) E1BD(HOR_MFCT, 1)

@@ -98,7 +98,7 @@ __host__ __device__ inline size_t e1b_smem_bytes(int nge, int nthr, int D)
 }
 
 template <int HOR, int TB, int QMODE, int D>
-__global__ void __launch_bounds__(kBlock, ADV_E1P_MINB) k_edge_flux_b(MeshDev m, Chunk<TB> b, int epb, int ng, int il)
+__global__ void __launch_bounds__(kBlock, ADV_E1P_MINB) k_edge_flux_b(MeshDev m, Chunk<TB> b, int epb, int ng, int il, int pf)
 {
     static_assert(HOR != HOR_UPW1, "the bulk variant stages edge_up_dn_grad");
     using C = E1bCells<TB, QMODE>;
@@ -122,6 +122,20 @@ __global__ void __launch_bounds__(kBlock, ADV_E1P_MINB) k_edge_flux_b(MeshDev m,
 #pragma unroll
         for (int s = 0; s < D; ++s) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // L2 prefetch of the metadata block of the CTA `pf` launches ahead (the only dependent wait of this kernel)
+    if (pf > 0 && il == 0 && tid >= 32 && tid < 64) {
+        const long long ef = ((long long)blockIdx.x + pf) * nge;
+        if (ef < m.E) {
+            const int ne = (int)min((long long)nge, (long long)m.E - ef);
+            const int k = tid - 32;                        // 128-byte lines: 0-7 edge_cross, 8-11 edge_meta, 12-15 edge_c, 16 edge_lev
+            const char* base = nullptr; unsigned bytes = 0, off = 0;
+            if (k < 8) { base = reinterpret_cast<const char*>(m.edge_cross + ef); bytes = ne * 32u; off = k * 128u; }
+            else if (k < 12) { base = reinterpret_cast<const char*>(m.edge_meta + ef); bytes = ne * 16u; off = (k - 8) * 128u; }
+            else if (k < 16) { base = reinterpret_cast<const char*>(m.edge_c + ef); bytes = ne * 16u; off = (k - 12) * 128u; }
+            else if (k == 16) { base = reinterpret_cast<const char*>(m.edge_lev + ef); bytes = ne * 4u; off = 0; }
+            if (base && off < bytes + 127u) l2_prefetch_line(base + min(off, bytes - 1u));
+        }
     }
     for (int i = tid; i < nge; i += nthr) {
         const int gi = i / epb;
