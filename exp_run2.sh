@@ -1,5 +1,7 @@
 #!/bin/bash
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus 8 --steps 10 --warmup 3 --no-e2e > gpurun_out/r2d_bench8.json 2> gpurun_out/r2d_bench8.err
-cat gpurun_out/r2d_bench8.json; tail -2 gpurun_out/r2d_bench8.err
+timeout 900 python -m pytest tests/test_gpu_multirank.py -x -q > gpurun_out/r2p_tests2.log 2>&1
+echo "tests exit $?" >> gpurun_out/r2p_tests2.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 2 --steps 20 --warmup 3 --no-e2e > gpurun_out/r2p_bench2.json 2> gpurun_out/r2p_bench2.err
+tail -3 gpurun_out/r2p_tests2.log; grep '^{"metric' gpurun_out/r2p_bench2.json | cut -c1-330; tail -2 gpurun_out/r2p_bench2.err

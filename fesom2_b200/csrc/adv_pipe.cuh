@@ -64,6 +64,10 @@ __device__ __forceinline__ void mbar_expect(unsigned long long* b, unsigned byte
 {
     asm volatile("mbarrier.arrive.expect_tx.shared.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b)
+{
+    asm volatile("mbarrier.arrive.shared.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity)
 {
     asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
@@ -75,6 +79,9 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
 }
 
+#ifndef ADV_E1B_NOSYNC
+#define ADV_E1B_NOSYNC 1     // stage release through an mbarrier instead of a CTA-wide barrier per group
+#endif
 #ifndef ADV_E1B_DIRECT
 #define ADV_E1B_DIRECT 1     // 1: ttf/ttfAB end values are loaded straight to registers in the compute phase (not staged)
 #endif
@@ -94,7 +101,7 @@ __host__ __device__ inline size_t e1b_stage_bytes(int nthr) { return e1b_bulk_by
 template <int TB, int QMODE>
 __host__ __device__ inline size_t e1b_smem_bytes(int nge, int nthr, int D)
 {
-    return align128(e1p_meta_bytes(nge)) + (size_t)D * e1b_stage_bytes<TB, QMODE>(nthr) + 64;
+    return align128(e1p_meta_bytes(nge)) + (size_t)D * e1b_stage_bytes<TB, QMODE>(nthr) + 16 * D;
 }
 
 template <int HOR, int TB, int QMODE, int D>
@@ -120,7 +127,7 @@ __global__ void __launch_bounds__(kBlock, ADV_E1P_MINB) k_edge_flux_b(MeshDev m,
     unsigned long long* full = reinterpret_cast<unsigned long long*>(s_stage + (size_t)D * stage_bytes);
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < D; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < D; ++s) { mbar_init(&full[s], 1); mbar_init(&full[D + s], nthr); }   // full[D+s] = "stage s is free again"
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // L2 prefetch of the metadata block of the CTA `pf` launches ahead (the only dependent wait of this kernel)
@@ -221,15 +228,28 @@ __global__ void __launch_bounds__(kBlock, ADV_E1P_MINB) k_edge_flux_b(MeshDev m,
 #pragma unroll
     for (int s = 0; s < D - 1; ++s) issue(s);
     for (int i = 0; i < ngrp; ++i) {
-        // everybody is done with group i-1, whose stage the copies of group i+D-1 overwrite
+        // the copies of group i+D-1 overwrite the stage of group i-1: the issuing thread waits until all
+        // threads have released it (mbarrier, no CTA-wide barrier: the other warps run ahead)
+#if ADV_E1B_NOSYNC
+        if (tid == 0 && i >= 1 && i + D - 1 < ngrp) {
+            mbar_wait(&full[D + (i - 1) % D], (unsigned)(((i - 1) / D) & 1));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+#else
         __syncthreads();
         if (tid == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
         issue(i + D - 1);
         cpa_wait<D - 1>();
         mbar_wait(&full[i % D], (unsigned)((i / D) & 1));
         const int li = i * epb + c.g;
         const int e = (g0 + i * gs) * epb + c.g;
-        if (e >= m.E) continue;
+        if (e >= m.E) {
+#if ADV_E1B_NOSYNC
+            mbar_arrive(&full[D + i % D]);
+#endif
+            continue;
+        }
         const unsigned lvw = s_lv[li];
         const int nu1 = lvw & 0xff, nl1 = (lvw >> 8) & 0xff, nu2 = (lvw >> 16) & 0xff, nl2 = lvw >> 24;
         const int lo = nu2 > 0 ? min(nu1, nu2) : nu1, hi = max(nl1, nl2);
@@ -297,6 +317,9 @@ __global__ void __launch_bounds__(kBlock, ADV_E1P_MINB) k_edge_flux_b(MeshDev m,
             }
         }
         if (inr) stv<TB>(b.adf_h + (size_t)oe * TB, out);   // out-of-range levels are never read and stay zero
+#if ADV_E1B_NOSYNC
+        mbar_arrive(&full[D + i % D]);                         // this thread is done with the stage
+#endif
     }
 }
 
