@@ -508,11 +508,11 @@ __device__ __forceinline__ NodeThread node_thread(const MeshDev& m, const NodeRa
             l2_prefetch_line(row + m.ell_w * 16 - 1);
         }
     }
+    t.n = 0; t.nzmin = 1; t.nzmax = 0;
+    t.pad_lo = 0; t.pad_hi = 255; t.self_lo = 1; t.self_hi = 0; t.deg = 0;
     t.nz0 = c.nz0;
     const int i = blockIdx.x * r.cpb + c.g;
     t.active = i < r.count;
-    t.n = 0; t.nzmin = 1; t.nzmax = 0;
-    t.pad_lo = 0; t.pad_hi = 255; t.self_lo = 1; t.self_hi = 0; t.deg = 0;
     if (t.active) {
         t.n = r.list ? __ldg(&r.list[r.begin + i]) : r.begin + i;
         const uint2 rec = __ldg(&m.node_rec[t.n]);
