@@ -853,6 +853,29 @@ int adv_update_values(adv_ctx_t* c, int ntr, double* const* values, const double
     return ADV_OK;
 }
 
+int adv_init_tracers_AB(adv_ctx_t* c, int ntr, int ab_order, double epsilon, const double* const* values,
+                        double* const* valuesold, double* const* valuesAB, double* const* del_ttf,
+                        double* const* del_ttf_advhoriz, double* const* del_ttf_advvert)
+{
+    if (!c || !values || !valuesold || !valuesAB || ntr < 1) return fail(ADV_EINVAL, "bad argument");
+    if (ab_order != 2 && ab_order != 3)
+        return fail(ADV_EINVAL, "Adams-Bashfort tracer order must be 2 or 3, others are not supported (AB_order = " + std::to_string(ab_order) + ")");
+    CU(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->m.L * c->m.Nh;
+    const int grid = (int)((n + 255) / 256);
+    for (int i = 0; i < ntr; ++i) {
+        if (!values[i] || !valuesold[i] || !valuesAB[i]) return fail(ADV_EINVAL, "tracer " + std::to_string(i + 1) + ": null field");
+        double* d0 = del_ttf ? del_ttf[i] : nullptr;
+        double* d1 = del_ttf_advhoriz ? del_ttf_advhoriz[i] : nullptr;
+        double* d2 = del_ttf_advvert ? del_ttf_advvert[i] : nullptr;
+        if (ab_order == 2) k_init_tracers_AB<2><<<grid, 256, 0, c->s_comp>>>(n, epsilon, values[i], valuesold[i], valuesAB[i], d0, d1, d2);
+        else k_init_tracers_AB<3><<<grid, 256, 0, c->s_comp>>>(n, epsilon, values[i], valuesold[i], valuesAB[i], d0, d1, d2);
+        ++c->launches;
+    }
+    CU(cudaGetLastError());
+    return ADV_OK;
+}
+
 int adv_ctx_get_work(adv_ctx_t* c, const char* name, int slot, double* out)
 {
     if (!c || !name || !out) return fail(ADV_EINVAL, "null argument");

@@ -1281,6 +1281,31 @@ __global__ void __launch_bounds__(kBlock) k_update_values(MeshDev m, NodeRange r
     values[idx] = values[idx] + del / m.hnode_new[idx];
 }
 
+// init_tracers_AB (src/oce_tracer_mod.F90:28-34, :45-54, :97-122): one thread per (layer, node) of ALL
+// Nh columns; evaluation order of the Fortran expressions, no contraction.
+template <int ORDER>
+__global__ void __launch_bounds__(256) k_init_tracers_AB(size_t n, double eps, const double* __restrict__ values,
+                                                         double* __restrict__ vold, double* __restrict__ vab,
+                                                         double* __restrict__ d0, double* __restrict__ d1, double* __restrict__ d2)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = values[i];
+    if (ORDER == 2) {
+        const double o1 = vold[i];
+        vab[i] = -(0.5 + eps) * o1 + (1.5 + eps) * v;
+        vold[i] = v;
+    } else {
+        const double o1 = vold[2 * i], o2 = vold[2 * i + 1];
+        const double t = 5.0 * o2 - 16.0 * o1 + 23.0 * v;
+        vab[i] = t / 12.0;
+        vold[2 * i + 1] = o1; vold[2 * i] = v;
+    }
+    if (d0) d0[i] = 0.0;
+    if (d1) d1[i] = 0.0;
+    if (d2) d2[i] = 0.0;
+}
+
 // self-test of div_rcp against the IEEE division: returns the number of mismatching results over
 // `count` pseudo-random operand pairs (mode 0: b = 6, 1: b = 3, 2: random b in [1e-3, 1e13])
 __global__ void k_selftest_div(unsigned long long count, unsigned long long seed, int mode, unsigned long long* bad)

@@ -62,7 +62,7 @@ class TracerDesc(C.Structure):
 
 EXPORTS = ["adv_ctx_create", "adv_ctx_destroy", "adv_last_error", "adv_comm_unique_id",
            "adv_ctx_comm_init", "adv_ctx_set_state", "adv_do_oce_adv_tra", "adv_do_oce_adv_tra_async",
-           "adv_ctx_synchronize", "adv_exchange_nod", "adv_update_values", "adv_ctx_get_work",
+           "adv_ctx_synchronize", "adv_exchange_nod", "adv_update_values", "adv_init_tracers_AB", "adv_ctx_get_work",
            "adv_ctx_launch_count", "adv_ctx_stream", "adv_ctx_last_elapsed_ms",
            "adv_ctx_set_profiling", "adv_ctx_phase_ms", "adv_selftest_div"]
 
@@ -92,6 +92,7 @@ def load_library():
         L.adv_ctx_synchronize.argtypes = [C.c_void_p]
         L.adv_exchange_nod.argtypes = [C.c_void_p, C.c_int, C.POINTER(c_dp), C.c_int]
         L.adv_update_values.argtypes = [C.c_void_p, C.c_int, C.POINTER(c_dp), C.POINTER(c_dp), C.POINTER(c_dp)]
+        L.adv_init_tracers_AB.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double] + [C.POINTER(c_dp)] * 6
         L.adv_ctx_get_work.argtypes = [C.c_void_p, C.c_char_p, C.c_int, c_dp]
         L.adv_ctx_last_elapsed_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.adv_ctx_set_profiling.argtypes = [C.c_void_p, C.c_int]
@@ -230,6 +231,19 @@ class AdvB200:
         PA = c_dp * n
         _check(self.lib.adv_update_values(self.h, n, PA(*[_ptr(v) for v in values]),
                                           PA(*[_ptr(v) for v in dttf_h]), PA(*[_ptr(v) for v in dttf_v])))
+
+    def init_tracers_AB(self, values: Sequence, valuesold: Sequence, valuesAB: Sequence, ab_order: int = 2,
+                        epsilon: float = 0.1, del_ttf: Optional[Sequence] = None, dttf_h: Optional[Sequence] = None,
+                        dttf_v: Optional[Sequence] = None):
+        """``init_tracers_AB`` (src/oce_tracer_mod.F90:13-123) for a batch: AB2/AB3 extrapolation into
+        valuesAB, rotation of valuesold, zeroing of the tendencies.  Device tensors, asynchronous."""
+        n = len(values)
+        PA = c_dp * n
+
+        def arr(lst):
+            return PA(*[_ptr(v) for v in lst]) if lst is not None else None
+        _check(self.lib.adv_init_tracers_AB(self.h, n, int(ab_order), float(epsilon), arr(values), arr(valuesold),
+                                            arr(valuesAB), arr(del_ttf), arr(dttf_h), arr(dttf_v)))
 
     # -- introspection ------------------------------------------------------------------------
     def get_work(self, name: str, slot: int = 0) -> np.ndarray:

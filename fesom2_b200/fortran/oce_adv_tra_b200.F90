@@ -94,6 +94,27 @@ module oce_adv_tra_b200
        type(adv_tracer_desc_t), intent(in) :: tr(*)
        integer(c_int), value :: where
      end function
+     ! device-resident dwarf loop (dwarf_ini/fesom.F90:85-128): prologue, epilogue, halo exchange
+     integer(c_int) function adv_init_tracers_AB(ctx, ntr, ab_order, epsilon, values, valuesold, valuesAB, &
+                                                 del_ttf, del_ttf_advhoriz, del_ttf_advvert) bind(C, name='adv_init_tracers_AB')
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value    :: ctx
+       integer(c_int), value :: ntr, ab_order
+       real(c_double), value :: epsilon
+       type(c_ptr), value    :: values, valuesold, valuesAB, del_ttf, del_ttf_advhoriz, del_ttf_advvert   ! arrays of ntr device pointers
+     end function
+     integer(c_int) function adv_update_values(ctx, ntr, values, del_ttf_advhoriz, del_ttf_advvert) bind(C, name='adv_update_values')
+       import :: c_ptr, c_int
+       type(c_ptr), value    :: ctx
+       integer(c_int), value :: ntr
+       type(c_ptr), value    :: values, del_ttf_advhoriz, del_ttf_advvert
+     end function
+     integer(c_int) function adv_exchange_nod(ctx, nfields, fields, nlev) bind(C, name='adv_exchange_nod')
+       import :: c_ptr, c_int
+       type(c_ptr), value    :: ctx
+       integer(c_int), value :: nfields, nlev
+       type(c_ptr), value    :: fields
+     end function
   end interface
 
   type(c_ptr), save :: adv_b200_ctx = c_null_ptr   ! one context per MPI rank (one rank <-> one GPU)

@@ -138,6 +138,18 @@ int adv_exchange_nod(adv_ctx_t *ctx, int nfields, double *const *fields, int nle
 int adv_update_values(adv_ctx_t *ctx, int ntr, double *const *values,
                       const double *const *del_ttf_advhoriz, const double *const *del_ttf_advvert);
 
+/* The prologue of the tracer step, `init_tracers_AB(tr_num, tracers, partit, mesh)`
+ * (src/oce_tracer_mod.F90:13-123) without its gradient calls, for ntr tracers: zeroes del_ttf /
+ * del_ttf_advhoriz / del_ttf_advvert (each may be NULL), sets valuesAB from the Adams-Bashforth
+ * extrapolation of order ab_order (2: -(0.5+eps)*valuesold(1) + (1.5+eps)*values; 3: (5*valuesold(2)
+ * - 16*valuesold(1) + 23*values)/12) and rotates valuesold.  valuesold has the reference layout
+ * (ab_order-1, nl-1, Nh), first index fastest.  epsilon = o_PARAM epsilon (src/oce_modules.F90:105).
+ * Any other order returns ADV_EINVAL (the reference stops with par_ex).  DEVICE pointers, asynchronous
+ * on the context's stream. */
+int adv_init_tracers_AB(adv_ctx_t *ctx, int ntr, int ab_order, double epsilon,
+                        const double *const *values, double *const *valuesold, double *const *valuesAB,
+                        double *const *del_ttf, double *const *del_ttf_advhoriz, double *const *del_ttf_advvert);
+
 /* --- introspection (tests, profiling) -------------------------------------------------------- */
 /* Copies an internal work array of tracer slot `slot` to a HOST buffer.  name is one of
  * "fct_LO" (nl-1,Nh), "adv_flux_hor" (nl-1,E), "adv_flux_ver" (nl,N), "fct_plus", "fct_minus"

@@ -251,3 +251,19 @@ class NumpyAdv:
             val = np.stack([np.where(self.scat, c / a1, 0.0), np.where(self.scat, -(c / a2), 0.0)], 1).reshape(-1, L)
         np.add.at(dttf_h, idx, val)
         return dttf_h, dttf_v
+
+
+def init_tracers_AB(values, valuesold, ab_order=2, epsilon=0.1):
+    """src/oce_tracer_mod.F90:45-54, :97-122: returns (valuesAB, new valuesold).  ``valuesold`` has the shape
+    (Nh, L, ab_order-1) (the reference's (ab_order-1, nl-1, Nh) read in C order)."""
+    v = np.asarray(values, dtype=np.float64)
+    o = np.asarray(valuesold, dtype=np.float64)
+    if ab_order == 2:
+        vab = -(0.5 + epsilon) * o[..., 0] + (1.5 + epsilon) * v
+        new = v[..., None].copy()
+    elif ab_order == 3:
+        vab = (5.0 * o[..., 1] - 16.0 * o[..., 0] + 23.0 * v) / 12.0
+        new = np.stack([v, o[..., 0]], axis=-1)
+    else:
+        raise ValueError("Adams-Bashfort tracer order must be 2 or 3")
+    return vab, new

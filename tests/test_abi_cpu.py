@@ -15,7 +15,7 @@ HEADER = os.path.join(ROOT, "include", "fesom_adv_b200.h")
 def _declared():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(adv_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(adv_[A-Za-z0-9_]+)\s*\(", src)))
 
 
 @pytest.fixture(scope="module")

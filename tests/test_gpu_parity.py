@@ -185,3 +185,34 @@ def test_unaligned_device_pointers_are_staged(small_mesh):
     ctx.do_oce_adv_tra(dt, trs_d, dh, dv)
     _compare(small_mesh, ctx, [x.cpu().numpy() for x in dh], [x.cpu().numpy() for x in dv], ora, 2)
     ctx.close()
+
+
+@pytest.mark.parametrize("order", [2, 3])
+def test_init_tracers_AB(small_mesh, order):
+    """the prologue of the tracer step (src/oce_tracer_mod.F90:13-123), bit for bit against the NumPy restatement"""
+    from fesom2_b200.driver import AdvB200, AdvError, ADV_EINVAL
+    from oracle import numpy_ref as R
+    g = small_mesh
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(20261017)
+    v = rng.normal(10.0, 3.0, (g.Nh, g.L))
+    o = rng.normal(10.0, 3.0, (g.Nh, g.L, order - 1))
+    ref_ab, ref_old = R.init_tracers_AB(v, o, order, 0.1)
+    ctx = AdvB200(g, M_nb(g), max_tracers=1)
+    tv, to = torch.as_tensor(v, device=dev), torch.as_tensor(o, device=dev).contiguous()
+    tab = torch.empty_like(tv)
+    d = [torch.full_like(tv, 7.0) for _ in range(3)]
+    ctx.init_tracers_AB([tv], [to], [tab], order, 0.1, [d[0]], [d[1]], [d[2]])
+    ctx.synchronize()
+    assert np.array_equal(tab.cpu().numpy(), ref_ab)
+    assert np.array_equal(to.cpu().numpy(), ref_old)
+    assert all(float(x.abs().max()) == 0.0 for x in d)
+    with pytest.raises(AdvError) as ei:
+        ctx.init_tracers_AB([tv], [to], [tab], 4, 0.1)
+    assert ei.value.code == ADV_EINVAL
+    ctx.close()
+
+
+def M_nb(g):
+    from fesom2_b200 import mesh as M
+    return M.nboundary_lay(g)
