@@ -458,7 +458,13 @@ namespace {
 struct Group { int fct, hor, ver; std::vector<int> idx; };
 struct ChunkSel { int fct, hor, ver, tb; int idx[2]; int buf; };
 
-inline int cols_per_block(int L) { return kBlock / L; }
+// columns per CTA: as many as fit into 224 threads (7 warps) -- the size the per-kernel register
+// budgets were tuned for (4-5 resident CTAs per SM); one column when a column alone is longer
+inline int cols_per_block(int L)
+{
+    static const int limit = getenv("ADV_CTA_THREADS") ? std::max(32, std::min(kBlock, atoi(getenv("ADV_CTA_THREADS")))) : 224;
+    return std::max(1, limit / L);
+}
 inline int nblocks(int count, int cpb) { return (count + cpb - 1) / cpb; }
 
 struct TrPtrs {   // device pointers of the call's tracers
