@@ -39,6 +39,9 @@ enum { HOR_UPW1 = 0, HOR_MUSCL = 1, HOR_MFCT = 2 };
 enum { VER_UPW1 = 0, VER_QR4C = 1, VER_PPM = 2, VER_CDIFF = 3 };
 
 constexpr int kBlock = 256;
+#ifndef ADV_QR4C_RCP
+#define ADV_QR4C_RCP 1   // k_node_lo: one reciprocal per thread shared through smem instead of six IEEE divisions
+#endif
 #ifndef ADV_PF_OWN
 #define ADV_PF_OWN 4     // bit mask N1|K2|K3: also pull the next CTAs' own columns into L2 (helps K3 only: 1.37 -> 1.26 ms)
 #endif
@@ -349,6 +352,33 @@ __device__ __forceinline__ double ver_qr4c_s(const ColV& c, const double* S, int
         const double zb = CZB(k);
         const double Tmean1 = CT(k) + div3((2 * qc + qu) * (zb - CZ(k)));
         const double Tmean2 = CT(k - 1) + div3((2 * qc + qd) * (zb - CZ(k - 1)));
+        const double w = CW(k);
+        const double Tmean = (w + fabs(w)) * Tmean1 + (w - fabs(w)) * Tmean2;
+        v = (-0.5 * (1.0 - c.num_ord) * Tmean - c.num_ord * (0.5 * (Tmean1 + Tmean2)) * w) * CA(k) - v;
+    }
+    return v;
+}
+
+// adv_tra_ver_qr4c with the reciprocals of the three layer-centre distances taken from a per-column
+// array R(j) = RN(1 / (Z(j-1) - Z(j))), j in [nzmin+1, nzmax-1]: each thread computes ONE reciprocal
+// (the only IEEE division left) and the six slopes of :417-419 (3 per tracer) become div_rcp, which is
+// bit-identical to the division (adv_selftest_div).
+__device__ __forceinline__ double ver_qr4c_r(const ColV& c, const double* R, int k, double fin)
+{
+    double v = fin;
+    if (k == c.nzmin) v = -CT(k) * CW(k) * CA(k) - v;
+    if (k == c.nzmin + 1) v = -0.5 * (CT(k - 1) + CT(k)) * CW(k) * CA(k) - v;
+    if (k == c.nzmax - 1) v = -0.5 * (CT(k - 1) + CT(k)) * CW(k) * CA(k) - v;
+    if (k == c.nzmax) v = 0.0 - v;
+    if (k >= c.nzmin + 2 && k <= c.nzmax - 2) {
+        const double t0 = CT(k), tm1 = CT(k - 1), tm2 = CT(k - 2), tp1 = CT(k + 1);
+        const double z0 = CZ(k), zm1 = CZ(k - 1), zm2 = CZ(k - 2), zp1 = CZ(k + 1);
+        const double qc = div_rcp(tm1 - t0, zm1 - z0, R[k - 1]);
+        const double qu = div_rcp(t0 - tp1, z0 - zp1, R[k]);
+        const double qd = div_rcp(tm2 - tm1, zm2 - zm1, R[k - 2]);
+        const double zb = CZB(k);
+        const double Tmean1 = t0 + div3((2 * qc + qu) * (zb - z0));
+        const double Tmean2 = tm1 + div3((2 * qc + qd) * (zb - zm1));
         const double w = CW(k);
         const double Tmean = (w + fabs(w)) * Tmean1 + (w - fabs(w)) * Tmean2;
         v = (-0.5 * (1.0 - c.num_ord) * Tmean - c.num_ord * (0.5 * (Tmean1 + Tmean2)) * w) * CA(k) - v;
@@ -679,7 +709,7 @@ __global__ void __launch_bounds__(kBlock, ADV_E1_MINB) k_edge_flux(MeshDev m, Ch
 // from there: one memory wait per thread instead of one per stencil point.
 // ----------------------------------------------------------------------------------------------
 template <int VER, int TB>
-__host__ __device__ constexpr int n1_smem_arrays() { return 3 * TB + 5 + (VER == VER_PPM ? 2 : 0); }
+__host__ __device__ constexpr int n1_smem_arrays() { return 3 * TB + 5 + (VER == VER_PPM ? 2 : 0) + (VER == VER_QR4C && ADV_QR4C_RCP ? 1 : 0); }
 
 template <int VER, int TB, int G>
 __global__ void ADV_N1_BOUNDS k_node_lo(MeshDev m, Chunk<TB> b, NodeRange r, double dt)
@@ -712,6 +742,7 @@ __global__ void ADV_N1_BOUNDS k_node_lo(MeshDev m, Chunk<TB> b, NodeRange r, dou
     double* s_area = s_we + nthr;
     double* s_hn = s_area + nthr;                     // PPM only
     double* s_hnn = s_hn + nthr;                      // PPM only
+    double* s_rdz = s_area + nthr;                    // QR4C only (aliases s_hn, which QR4C does not use)
 
     // ---- all global loads ---------------------------------------------------------------------
     int4 ent[G];
@@ -731,6 +762,9 @@ __global__ void ADV_N1_BOUNDS k_node_lo(MeshDev m, Chunk<TB> b, NodeRange r, dou
         zz = __ldg(&m.Z3d[oL]); zb = __ldg(&m.zbar3d[cN + nz0]);
         ww = __ldg(&m.w[cN + nz0]); wwe = __ldg(&m.we[cN + nz0]); ar = __ldg(&m.area[cN + nz0]);
     }
+    double zup = 0.0;                                 // Z of the layer above (an L1 hit: the thread above loads it too)
+    const bool has_rdz = VER == VER_QR4C && ADV_QR4C_RCP && valid && nz > nzmin;
+    if (has_rdz) zup = __ldg(&m.Z3d[oL - 1]);
 #pragma unroll
     for (int j = 0; j < G; ++j) {
         const int lo = ent[j].z & 0xff, hi = (ent[j].z >> 8) & 0xff;
@@ -750,6 +784,7 @@ __global__ void ADV_N1_BOUNDS k_node_lo(MeshDev m, Chunk<TB> b, NodeRange r, dou
     for (int t = 0; t < TB; ++t) { s_ttf[t * nthr + tid] = tn[t]; s_tab[t * nthr + tid] = tab[t]; }
     s_Z[tid] = zz; s_zbar[tid] = zb; s_w[tid] = ww; s_we[tid] = wwe; s_area[tid] = ar;
     if (VER == VER_PPM) { s_hn[tid] = hn; s_hnn[tid] = hnn; }
+    if (VER == VER_QR4C && ADV_QR4C_RCP) s_rdz[tid] = has_rdz ? 1.0 / (zup - zz) : 0.0;
     __syncthreads();
 
     // ---- horizontal LO gather: ordered accumulation ----------------------------------------------
@@ -806,7 +841,8 @@ __global__ void ADV_N1_BOUNDS k_node_lo(MeshDev m, Chunk<TB> b, NodeRange r, dou
             if (m.use_wsplit) { c.w = s_w + c0; flo = ver_upw1(c, nz, 0.0); }  // driver :333
             c.ttf = s_tab + t * nthr + c0; c.w = s_w + c0; c.num_ord = b.pv[t];
             flo_top[t] = fe;
-            adfv_top[t] = ver_flux<VER>(c, nz, flo);                    // driver :363-379
+            if (VER == VER_QR4C && ADV_QR4C_RCP) adfv_top[t] = ver_qr4c_r(c, s_rdz + c0, nz, flo);
+            else adfv_top[t] = ver_flux<VER>(c, nz, flo);               // driver :363-379
         }
     }
 #pragma unroll

@@ -83,12 +83,13 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
 #define ADV_E1B_NOSYNC 1     // stage release through an mbarrier instead of a CTA-wide barrier per group
 #endif
 #ifndef ADV_E1B_DIRECT
-#define ADV_E1B_DIRECT 1     // 1: ttf/ttfAB end values are loaded straight to registers in the compute phase (not staged)
+#define ADV_E1B_DIRECT 2     // 0: every operand staged in cp.async cells; 1: ttf/ttfAB end values loaded straight to registers
+                             // in the compute phase; 2: uv/helem/Q too (only edge_up_dn_grad is staged, by bulk copy)
 #endif
 template <int TB, int QMODE>
 struct E1bCells {
-    static constexpr int n16 = (QMODE == 0 ? 2 : 0);
-    static constexpr int n8 = (ADV_E1B_DIRECT ? 0 : 4 * TB) + (QMODE == 0 ? 2 : 1);   // + he1, he2 (QMODE 0) or q (QMODE 1)
+    static constexpr int n16 = (ADV_E1B_DIRECT == 2 ? 0 : (QMODE == 0 ? 2 : 0));
+    static constexpr int n8 = ADV_E1B_DIRECT == 2 ? 0 : (ADV_E1B_DIRECT ? 0 : 4 * TB) + (QMODE == 0 ? 2 : 1);   // + he1, he2 (QMODE 0) or q (QMODE 1)
     static constexpr int bytes = 16 * n16 + 8 * n8;     // per thread and stage
     static constexpr int c_uv = 0;
     static constexpr int c_t1 = 0, c_t2 = TB, c_a1 = 2 * TB, c_a2 = 3 * TB, c_he = (ADV_E1B_DIRECT ? 0 : 4 * TB);
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(kBlock, ADV_E1P_MINB) k_edge_flux_b(MeshDev m,
                 }
             }
             const int li = i * epb + c.g;
-            if (eg + c.g < m.E) {
+            if (ADV_E1B_DIRECT != 2 && eg + c.g < m.E) {
                 const int4 em = s_em[li];
                 const unsigned lvw = s_lv[li];
                 const int nu1 = lvw & 0xff, nl1 = (lvw >> 8) & 0xff, nu2 = (lvw >> 16) & 0xff, nl2 = lvw >> 24;
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(kBlock, ADV_E1P_MINB) k_edge_flux_b(MeshDev m,
                 }
             }
         }
-        cpa_commit();
+        if (ADV_E1B_DIRECT != 2) cpa_commit();
     };
 
 #pragma unroll
@@ -240,11 +241,11 @@ __global__ void __launch_bounds__(kBlock, ADV_E1P_MINB) k_edge_flux_b(MeshDev m,
         if (tid == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #endif
         issue(i + D - 1);
-        cpa_wait<D - 1>();
-        mbar_wait(&full[i % D], (unsigned)((i / D) & 1));
+        if (ADV_E1B_DIRECT != 2) cpa_wait<D - 1>();
         const int li = i * epb + c.g;
         const int e = (g0 + i * gs) * epb + c.g;
-        if (e >= m.E) {
+        if (e >= m.E) {                                       // no edge (partial last CTA): keep in step with the others
+            mbar_wait(&full[i % D], (unsigned)((i / D) & 1));
 #if ADV_E1B_NOSYNC
             mbar_arrive(&full[D + i % D]);
 #endif
@@ -277,25 +278,32 @@ __global__ void __launch_bounds__(kBlock, ADV_E1P_MINB) k_edge_flux_b(MeshDev m,
             }
         }
         double q = 0.0;
+        bool use1 = false, use2 = false;
+        double2 uv1 = make_double2(0.0, 0.0), uv2 = uv1;
+        double he1 = 0.0, he2 = 0.0;
         if (QMODE == 0) {
-            bool use1, use2;
             edge_use(make_uchar4(nu1, nl1, nu2, nl2), nz, use1, use2);
+            if (ADV_E1B_DIRECT == 2) {                       // element columns straight from L1/L2 (three edges share them)
+                const int4 em = s_em[li];
+                if (use1) { const unsigned o = (unsigned)em.z * L + nz0; uv1 = __ldg(reinterpret_cast<const double2*>(m.uv) + o); he1 = __ldg(&m.helem[o]); }
+                if (use2) { const unsigned o = (unsigned)em.w * L + nz0; uv2 = __ldg(reinterpret_cast<const double2*>(m.uv) + o); he2 = __ldg(&m.helem[o]); }
+            } else {
+                if (use1) { uv1 = c16[(C::c_uv + 0) * nthr]; he1 = c8[(C::c_he + 0) * nthr]; }
+                if (use2) { uv2 = c16[(C::c_uv + 1) * nthr]; he2 = c8[(C::c_he + 1) * nthr]; }
+            }
+        } else if (inr) q = ADV_E1B_DIRECT == 2 ? __ldg(&m.Q[oe]) : c8[C::c_he * nthr];
+        mbar_wait(&full[i % D], (unsigned)((i / D) & 1));   // the bulk-copied gradient columns of group i
+        if (QMODE == 0) {
             const double2 cr12 = s_cr[2 * li], cr34 = s_cr[2 * li + 1];
             double v1 = 0.0, v2 = 0.0;
             // Q(nz,e): vflux of oce_adv_tra_hor.F90:170,190,211-212,226,242
-            if (use1) {
-                const double2 uv1 = c16[(C::c_uv + 0) * nthr];
-                v1 = (-uv1.y * cr12.x + uv1.x * cr12.y) * c8[(C::c_he + 0) * nthr];
-            }
-            if (use2) {
-                const double2 uv2 = c16[(C::c_uv + 1) * nthr];
-                v2 = (uv2.y * cr34.x - uv2.x * cr34.y) * c8[(C::c_he + 1) * nthr];
-            }
+            if (use1) v1 = (-uv1.y * cr12.x + uv1.x * cr12.y) * he1;
+            if (use2) v2 = (uv2.y * cr34.x - uv2.x * cr34.y) * he2;
             if (use1 && use2) q = v1 + v2;
             else if (use1) q = v1;
             else if (use2) q = v2;
             if (use1 || use2 || inr) m.Q[oe] = q;       // dry levels keep the zero of the allocation
-        } else if (inr) q = c8[C::c_he * nthr];
+        }
         double out[TB];
 #pragma unroll
         for (int t = 0; t < TB; ++t) out[t] = 0.0;
