@@ -43,7 +43,7 @@ constexpr int kBlock = 256;
 #define ADV_QR4C_RCP 1   // k_node_lo: one reciprocal per thread shared through smem instead of six IEEE divisions
 #endif
 #ifndef ADV_PF_OWN
-#define ADV_PF_OWN 4     // bit mask N1|K2|K3: also pull the next CTAs' own columns into L2 (helps K3 only: 1.37 -> 1.26 ms)
+#define ADV_PF_OWN 5     // bit mask N1|K2|K3: also pull the next CTAs' own columns into L2 (K3: 1.37 -> 1.26 ms, N1: -1 %, K2: nothing)
 #endif
 // minimum resident CTAs per SM (register caps): measured on B200, see DESIGN.md section 4 --
 // occupancy beats register-resident batching: 4-5 CTAs of 7 warps with a few spilled words run
