@@ -130,6 +130,11 @@ struct adv_ctx {
     DevBuf<double4> edge_cross;
     DevBuf<double2> edge_c;
     DevBuf<double> area, areasvol, r_areasvol, Q;
+    // gradient producer (adv_ctx_set_gradient_mesh)
+    DevBuf<int> g_nie, g_nie_num, g_nlevels, g_ulevels, g_tri, g_nmin, g_umax, g_elem_nodes;
+    DevBuf<double> g_sca, g_earea;
+    GradMeshDev gm{};
+    bool grad_mesh_set = false;
     int nS = 0, nI = 0, nSH = 0;
     int pf_dist = 200;                        // L2 prefetch distance of the node kernels in CTAs (ADV_PF; 0 = off)
     int g_lo = 3, g_k2 = 2, g_k3 = 2;         // gather batch sizes (tunable: ADV_G_LO / ADV_G_K2 / ADV_G_K3)
@@ -320,6 +325,10 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
         CUF(c->r_areasvol.upload(tmp));
     }
     CUF(c->Q.alloc((size_t)L * E));
+    {
+        std::vector<int> en(d->elem2D_nodes, d->elem2D_nodes + (size_t)3 * T);
+        CUF(c->g_elem_nodes.upload(en));
+    }
 
     // ---- halo bookkeeping (com_nod2D) ------------------------------------------------------------
     if (c->npes > 1) {
@@ -876,6 +885,84 @@ int adv_init_tracers_AB(adv_ctx_t* c, int ntr, int ab_order, double epsilon, con
         double* d2 = del_ttf_advvert ? del_ttf_advvert[i] : nullptr;
         if (ab_order == 2) k_init_tracers_AB<2><<<grid, 256, 0, c->s_comp>>>(n, epsilon, values[i], valuesold[i], valuesAB[i], d0, d1, d2);
         else k_init_tracers_AB<3><<<grid, 256, 0, c->s_comp>>>(n, epsilon, values[i], valuesold[i], valuesAB[i], d0, d1, d2);
+        ++c->launches;
+    }
+    CU(cudaGetLastError());
+    return ADV_OK;
+}
+
+int adv_ctx_set_gradient_mesh(adv_ctx_t* c, const adv_gradient_mesh_desc_t* g)
+{
+    if (!c || !g) return fail(ADV_EINVAL, "null argument");
+    if (!g->nod_in_elem2D || !g->nod_in_elem2D_num || !g->nlevels || !g->ulevels || !g->edge_up_dn_tri ||
+        !g->nlevels_nod2D_min || !g->ulevels_nod2D_max || !g->gradient_sca || !g->elem_area)
+        return fail(ADV_EINVAL, "adv_ctx_set_gradient_mesh: null array");
+    CU(cudaSetDevice(c->device));
+    const MeshDev& m = c->m;
+    const int ne = g->n_elem, nn = g->n_nod_in_elem, ld = g->nod_in_elem2D_ld;
+    if (ne < m.T || nn < 1 || nn > m.Nh || ld < 1) return fail(ADV_EINVAL, "adv_ctx_set_gradient_mesh: dimensions out of range");
+    for (int e = 0; e < m.E; ++e)
+        for (int k = 0; k < 2; ++k)
+            if (g->edge_up_dn_tri[2 * e + k] < 0 || g->edge_up_dn_tri[2 * e + k] > ne)
+                return fail(ADV_EINVAL, "edge_up_dn_tri out of range at edge " + std::to_string(e + 1));
+    for (int n = 0; n < nn; ++n) {
+        if (g->nod_in_elem2D_num[n] < 0 || g->nod_in_elem2D_num[n] > ld) return fail(ADV_EINVAL, "nod_in_elem2D_num out of range");
+        for (int k = 0; k < g->nod_in_elem2D_num[n]; ++k)
+            if (g->nod_in_elem2D[(size_t)n * ld + k] < 1 || g->nod_in_elem2D[(size_t)n * ld + k] > ne)
+                return fail(ADV_EINVAL, "nod_in_elem2D out of range at node " + std::to_string(n + 1));
+    }
+    // every end node of a local edge needs its element neighbourhood (src/oce_muscl_adv.F90:397,:420)
+    {
+        std::vector<int4> em(m.E);
+        CU(cudaMemcpy(em.data(), m.edge_meta, sizeof(int4) * m.E, cudaMemcpyDeviceToHost));
+        for (int e = 0; e < m.E; ++e)
+            if (em[e].x >= nn || em[e].y >= nn)
+                return fail(ADV_EINVAL, "nod_in_elem2D does not cover the end nodes of edge " + std::to_string(e + 1));
+    }
+    auto up_i = [&](DevBuf<int>& b, const int32_t* p, size_t n) { return b.upload(std::vector<int>(p, p + n)); };
+    auto up_d = [&](DevBuf<double>& b, const double* p, size_t n) { return b.upload(std::vector<double>(p, p + n)); };
+    CU(up_i(c->g_nie, g->nod_in_elem2D, (size_t)nn * ld)); CU(up_i(c->g_nie_num, g->nod_in_elem2D_num, nn));
+    CU(up_i(c->g_nlevels, g->nlevels, ne)); CU(up_i(c->g_ulevels, g->ulevels, ne));
+    CU(up_i(c->g_tri, g->edge_up_dn_tri, (size_t)2 * m.E));
+    CU(up_i(c->g_nmin, g->nlevels_nod2D_min, m.Nh)); CU(up_i(c->g_umax, g->ulevels_nod2D_max, m.Nh));
+    CU(up_d(c->g_sca, g->gradient_sca, (size_t)6 * m.T)); CU(up_d(c->g_earea, g->elem_area, ne));
+    GradMeshDev& gm = c->gm;
+    gm.n_elem = ne; gm.n_nie = nn; gm.ld = ld;
+    gm.nie = c->g_nie.p; gm.nie_num = c->g_nie_num.p; gm.nlevels = c->g_nlevels.p; gm.ulevels = c->g_ulevels.p;
+    gm.up_dn_tri = c->g_tri.p; gm.nmin = c->g_nmin.p; gm.umax = c->g_umax.p; gm.elem_nodes = c->g_elem_nodes.p;
+    gm.gsca = c->g_sca.p; gm.earea = c->g_earea.p;
+    c->grad_mesh_set = true;
+    return ADV_OK;
+}
+
+int adv_tracer_gradient_elements(adv_ctx_t* c, int ntr, const double* const* ttf, double* const* tr_xy)
+{
+    if (!c || !ttf || !tr_xy || ntr < 1) return fail(ADV_EINVAL, "bad argument");
+    if (!c->grad_mesh_set) return fail(ADV_ESTATE, "adv_ctx_set_gradient_mesh has not been called");
+    CU(cudaSetDevice(c->device));
+    const MeshDev& m = c->m;
+    const int cpb = cols_per_block(m.L);
+    for (int i = 0; i < ntr; ++i) {
+        if (!ttf[i] || !tr_xy[i]) return fail(ADV_EINVAL, "tracer " + std::to_string(i + 1) + ": null field");
+        if ((uintptr_t)tr_xy[i] & 15u) return fail(ADV_EINVAL, "tr_xy must be 16-byte aligned");
+        k_tracer_gradient_elements<<<nblocks(m.T, cpb), cpb * m.L, 0, c->s_comp>>>(m, c->gm, cpb, ttf[i], tr_xy[i]);
+        ++c->launches;
+    }
+    CU(cudaGetLastError());
+    return ADV_OK;
+}
+
+int adv_fill_up_dn_grad(adv_ctx_t* c, int ntr, const double* const* tr_xy, double* const* edge_up_dn_grad)
+{
+    if (!c || !tr_xy || !edge_up_dn_grad || ntr < 1) return fail(ADV_EINVAL, "bad argument");
+    if (!c->grad_mesh_set) return fail(ADV_ESTATE, "adv_ctx_set_gradient_mesh has not been called");
+    CU(cudaSetDevice(c->device));
+    const MeshDev& m = c->m;
+    const int cpb = cols_per_block(m.L);
+    for (int i = 0; i < ntr; ++i) {
+        if (!tr_xy[i] || !edge_up_dn_grad[i]) return fail(ADV_EINVAL, "tracer " + std::to_string(i + 1) + ": null field");
+        if ((uintptr_t)tr_xy[i] & 15u) return fail(ADV_EINVAL, "tr_xy must be 16-byte aligned");
+        k_fill_up_dn_grad<<<nblocks(m.E, cpb), cpb * m.L, 0, c->s_comp>>>(m, c->gm, cpb, tr_xy[i], edge_up_dn_grad[i]);
         ++c->launches;
     }
     CU(cudaGetLastError());

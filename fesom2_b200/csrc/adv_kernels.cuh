@@ -1342,6 +1342,95 @@ __global__ void __launch_bounds__(256) k_init_tracers_AB(size_t n, double eps, c
     if (d2) d2[i] = 0.0;
 }
 
+// ----------------------------------------------------------------------------------------------
+// The producer of edge_up_dn_grad, first version: correct and coalesced,
+// not yet fused into the edge kernel.
+// ----------------------------------------------------------------------------------------------
+struct GradMeshDev {
+    int n_elem, n_nie, ld;
+    const int* nie;          // (ld, n_nie) nod_in_elem2D, 1-based
+    const int* nie_num;      // (n_nie)
+    const int* nlevels;      // (n_elem)
+    const int* ulevels;      // (n_elem)
+    const int* up_dn_tri;    // (2, E) 1-based, 0 = none
+    const int* nmin;         // (Nh) nlevels_nod2D_min
+    const int* umax;         // (Nh) ulevels_nod2D_max
+    const int* elem_nodes;   // (3, T) 1-based
+    const double* gsca;      // (6, T)
+    const double* earea;     // (n_elem)
+};
+
+// tracer_gradient_elements, src/oce_tracer_mod.F90:171-180: one thread per (element, layer)
+__global__ void __launch_bounds__(kBlock) k_tracer_gradient_elements(MeshDev m, GradMeshDev g, int cpb,
+                                                                     const double* __restrict__ ttf, double* __restrict__ tr_xy)
+{
+    const ColThread c = col_thread(m);
+    const int el = blockIdx.x * cpb + c.g;
+    if (c.g >= cpb || el >= m.T) return;
+    const int nz = c.nz0 + 1;
+    if (nz < __ldg(&g.ulevels[el]) || nz > __ldg(&g.nlevels[el]) - 1) return;
+    const int n1 = __ldg(&g.elem_nodes[3 * el]) - 1, n2 = __ldg(&g.elem_nodes[3 * el + 1]) - 1, n3 = __ldg(&g.elem_nodes[3 * el + 2]) - 1;
+    const double t1 = __ldg(&ttf[(size_t)n1 * m.L + c.nz0]), t2 = __ldg(&ttf[(size_t)n2 * m.L + c.nz0]), t3 = __ldg(&ttf[(size_t)n3 * m.L + c.nz0]);
+    const double* gs = g.gsca + (size_t)el * 6;
+    const double tx = __ldg(&gs[0]) * t1 + __ldg(&gs[1]) * t2 + __ldg(&gs[2]) * t3;      // sum() left to right
+    const double ty = __ldg(&gs[3]) * t1 + __ldg(&gs[4]) * t2 + __ldg(&gs[5]) * t3;
+    reinterpret_cast<double2*>(tr_xy)[(size_t)el * m.L + c.nz0] = make_double2(tx, ty);
+}
+
+// area-weighted mean of the element gradients around `node` at layer nz, slots in their order
+// (src/oce_muscl_adv.F90:391-406)
+__device__ __forceinline__ double2 node_mean_gradient(const MeshDev& m, const GradMeshDev& g, int node, int nz,
+                                                       const double* __restrict__ tr_xy)
+{
+    double tvol = 0.0, tx = 0.0, ty = 0.0;
+    const int num = __ldg(&g.nie_num[node]);
+    const int* row = g.nie + (size_t)node * g.ld;
+    for (int k = 0; k < num; ++k) {
+        const int el = __ldg(&row[k]) - 1;
+        if (__ldg(&g.nlevels[el]) - 1 < nz || nz < __ldg(&g.ulevels[el])) continue;
+        const double a = __ldg(&g.earea[el]);
+        const double2 t = __ldg(reinterpret_cast<const double2*>(tr_xy) + (size_t)el * m.L + (nz - 1));
+        tvol = tvol + a;
+        tx = tx + t.x * a;
+        ty = ty + t.y * a;
+    }
+    return make_double2(tx / tvol, ty / tvol);
+}
+
+// fill_up_dn_grad, src/oce_muscl_adv.F90:378-522: one thread per (edge, layer); writes exactly the entries
+// the reference writes
+__global__ void __launch_bounds__(kBlock) k_fill_up_dn_grad(MeshDev m, GradMeshDev g, int cpb, const double* __restrict__ tr_xy,
+                                                            double* __restrict__ grad)
+{
+    const ColThread c = col_thread(m);
+    const int e = blockIdx.x * cpb + c.g;
+    if (c.g >= cpb || e >= m.E) return;
+    const int nz = c.nz0 + 1;
+    const int4 em = __ldg(&m.edge_meta[e]);                       // {edges(1,e), edges(2,e), ..} 0-based
+    const int t1 = __ldg(&g.up_dn_tri[2 * e]), t2 = __ldg(&g.up_dn_tri[2 * e + 1]);
+    const uchar4 l1 = __ldg(&m.node_lev[em.x]), l2 = __ldg(&m.node_lev[em.y]);   // {ulevels_nod2D, nlevels_nod2D, ..}
+    const bool both = t1 != 0 && t2 != 0;
+    int nzmin = 0, nzmax = 0;
+    if (both) {
+        nzmin = max(__ldg(&g.umax[em.x]), __ldg(&g.umax[em.y]));
+        nzmax = min(__ldg(&g.nmin[em.x]), __ldg(&g.nmin[em.y]));
+    }
+    const bool shared = both && nz >= nzmin && nz <= nzmax - 1;
+    double* out = grad + ((size_t)e * m.L + c.nz0) * 4;
+    const double2* txy = reinterpret_cast<const double2*>(tr_xy);
+    if (shared) {                                                 // :435-440
+        const double2 up = __ldg(&txy[(size_t)(t1 - 1) * m.L + c.nz0]), dn = __ldg(&txy[(size_t)(t2 - 1) * m.L + c.nz0]);
+        out[0] = up.x; out[1] = dn.x; out[2] = up.y; out[3] = dn.y;
+        return;
+    }
+    // loop bounds of :388,:411 (above the shared range), :445,:467 (below it) and :493,:511 (boundary edge)
+    const int u1 = l1.x, n1 = (int)l1.y - 1, u2 = l2.x, n2 = (int)l2.y - 1;
+    const bool w1 = both ? ((nz >= u1 && nz <= nzmin - 1) || (nz >= nzmax && nz <= n1)) : (nz >= u1 && nz <= n1);
+    const bool w2 = both ? ((nz >= u2 && nz <= nzmin - 1) || (nz >= nzmax && nz <= n2)) : (nz >= u2 && nz <= n2);
+    if (w1) { const double2 v = node_mean_gradient(m, g, em.x, nz, tr_xy); out[0] = v.x; out[2] = v.y; }
+    if (w2) { const double2 v = node_mean_gradient(m, g, em.y, nz, tr_xy); out[1] = v.x; out[3] = v.y; }
+}
+
 // self-test of div_rcp against the IEEE division: returns the number of mismatching results over
 // `count` pseudo-random operand pairs (mode 0: b = 6, 1: b = 3, 2: random b in [1e-3, 1e13])
 __global__ void k_selftest_div(unsigned long long count, unsigned long long seed, int mode, unsigned long long* bad)

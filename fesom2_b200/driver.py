@@ -60,9 +60,17 @@ class TracerDesc(C.Structure):
                 ("tra_adv_ph", C.c_double), ("tra_adv_pv", C.c_double)]
 
 
+class GradientMeshDesc(C.Structure):
+    _fields_ = [("n_elem", C.c_int32), ("n_nod_in_elem", C.c_int32), ("nod_in_elem2D_ld", C.c_int32),
+                ("nod_in_elem2D", c_ip), ("nod_in_elem2D_num", c_ip), ("nlevels", c_ip), ("ulevels", c_ip),
+                ("edge_up_dn_tri", c_ip), ("nlevels_nod2D_min", c_ip), ("ulevels_nod2D_max", c_ip),
+                ("gradient_sca", c_dp), ("elem_area", c_dp)]
+
+
 EXPORTS = ["adv_ctx_create", "adv_ctx_destroy", "adv_last_error", "adv_comm_unique_id",
            "adv_ctx_comm_init", "adv_ctx_set_state", "adv_do_oce_adv_tra", "adv_do_oce_adv_tra_async",
-           "adv_ctx_synchronize", "adv_exchange_nod", "adv_update_values", "adv_init_tracers_AB", "adv_ctx_get_work",
+           "adv_ctx_synchronize", "adv_exchange_nod", "adv_update_values", "adv_init_tracers_AB",
+           "adv_ctx_set_gradient_mesh", "adv_tracer_gradient_elements", "adv_fill_up_dn_grad", "adv_ctx_get_work",
            "adv_ctx_launch_count", "adv_ctx_stream", "adv_ctx_last_elapsed_ms",
            "adv_ctx_set_profiling", "adv_ctx_phase_ms", "adv_selftest_div"]
 
@@ -93,6 +101,9 @@ def load_library():
         L.adv_exchange_nod.argtypes = [C.c_void_p, C.c_int, C.POINTER(c_dp), C.c_int]
         L.adv_update_values.argtypes = [C.c_void_p, C.c_int, C.POINTER(c_dp), C.POINTER(c_dp), C.POINTER(c_dp)]
         L.adv_init_tracers_AB.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double] + [C.POINTER(c_dp)] * 6
+        L.adv_ctx_set_gradient_mesh.argtypes = [C.c_void_p, C.POINTER(GradientMeshDesc)]
+        L.adv_tracer_gradient_elements.argtypes = [C.c_void_p, C.c_int, C.POINTER(c_dp), C.POINTER(c_dp)]
+        L.adv_fill_up_dn_grad.argtypes = [C.c_void_p, C.c_int, C.POINTER(c_dp), C.POINTER(c_dp)]
         L.adv_ctx_get_work.argtypes = [C.c_void_p, C.c_char_p, C.c_int, c_dp]
         L.adv_ctx_last_elapsed_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.adv_ctx_set_profiling.argtypes = [C.c_void_p, C.c_int]
@@ -244,6 +255,33 @@ class AdvB200:
             return PA(*[_ptr(v) for v in lst]) if lst is not None else None
         _check(self.lib.adv_init_tracers_AB(self.h, n, int(ab_order), float(epsilon), arr(values), arr(valuesold),
                                             arr(valuesAB), arr(del_ttf), arr(dttf_h), arr(dttf_v)))
+
+    # -- producer of edge_up_dn_grad ---------------------------------------------
+    def set_gradient_mesh(self, edge_up_dn_tri: np.ndarray):
+        """Static inputs of tracer_gradient_elements / fill_up_dn_grad (t_tracer_work%edge_up_dn_tri and the
+        t_mesh fields gradient_sca, elem_area, nlevels_nod2D_min, ulevels_nod2D_max, nod_in_elem2D)."""
+        m, k = self.mesh, self._keep
+        d = GradientMeshDesc(n_elem=int(np.asarray(m.elem_area).shape[0]), n_nod_in_elem=int(np.asarray(m.nod_in_elem2D).shape[0]),
+                             nod_in_elem2D_ld=int(np.asarray(m.nod_in_elem2D).shape[1]))
+        for name, src in (("nod_in_elem2D", m.nod_in_elem2D), ("nod_in_elem2D_num", m.nod_in_elem2D_num), ("nlevels", m.nlevels),
+                          ("ulevels", m.ulevels), ("edge_up_dn_tri", edge_up_dn_tri), ("nlevels_nod2D_min", m.nlevels_nod2D_min),
+                          ("ulevels_nod2D_max", m.ulevels_nod2D_max)):
+            k["g_" + name] = np.ascontiguousarray(src, dtype=np.int32)
+            setattr(d, name, k["g_" + name].ctypes.data_as(c_ip))
+        for name, src in (("gradient_sca", m.gradient_sca), ("elem_area", m.elem_area)):
+            k["g_" + name] = np.ascontiguousarray(src, dtype=np.float64)
+            setattr(d, name, k["g_" + name].ctypes.data_as(c_dp))
+        _check(self.lib.adv_ctx_set_gradient_mesh(self.h, C.byref(d)))
+
+    def tracer_gradient_elements(self, ttf: Sequence, tr_xy: Sequence):
+        """``tracer_gradient_elements`` (src/oce_tracer_mod.F90:146-188): ttf[i] (Nh, L) -> tr_xy[i] (n_elem, L, 2)."""
+        PA = c_dp * len(ttf)
+        _check(self.lib.adv_tracer_gradient_elements(self.h, len(ttf), PA(*[_ptr(t) for t in ttf]), PA(*[_ptr(t) for t in tr_xy])))
+
+    def fill_up_dn_grad(self, tr_xy: Sequence, edge_up_dn_grad: Sequence):
+        """``fill_up_dn_grad`` (src/oce_muscl_adv.F90:356-525): tr_xy[i] -> edge_up_dn_grad[i] (E, L, 4)."""
+        PA = c_dp * len(tr_xy)
+        _check(self.lib.adv_fill_up_dn_grad(self.h, len(tr_xy), PA(*[_ptr(t) for t in tr_xy]), PA(*[_ptr(t) for t in edge_up_dn_grad])))
 
     # -- introspection ------------------------------------------------------------------------
     def get_work(self, name: str, slot: int = 0) -> np.ndarray:

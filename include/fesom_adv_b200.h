@@ -150,6 +150,35 @@ int adv_init_tracers_AB(adv_ctx_t *ctx, int ntr, int ab_order, double epsilon,
                         const double *const *values, double *const *valuesold, double *const *valuesAB,
                         double *const *del_ttf, double *const *del_ttf_advhoriz, double *const *del_ttf_advvert);
 
+/* --- the producer of edge_up_dn_grad (the caller's side of the path) ----
+ * Static inputs of tracer_gradient_elements / fill_up_dn_grad that adv_ctx_create does not get.  Index
+ * values 1-based, reference layouts.  The arrays are copied to the device. */
+typedef struct {
+    int32_t n_elem;                 /* elements tr_xy covers: myDim_elem2D + eDim_elem2D + eXDim_elem2D        */
+    int32_t n_nod_in_elem;          /* nodes nod_in_elem2D(_num) cover: every end node of a local edge          */
+    int32_t nod_in_elem2D_ld;
+    const int32_t *nod_in_elem2D;       /* (ld, n_nod_in_elem)                                                  */
+    const int32_t *nod_in_elem2D_num;   /* (n_nod_in_elem)                                                      */
+    const int32_t *nlevels, *ulevels;   /* (n_elem)                                                             */
+    const int32_t *edge_up_dn_tri;      /* (2, myDim_edge2D)  t_tracer_work%edge_up_dn_tri, 0 = none            */
+    const int32_t *nlevels_nod2D_min;   /* (myDim_nod2D + eDim_nod2D)                                           */
+    const int32_t *ulevels_nod2D_max;   /* (myDim_nod2D + eDim_nod2D)                                           */
+    const double *gradient_sca;         /* (6, myDim_elem2D)                                                    */
+    const double *elem_area;            /* (n_elem)                                                             */
+} adv_gradient_mesh_desc_t;
+int adv_ctx_set_gradient_mesh(adv_ctx_t *ctx, const adv_gradient_mesh_desc_t *g);
+
+/* Replaces `tracer_gradient_elements(ttf, partit, mesh)` (src/oce_tracer_mod.F90:146-188) for ntr tracers:
+ * tr_xy(1:2, nz, elem) for elem <= myDim_elem2D.  tr_xy[i] is (2, nl-1, n_elem); entries the reference does
+ * not write are left untouched.  DEVICE pointers, asynchronous on the context's stream.  The halo part of
+ * tr_xy (exchange_elem, src/oce_tracer_mod.F90:140) remains the caller's job on more than one rank. */
+int adv_tracer_gradient_elements(adv_ctx_t *ctx, int ntr, const double *const *ttf, double *const *tr_xy);
+
+/* Replaces `fill_up_dn_grad(twork, partit, mesh)` (src/oce_muscl_adv.F90:356-525) for ntr tracers:
+ * edge_up_dn_grad(1:4, nz, edge) for edge <= myDim_edge2D from the (exchanged) tr_xy.  Entries the reference
+ * does not write are left untouched.  DEVICE pointers, asynchronous on the context's stream. */
+int adv_fill_up_dn_grad(adv_ctx_t *ctx, int ntr, const double *const *tr_xy, double *const *edge_up_dn_grad);
+
 /* --- introspection (tests, profiling) -------------------------------------------------------- */
 /* Copies an internal work array of tracer slot `slot` to a HOST buffer.  name is one of
  * "fct_LO" (nl-1,Nh), "adv_flux_hor" (nl-1,E), "adv_flux_ver" (nl,N), "fct_plus", "fct_minus"

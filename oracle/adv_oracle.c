@@ -754,3 +754,81 @@ double ora_run_ranks(int nranks, ora_rank_t *ranks, double dt, int nsteps, int m
     free(tid); free(th); free(sh.slot);
     return t1 - t0;
 }
+
+
+/* ====================================================================================================
+ * tracer_gradient_elements, src/oce_tracer_mod.F90:146-188
+ * ==================================================================================================== */
+void ora_tracer_gradient_elements(int nl, int myDim_elem2D, const int *elem2D_nodes, const int *nlevels,
+                                  const int *ulevels, const double *gradient_sca, const double *ttf, double *tr_xy)
+{
+    const int L = nl - 1;
+#define G_TTF(nz, n) ttf[(size_t)((n) - 1) * L + ((nz) - 1)]
+#define G_TRXY(c, nz, e) tr_xy[((size_t)((e) - 1) * L + ((nz) - 1)) * 2 + ((c) - 1)]
+#define G_SCA(k, e) gradient_sca[(size_t)((e) - 1) * 6 + ((k) - 1)]
+    for (int elem = 1; elem <= myDim_elem2D; ++elem) {                         /* :171 */
+        const int n1 = elem2D_nodes[3 * (elem - 1)], n2 = elem2D_nodes[3 * (elem - 1) + 1], n3 = elem2D_nodes[3 * (elem - 1) + 2];
+        const int nzmin = ulevels[elem - 1], nzmax = nlevels[elem - 1];         /* :173-174 */
+        for (int nz = nzmin; nz <= nzmax - 1; ++nz) {                           /* :176 */
+            G_TRXY(1, nz, elem) = G_SCA(1, elem) * G_TTF(nz, n1) + G_SCA(2, elem) * G_TTF(nz, n2) + G_SCA(3, elem) * G_TTF(nz, n3);   /* :177 */
+            G_TRXY(2, nz, elem) = G_SCA(4, elem) * G_TTF(nz, n1) + G_SCA(5, elem) * G_TTF(nz, n2) + G_SCA(6, elem) * G_TTF(nz, n3);   /* :178 */
+        }
+    }
+#undef G_TTF
+#undef G_SCA
+}
+
+/* ====================================================================================================
+ * fill_up_dn_grad, src/oce_muscl_adv.F90:356-525
+ * ==================================================================================================== */
+static void ora_node_mean_gradient(int L, int node, int nz, const int *nod_in_elem2D, int ld, const int *nod_in_elem2D_num,
+                                   const int *nlevels, const int *ulevels, const double *elem_area, const double *tr_xy,
+                                   double *gx, double *gy)
+{
+    double tvol = 0.0, tx = 0.0, ty = 0.0;                                      /* :391-393 */
+    for (int k = 1; k <= nod_in_elem2D_num[node - 1]; ++k) {                    /* :397 */
+        const int elem = nod_in_elem2D[(size_t)(node - 1) * ld + (k - 1)];
+        if (nlevels[elem - 1] - 1 < nz || nz < ulevels[elem - 1]) continue;     /* :400 */
+        tvol = tvol + elem_area[elem - 1];
+        tx = tx + G_TRXY(1, nz, elem) * elem_area[elem - 1];
+        ty = ty + G_TRXY(2, nz, elem) * elem_area[elem - 1];
+    }
+    *gx = tx / tvol;                                                            /* :405 */
+    *gy = ty / tvol;
+}
+
+void ora_fill_up_dn_grad(int nl, int myDim_edge2D, const int *edges, const int *edge_up_dn_tri,
+                         const int *nod_in_elem2D, int ld, const int *nod_in_elem2D_num,
+                         const int *nlevels, const int *ulevels, const int *nlevels_nod2D, const int *ulevels_nod2D,
+                         const int *nlevels_nod2D_min, const int *ulevels_nod2D_max,
+                         const double *elem_area, const double *tr_xy, double *edge_up_dn_grad)
+{
+    const int L = nl - 1;
+#define G_GRAD(c, nz, e) edge_up_dn_grad[((size_t)((e) - 1) * L + ((nz) - 1)) * 4 + ((c) - 1)]
+#define NODE_MEAN(node, nz, cx, cy) do { double gx_, gy_; \
+        ora_node_mean_gradient(L, node, nz, nod_in_elem2D, ld, nod_in_elem2D_num, nlevels, ulevels, elem_area, tr_xy, &gx_, &gy_); \
+        G_GRAD(cx, nz, edge) = gx_; G_GRAD(cy, nz, edge) = gy_; } while (0)
+    for (int edge = 1; edge <= myDim_edge2D; ++edge) {                          /* :378 */
+        const int e1 = edges[2 * (edge - 1)], e2 = edges[2 * (edge - 1) + 1];
+        const int t1 = edge_up_dn_tri[2 * (edge - 1)], t2 = edge_up_dn_tri[2 * (edge - 1) + 1];
+        if (t1 != 0 && t2 != 0) {                                               /* :382 */
+            const int a = ulevels_nod2D_max[e1 - 1], b = ulevels_nod2D_max[e2 - 1];
+            const int c = nlevels_nod2D_min[e1 - 1], d = nlevels_nod2D_min[e2 - 1];
+            const int nzmin = a > b ? a : b, nzmax = c < d ? c : d;             /* :383-384 */
+            for (int nz = ulevels_nod2D[e1 - 1]; nz <= nzmin - 1; ++nz) NODE_MEAN(e1, nz, 1, 3);      /* :388-407 */
+            for (int nz = ulevels_nod2D[e2 - 1]; nz <= nzmin - 1; ++nz) NODE_MEAN(e2, nz, 2, 4);      /* :411-430 */
+            for (int nz = nzmin; nz <= nzmax - 1; ++nz) {                       /* :435-440 */
+                G_GRAD(1, nz, edge) = G_TRXY(1, nz, t1); G_GRAD(2, nz, edge) = G_TRXY(1, nz, t2);
+                G_GRAD(3, nz, edge) = G_TRXY(2, nz, t1); G_GRAD(4, nz, edge) = G_TRXY(2, nz, t2);
+            }
+            for (int nz = nzmax; nz <= nlevels_nod2D[e1 - 1] - 1; ++nz) NODE_MEAN(e1, nz, 1, 3);      /* :445-463 */
+            for (int nz = nzmax; nz <= nlevels_nod2D[e2 - 1] - 1; ++nz) NODE_MEAN(e2, nz, 2, 4);      /* :467-485 */
+        } else {                                                                /* :489: surface boundary edge */
+            for (int nz = ulevels_nod2D[e1 - 1]; nz <= nlevels_nod2D[e1 - 1] - 1; ++nz) NODE_MEAN(e1, nz, 1, 3);   /* :491-508 */
+            for (int nz = ulevels_nod2D[e2 - 1]; nz <= nlevels_nod2D[e2 - 1] - 1; ++nz) NODE_MEAN(e2, nz, 2, 4);   /* :509-524 */
+        }
+    }
+#undef NODE_MEAN
+#undef G_GRAD
+}
+#undef G_TRXY

@@ -94,6 +94,24 @@ void ora_oce_tra_adv_flux2dtracer(const ora_mesh_t *m, double dt, double *dttf_h
                                   double *flux_h, double *flux_v, int use_lo,
                                   const double *ttf, const double *lo);
 
+/* ---- the producer of edge_up_dn_grad ------------------------------
+ * tracer_gradient_elements (src/oce_tracer_mod.F90:146-188): tr_xy(1:2,nz,elem) for elem <= myDim_elem2D,
+ * layers ulevels(elem) .. nlevels(elem)-1.  `sum()` of the three products is taken left to right.
+ * tr_xy is (2, nl-1, >= myDim_elem2D); entries outside the loop bounds are left untouched. */
+void ora_tracer_gradient_elements(int nl, int myDim_elem2D, const int *elem2D_nodes, const int *nlevels,
+                                  const int *ulevels, const double *gradient_sca /* (6,T) */,
+                                  const double *ttf /* (nl-1,Nh) */, double *tr_xy);
+/* fill_up_dn_grad (src/oce_muscl_adv.F90:356-525): edge_up_dn_grad(1:4,nz,edge) for edge <= myDim_edge2D
+ * from tr_xy (which the caller has halo-exchanged, src/oce_tracer_mod.F90:140) -- the up/down-wind
+ * triangle's gradient on the levels both end nodes share, the area-weighted mean over the wet elements
+ * around the end node elsewhere.  Entries the reference does not write are left untouched. */
+void ora_fill_up_dn_grad(int nl, int myDim_edge2D, const int *edges, const int *edge_up_dn_tri /* (2,E) */,
+                         const int *nod_in_elem2D, int ld, const int *nod_in_elem2D_num,
+                         const int *nlevels, const int *ulevels,
+                         const int *nlevels_nod2D, const int *ulevels_nod2D,
+                         const int *nlevels_nod2D_min, const int *ulevels_nod2D_max,
+                         const double *elem_area, const double *tr_xy, double *edge_up_dn_grad /* (4,nl-1,E) */);
+
 /* do_oce_adv_tra (oce_adv_tra_driver.F90:46-490) for one tracer.  Returns 0, or 1 for an unknown
  * scheme (the reference calls par_ex there). */
 int ora_do_oce_adv_tra(const ora_mesh_t *m, ora_work_t *wk, double dt,

@@ -267,3 +267,57 @@ def init_tracers_AB(values, valuesold, ab_order=2, epsilon=0.1):
     else:
         raise ValueError("Adams-Bashfort tracer order must be 2 or 3")
     return vab, new
+
+
+def tracer_gradient_elements(mesh, ttf):
+    """src/oce_tracer_mod.F90:171-180, vectorised: ttf (Nh, L) -> tr_xy (T, L, 2); zero outside ulevels..nlevels-1."""
+    en = np.asarray(mesh.elem2D_nodes, dtype=np.int64) - 1
+    g = np.asarray(mesh.gradient_sca, dtype=np.float64)
+    t = np.asarray(ttf, dtype=np.float64)
+    lev = np.arange(1, mesh.L + 1)[None, :]
+    wet = (lev >= np.asarray(mesh.ulevels)[:mesh.T, None]) & (lev <= np.asarray(mesh.nlevels)[:mesh.T, None] - 1)
+    out = np.zeros((mesh.T, mesh.L, 2))
+    for c in range(2):
+        v = g[:, 3 * c + 0, None] * t[en[:, 0]] + g[:, 3 * c + 1, None] * t[en[:, 1]] + g[:, 3 * c + 2, None] * t[en[:, 2]]
+        out[:, :, c] = np.where(wet, v, 0.0)
+    return out
+
+
+def fill_up_dn_grad(mesh, tr_xy, edge_up_dn_tri):
+    """src/oce_muscl_adv.F90:378-522, vectorised over edges and levels; the node mean runs over the
+    nod_in_elem2D slots in their order (k = 1 .. nod_in_elem2D_num), like the reference's inner loop."""
+    L, E = mesh.L, mesh.E
+    tr = np.asarray(tr_xy, dtype=np.float64)
+    nlev_e, ulev_e = np.asarray(mesh.nlevels), np.asarray(mesh.ulevels)
+    area = np.asarray(mesh.elem_area, dtype=np.float64)
+    nie = np.asarray(mesh.nod_in_elem2D, dtype=np.int64) - 1
+    num = np.asarray(mesh.nod_in_elem2D_num)
+    Nn = nie.shape[0]
+    lev = np.arange(1, L + 1)[None, :]
+    tvol = np.zeros((Nn, L)); tx = np.zeros((Nn, L)); ty = np.zeros((Nn, L))
+    for k in range(nie.shape[1]):
+        el = np.where(k < num, nie[:, k], 0)
+        ok = (k < num)[:, None] & ~((nlev_e[el][:, None] - 1 < lev) | (lev < ulev_e[el][:, None]))
+        a = area[el][:, None]
+        tvol = np.where(ok, tvol + a, tvol)
+        tx = np.where(ok, tx + tr[el, :, 0] * a, tx)
+        ty = np.where(ok, ty + tr[el, :, 1] * a, ty)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        gx, gy = tx / tvol, ty / tvol
+    ed = np.asarray(mesh.edges, dtype=np.int64) - 1
+    tri = np.asarray(edge_up_dn_tri, dtype=np.int64)
+    n1, n2 = ed[:, 0], ed[:, 1]
+    both = ((tri[:, 0] != 0) & (tri[:, 1] != 0))[:, None]
+    nmin, umax = np.asarray(mesh.nlevels_nod2D_min), np.asarray(mesh.ulevels_nod2D_max)
+    nln, uln = np.asarray(mesh.nlevels_nod2D), np.asarray(mesh.ulevels_nod2D)
+    nzmin = np.maximum(umax[n1], umax[n2])[:, None]
+    nzmax = np.minimum(nmin[n1], nmin[n2])[:, None]
+    shared = both & (lev >= nzmin) & (lev <= nzmax - 1)
+    out = np.zeros((E, L, 4))
+    up, dn = np.maximum(tri[:, 0] - 1, 0), np.maximum(tri[:, 1] - 1, 0)
+    for node, t_el, cx, cy in ((n1, up, 0, 2), (n2, dn, 1, 3)):
+        col = (lev >= uln[node][:, None]) & (lev <= nln[node][:, None] - 1)
+        mean = col & (~both | (lev <= nzmin - 1) | (lev >= nzmax))
+        out[:, :, cx] = np.where(shared, tr[t_el, :, 0], np.where(mean, gx[node], 0.0))
+        out[:, :, cy] = np.where(shared, tr[t_el, :, 1], np.where(mean, gy[node], 0.0))
+    return out

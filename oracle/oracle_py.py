@@ -186,3 +186,45 @@ def run(ranks: Sequence[OracleRank], dt: float, nsteps: int = 1, mode: int = 0, 
     for r, rk in enumerate(ranks):
         rk.fill(arr[r])
     return lib(fast).ora_run_ranks(n, arr, float(dt), int(nsteps), int(mode))
+
+
+# ---- producer of edge_up_dn_grad ---------------------------------------
+def _ipk(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(c_ip)
+
+
+def tracer_gradient_elements(mesh, ttf: np.ndarray) -> np.ndarray:
+    """ora_tracer_gradient_elements: ttf (Nh, L) -> tr_xy (T, L, 2), zero where the reference does not write."""
+    L_ = lib()
+    L_.ora_tracer_gradient_elements.argtypes = [C.c_int, C.c_int, c_ip, c_ip, c_ip, c_dp, c_dp, c_dp]
+    L_.ora_tracer_gradient_elements.restype = None
+    en, enp = _ipk(mesh.elem2D_nodes)
+    nlv, nlvp = _ipk(mesh.nlevels)
+    ulv, ulvp = _ipk(mesh.ulevels)
+    g = np.ascontiguousarray(mesh.gradient_sca, dtype=np.float64)
+    t = np.ascontiguousarray(ttf, dtype=np.float64)
+    out = np.zeros((mesh.T + mesh.eDim_elem2D, mesh.L, 2), np.float64)
+    L_.ora_tracer_gradient_elements(mesh.nl, mesh.T, enp, nlvp, ulvp, g.ctypes.data_as(c_dp), t.ctypes.data_as(c_dp),
+                                    out.ctypes.data_as(c_dp))
+    return out
+
+
+def fill_up_dn_grad(mesh, tr_xy: np.ndarray, edge_up_dn_tri: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+    """ora_fill_up_dn_grad: tr_xy (>=T, L, 2) -> edge_up_dn_grad (E, L, 4); entries the reference leaves alone
+    keep the contents of ``out`` (zeros by default, like the freshly allocated array of the reference)."""
+    L_ = lib()
+    L_.ora_fill_up_dn_grad.argtypes = [C.c_int, C.c_int, c_ip, c_ip, c_ip, C.c_int, c_ip, c_ip, c_ip, c_ip, c_ip, c_ip, c_ip,
+                                       c_dp, c_dp, c_dp]
+    L_.ora_fill_up_dn_grad.restype = None
+    keep = [_ipk(a) for a in (mesh.edges, edge_up_dn_tri, mesh.nod_in_elem2D, mesh.nod_in_elem2D_num, mesh.nlevels, mesh.ulevels,
+                             mesh.nlevels_nod2D, mesh.ulevels_nod2D, mesh.nlevels_nod2D_min, mesh.ulevels_nod2D_max)]
+    p = [k[1] for k in keep]
+    ea = np.ascontiguousarray(mesh.elem_area, dtype=np.float64)
+    tx = np.ascontiguousarray(tr_xy, dtype=np.float64)
+    if out is None:
+        out = np.zeros((mesh.E, mesh.L, 4), np.float64)
+    assert out.flags.c_contiguous and out.dtype == np.float64
+    L_.ora_fill_up_dn_grad(mesh.nl, mesh.E, p[0], p[1], p[2], keep[2][0].shape[1], p[3], p[4], p[5], p[6], p[7], p[8], p[9],
+                           ea.ctypes.data_as(c_dp), tx.ctypes.data_as(c_dp), out.ctypes.data_as(c_dp))
+    return out

@@ -35,14 +35,14 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_library_is_sm100a_only_and_uses_bulk_copies(lib):
-    """one architecture, and the Blackwell-era copy instructions are in the SASS (UBLKCP = cp.async.bulk,
-    LDGSTS = cp.async, 256-bit LDG)"""
+    """one architecture, and the bulk-copy machinery is in the SASS (UBLKCP = cp.async.bulk, UBLKPF =
+    cp.async.bulk.prefetch.L2, SYNCS = mbarrier, 256-bit LDG)"""
     from fesom2_b200.build import OUT
     elf = subprocess.run(["cuobjdump", "-lelf", OUT], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_\d+a?", elf))
     assert archs == {"sm_100a"}, archs
     sass = subprocess.run(["cuobjdump", "-sass", OUT], capture_output=True, text=True).stdout
-    for mnemonic in ("UBLKCP", "LDGSTS", "LDG.E.ENL2.256", "SYNCS"):
+    for mnemonic in ("UBLKCP", "UBLKPF", "LDG.E.ENL2.256", "SYNCS"):
         assert mnemonic in sass, mnemonic
     assert "HMMA" not in sass and "DMMA" not in sass      # no tensor cores on this path, by design
 

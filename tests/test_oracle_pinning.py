@@ -127,3 +127,21 @@ def test_fct_no_new_extrema(pi_mesh):
     m = mask[:N]
     assert (new[m] <= vmax[:N][m] + eps).all()
     assert (new[m] >= vmin[:N][m] - eps).all()
+
+
+@pytest.mark.parametrize("which", ["pi", "soufflet"])
+def test_gradient_producer_restatements_agree(which, pi_mesh, souf_mesh):
+    """tracer_gradient_elements / fill_up_dn_grad: the C restatement, the NumPy restatement (bit for bit)
+    and the torch generator of the synthetic inputs (to round-off: it sums with index_add)."""
+    import torch
+    from fesom2_b200 import fields as F
+    from oracle import numpy_ref as R, oracle_py as O
+    g = {"pi": pi_mesh, "soufflet": souf_mesh}[which]
+    v, _ = F.make_tracer_values(g, "cpu", kind=0)
+    tri = F.find_up_downwind_triangles(g)
+    a, b = O.tracer_gradient_elements(g, v.numpy()), R.tracer_gradient_elements(g, v.numpy())
+    assert np.array_equal(a[:g.T], b)
+    ga, gb = O.fill_up_dn_grad(g, a, tri), R.fill_up_dn_grad(g, b, tri)
+    assert np.isfinite(ga).all() and np.array_equal(ga, gb)
+    gt = F.fill_up_dn_grad(g, F.tracer_gradient_elements(g, v, "cpu"), tri, "cpu").numpy()
+    assert np.abs(ga - gt).max() <= 1e-13 * np.abs(ga).max()
