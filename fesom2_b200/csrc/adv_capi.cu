@@ -97,8 +97,8 @@ struct DevBuf {
     ~DevBuf() { release(); }
 };
 
-struct Slot {  // per-tracer host staging, only used with ADV_HOST pointers
-    DevBuf<double> ttf, ttfAB, grad, dh, dv;
+struct Slot {  // per-tracer staging: host pointers, unaligned device pointers, library-computed gradients
+    DevBuf<double> ttf, ttfAB, grad, dh, dv, tr_xy;
 };
 
 // work arrays of one chunk of <= 2 tracers (t_tracer_work, allocated by oce_adv_tra_fct_init in the
@@ -804,6 +804,28 @@ static int do_adv(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr, i
             }
             p.ttf[i] = s.ttf.p; p.ttfAB[i] = s.ttfAB.p; p.dh[i] = s.dh.p; p.dv[i] = s.dv.p;
         }
+    }
+    // edge_up_dn_grad == NULL for a gradient-based scheme: the library runs the caller's
+    // tracer_gradient_elements + fill_up_dn_grad itself (adv_ctx_set_gradient_mesh; one rank: on more
+    // ranks tr_xy needs the caller's exchange_elem).  Saves the 4 E L words of H2D per tracer.
+    for (int i = 0; i < ntr; ++i) {
+        if (p.grad[i] || !c->grad_mesh_set) continue;
+        char hbuf[16]; int k = 0;
+        for (const char* q = tr[i].tra_adv_hor; q && *q && *q != ' ' && k < 15; ++q) hbuf[k++] = *q;
+        hbuf[k] = 0;
+        if (strcmp(hbuf, "UPW1") == 0) continue;
+        if (c->npes > 1) return fail(ADV_EINVAL, "edge_up_dn_grad = NULL needs the caller's exchange_elem(tr_xy) on more than one rank");
+        Slot& s = c->slots[i];
+        const size_t nxy = (size_t)2 * m.L * c->gm.n_elem;
+        if (s.tr_xy.n != nxy) CU(s.tr_xy.alloc(nxy));
+        if (s.grad.n != 4 * nLE) CU(s.grad.alloc(4 * nLE));
+        const double* ttf1[1] = {p.ttf[i]};
+        double* xy1[1] = {s.tr_xy.p};
+        double* g1[1] = {s.grad.p};
+        if (int rc = adv_tracer_gradient_elements(c, 1, ttf1, xy1)) return rc;
+        const double* cxy1[1] = {s.tr_xy.p};
+        if (int rc = adv_fill_up_dn_grad(c, 1, cxy1, g1)) return rc;
+        p.grad[i] = s.grad.p;
     }
     CU(cudaEventRecord(c->ev_t0, c->s_comp));
     if (int rc = run_batch(c, dt, ntr, tr, p)) return rc;

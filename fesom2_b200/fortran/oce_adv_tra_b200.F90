@@ -94,6 +94,24 @@ module oce_adv_tra_b200
        type(adv_tracer_desc_t), intent(in) :: tr(*)
        integer(c_int), value :: where
      end function
+     ! the producer of edge_up_dn_grad on the device (tracer_gradient_elements, fill_up_dn_grad)
+     integer(c_int) function adv_ctx_set_gradient_mesh(ctx, g) bind(C, name='adv_ctx_set_gradient_mesh')
+       import :: c_ptr, c_int
+       type(c_ptr), value :: ctx
+       type(c_ptr), value :: g       ! c_loc of an adv_gradient_mesh_desc_t (include/fesom_adv_b200.h)
+     end function
+     integer(c_int) function adv_tracer_gradient_elements(ctx, ntr, ttf, tr_xy) bind(C, name='adv_tracer_gradient_elements')
+       import :: c_ptr, c_int
+       type(c_ptr), value    :: ctx
+       integer(c_int), value :: ntr
+       type(c_ptr), value    :: ttf, tr_xy          ! arrays of ntr device pointers
+     end function
+     integer(c_int) function adv_fill_up_dn_grad(ctx, ntr, tr_xy, edge_up_dn_grad) bind(C, name='adv_fill_up_dn_grad')
+       import :: c_ptr, c_int
+       type(c_ptr), value    :: ctx
+       integer(c_int), value :: ntr
+       type(c_ptr), value    :: tr_xy, edge_up_dn_grad
+     end function
      ! device-resident dwarf loop (dwarf_ini/fesom.F90:85-128): prologue, epilogue, halo exchange
      integer(c_int) function adv_init_tracers_AB(ctx, ntr, ab_order, epsilon, values, valuesold, valuesAB, &
                                                  del_ttf, del_ttf_advhoriz, del_ttf_advvert) bind(C, name='adv_init_tracers_AB')

@@ -178,6 +178,9 @@ int adv_tracer_gradient_elements(adv_ctx_t *ctx, int ntr, const double *const *t
  * edge_up_dn_grad(1:4, nz, edge) for edge <= myDim_edge2D from the (exchanged) tr_xy.  Entries the reference
  * does not write are left untouched.  DEVICE pointers, asynchronous on the context's stream. */
 int adv_fill_up_dn_grad(adv_ctx_t *ctx, int ntr, const double *const *tr_xy, double *const *edge_up_dn_grad);
+/* After adv_ctx_set_gradient_mesh a tracer descriptor may also carry edge_up_dn_grad = NULL (gradient-based
+ * scheme, one rank): adv_do_oce_adv_tra then runs the two routines above on `values` itself before the
+ * step, which saves the 4 E (nl-1) words of host-to-device copy per tracer on the HOST-pointer path. */
 
 /* --- introspection (tests, profiling) -------------------------------------------------------- */
 /* Copies an internal work array of tracer slot `slot` to a HOST buffer.  name is one of

@@ -100,3 +100,32 @@ def test_call_order_is_checked(small_mesh):
         ctx.tracer_gradient_elements([t], [x])
     assert ei.value.code == ADV_ESTATE
     ctx.close()
+
+
+@pytest.mark.parametrize("host", [False, True])
+def test_null_gradient_pointer_lets_the_library_compute_them(souf_mesh, host):
+    """edge_up_dn_grad = NULL in the tracer descriptor: the library runs tracer_gradient_elements +
+    fill_up_dn_grad itself (saves the 4 E L words of H2D per tracer on the host-pointer path)"""
+    from oracle import oracle_py as O
+    from fesom2_b200.driver import AdvB200
+    mesh = souf_mesh
+    st, trs, nb, dt = make_case(mesh, 3, "MFCT", "QR4C", "FCT")
+    trs[2].tra_adv_hor = "MUSCL"
+    tri = F.find_up_downwind_triangles(mesh)
+    for t in trs:
+        t.edge_up_dn_grad = torch.as_tensor(O.fill_up_dn_grad(mesh, O.tracer_gradient_elements(mesh, t.values.numpy()), tri))
+    ora = run_oracle(mesh, st, trs, nb, dt)
+    dev = "cpu" if host else torch.device("cuda:0")
+    st_d, trs_d = (st, trs) if host else to_device(st, trs, dev)
+    for t in trs_d:
+        t.edge_up_dn_grad = None
+    ctx = AdvB200(mesh, nb, max_tracers=3)
+    ctx.set_gradient_mesh(tri)
+    ctx.set_state(st_d)
+    dh = [torch.zeros((mesh.Nh, mesh.L), dtype=torch.float64, device=dev) for _ in trs]
+    dv = [torch.zeros((mesh.Nh, mesh.L), dtype=torch.float64, device=dev) for _ in trs]
+    ctx.do_oce_adv_tra(dt, trs_d, dh, dv)
+    for k in range(3):
+        assert np.array_equal(dh[k].cpu().numpy(), ora.dttf_h[k])
+        assert np.array_equal(dv[k].cpu().numpy(), ora.dttf_v[k])
+    ctx.close()
