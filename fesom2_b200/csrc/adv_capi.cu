@@ -140,6 +140,7 @@ struct adv_ctx {
     int g_lo = 3, g_k2 = 2, g_k3 = 2;         // gather batch sizes (tunable: ADV_G_LO / ADV_G_K2 / ADV_G_K3)
     int bulk = 1;                             // bulk-copy edge kernel (adv_pipe.cuh); 0 = register-gather k_edge_flux (ADV_BULK)
     int e1_ng = 8, e1_depth = 2, e1_il = 0;   // edge groups per CTA / stages / grid-strided groups (ADV_E1_NG, ADV_E1_D, ADV_E1_IL)
+    int i_identity = 1;                       // interior range as identity range + skip flags (ADV_I_IDENTITY)
     int e1_pf = 100;                          // metadata prefetch distance of the bulk edge kernel in CTAs (ADV_E1_PF)
     int force_tb1 = 0;                        // experiments: one tracer per chunk (ADV_TB1)
     int max_smem_optin = 0;
@@ -306,6 +307,7 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
     if (const char* v = getenv("ADV_E1_IL")) c->e1_il = atoi(v) ? 1 : 0;
     if (const char* v = getenv("ADV_E1_D")) c->e1_depth = std::max(2, std::min(4, atoi(v)));
     if (const char* v = getenv("ADV_TB1")) c->force_tb1 = atoi(v);
+    if (const char* v = getenv("ADV_I_IDENTITY")) c->i_identity = atoi(v) ? 1 : 0;
     if (const char* v = getenv("ADV_E1_PF")) c->e1_pf = std::max(0, atoi(v));
     cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
 #define CUF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { delete c; return fail(ADV_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
@@ -359,6 +361,8 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
         }
         std::vector<int> S, I, SH;
         for (int n = 0; n < N; ++n) (isS[n] ? S : I).push_back(n);
+        for (int n = 0; n < N; ++n) if (isS[n]) node_rec[n].y |= 1u << 24;       // boundary-set flag (NodeRange::skip_s)
+        CUF(c->node_rec.upload(node_rec));
         SH = S;
         for (int n = N; n < Nh; ++n) SH.push_back(n);
         c->nS = (int)S.size(); c->nI = (int)I.size(); c->nSH = (int)SH.size();
@@ -511,11 +515,13 @@ static NodeRange node_range(const adv_ctx* c, int rid, int cpb)
 {
     const MeshDev& m = c->m;
     switch (rid) {
-    case R_S: return NodeRange{c->list_S.p, 0, c->nS, cpb, c->pf_dist};
-    case R_I: return NodeRange{c->list_I.p, 0, c->nI, cpb, c->pf_dist};
-    case R_SH: return NodeRange{c->list_SH.p, 0, c->nSH, cpb, c->pf_dist};
-    case R_ALLH: return NodeRange{nullptr, 0, m.Nh, cpb, c->pf_dist};
-    default: return NodeRange{nullptr, 0, m.N, cpb, c->pf_dist};
+    case R_S: return NodeRange{c->list_S.p, 0, c->nS, cpb, c->pf_dist, 0};
+    // interior = all owned nodes minus the boundary set: an identity range with the flagged columns skipped
+    // (no list indirection: one dependent load less per thread, block prefetch of the own columns)
+    case R_I: return c->i_identity ? NodeRange{nullptr, 0, m.N, cpb, c->pf_dist, 1} : NodeRange{c->list_I.p, 0, c->nI, cpb, c->pf_dist, 0};
+    case R_SH: return NodeRange{c->list_SH.p, 0, c->nSH, cpb, c->pf_dist, 0};
+    case R_ALLH: return NodeRange{nullptr, 0, m.Nh, cpb, c->pf_dist, 0};
+    default: return NodeRange{nullptr, 0, m.N, cpb, c->pf_dist, 0};
     }
 }
 
@@ -557,8 +563,8 @@ int launch_phase(adv_ctx* c, Phase ph, int hor, int ver, bool q_stored, const Ch
         }
         if (!piped) {
             grid = nblocks(m.E, epb);
-#define E1(H) if (hor == H) { if (q_stored) k_edge_flux<H, TB, 1><<<grid, nthr, 0, s>>>(m, b, epb, 0); \
-                              else k_edge_flux<H, TB, 0><<<grid, nthr, 0, s>>>(m, b, epb, 0); }
+#define E1(H) if (hor == H) { if (q_stored) k_edge_flux<H, TB, 1><<<grid, nthr, 0, s>>>(m, b, epb); \
+                              else k_edge_flux<H, TB, 0><<<grid, nthr, 0, s>>>(m, b, epb); }
             E1(HOR_UPW1) E1(HOR_MUSCL) E1(HOR_MFCT)
 #undef E1
         }
@@ -880,7 +886,7 @@ int adv_update_values(adv_ctx_t* c, int ntr, double* const* values, const double
     if (!c->state_set) return fail(ADV_ESTATE, "adv_ctx_set_state has not been called");
     CU(cudaSetDevice(c->device));
     const int cpb = cols_per_block(c->m.L);
-    const NodeRange rAll{nullptr, 0, c->m.N, cpb, 0};
+    const NodeRange rAll{nullptr, 0, c->m.N, cpb, 0, 0};
     for (int i = 0; i < ntr; ++i) {
         k_update_values<<<nblocks(c->m.N, cpb), cpb * c->m.L, 0, c->s_comp>>>(c->m, rAll, values[i], dh[i], dv[i]);
         ++c->launches;

@@ -135,6 +135,7 @@ struct NodeRange {
     int begin, count;
     int cpb;          // columns per CTA
     int pf;           // metadata prefetch distance in CTAs (0 = off)
+    int skip_s;       // 1: columns flagged "boundary set" in node_rec (bit 24 of .y) are left to another launch
 };
 
 __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
@@ -549,6 +550,7 @@ __device__ __forceinline__ NodeThread node_thread(const MeshDev& m, const NodeRa
         t.nzmin = rec.x & 0xff; t.nzmax = (rec.x >> 8) & 0xff;
         t.pad_lo = (rec.x >> 16) & 0xff; t.pad_hi = rec.x >> 24;
         t.self_lo = rec.y & 0xff; t.self_hi = (rec.y >> 8) & 0xff; t.deg = (rec.y >> 16) & 0xff;
+        if (r.skip_s && ((rec.y >> 24) & 1u)) { t.active = false; t.nzmin = 1; t.nzmax = 0; t.deg = 0; }
     }
     return t;
 }
@@ -592,23 +594,10 @@ __device__ __forceinline__ void prefetch_own_columns(const NodeRange& r, const P
 // QMODE 1: read the stored Q (later chunks of the same step: geometry reads amortised).
 // ----------------------------------------------------------------------------------------------
 template <int HOR, int TB, int QMODE>
-__global__ void __launch_bounds__(kBlock, ADV_E1_MINB) k_edge_flux(MeshDev m, Chunk<TB> b, int epb, int pf)
+__global__ void __launch_bounds__(kBlock, ADV_E1_MINB) k_edge_flux(MeshDev m, Chunk<TB> b, int epb)
 {
     const ColThread c = col_thread(m);
     const int L = m.L;
-    // ---- prefetch-ahead, part 1: thread j < epb looks up future edge (blockIdx.x + pf) * epb + j
-    int ef = -1;
-    int4 mf = make_int4(0, 0, 0, -1);
-    if (pf > 0 && threadIdx.x < epb) {
-        const long long cand = ((long long)blockIdx.x + pf) * epb + threadIdx.x;
-        if (cand < m.E) {
-            ef = (int)cand;
-            mf = __ldg(&m.edge_meta[ef]);
-            l2_prefetch_line(&m.edge_lev[ef]);
-            l2_prefetch_line(&m.edge_cross[ef]);
-            if (HOR != HOR_UPW1) l2_prefetch_line(&m.edge_c[ef]);
-        }
-    }
     const int e = blockIdx.x * epb + c.g;
     if (e >= m.E) return;
     const int nz0 = c.nz0, nz = nz0 + 1;
@@ -683,20 +672,6 @@ __global__ void __launch_bounds__(kBlock, ADV_E1_MINB) k_edge_flux(MeshDev m, Ch
         }
     }
     stv<TB>(b.adf_h + (size_t)oe * TB, out);
-    // ---- prefetch-ahead, part 2: the future edge's operand columns into L2
-    if (ef >= 0) {
-        const unsigned colb = (unsigned)L * 8u;
-#pragma unroll
-        for (int t = 0; t < TB; ++t) {
-            if (HOR != HOR_UPW1) l2_prefetch(b.grad[t] + (size_t)ef * L * 4, colb * 4);
-            l2_prefetch(b.ttf[t] + (size_t)mf.x * L, colb); l2_prefetch(b.ttf[t] + (size_t)mf.y * L, colb);
-            l2_prefetch(b.ttfAB[t] + (size_t)mf.x * L, colb); l2_prefetch(b.ttfAB[t] + (size_t)mf.y * L, colb);
-        }
-        if (QMODE == 0) {
-            l2_prefetch(m.uv + (size_t)mf.z * L * 2, colb * 2); l2_prefetch(m.helem + (size_t)mf.z * L, colb);
-            if (mf.w >= 0) { l2_prefetch(m.uv + (size_t)mf.w * L * 2, colb * 2); l2_prefetch(m.helem + (size_t)mf.w * L, colb); }
-        } else l2_prefetch(m.Q + (size_t)ef * L, colb);
-    }
 }
 
 // ----------------------------------------------------------------------------------------------
