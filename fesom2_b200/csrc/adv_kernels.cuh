@@ -6,7 +6,9 @@
 //
 //   k_edge_flux    D1 + D7 (+ the tracer-independent volume flux Q): one thread per (edge, layer)
 //                  computes the low-order and high-order edge flux ONCE and stores the antidiffusive
-//                  flux HO-LO; a pure streaming kernel, every operand read exactly once
+//                  flux HO-LO; a pure streaming kernel, every operand read exactly once.  The shipped
+//                  path is its bulk-copy form k_edge_flux_b (adv_pipe.cuh); this register-gather form
+//                  serves UPW1 and ADV_BULK=0
 //   k_node_lo      D2-D5 + D8: LO solution by an ordered gather of the upwind edge fluxes
 //                  (recomputed from Q: 3 flops instead of a stored field), vertical LO/HO fluxes
 //   ------------------------------------------------------------ exchange_nod(fct_LO)
@@ -15,6 +17,8 @@
 //   k_fct_update   F10-F11 + U1-U3: limit and accumulate del_ttf_advhoriz / del_ttf_advvert
 //   k_nofct        D7/D8 + U2-U3 when tra_adv_lim /= 'FCT'
 //   k_vert_impl    adv_tra_vert_impl (use_wsplit only)
+//   k_tracer_gradient_elements, k_fill_up_dn_grad   the producer of edge_up_dn_grad
+//   k_init_tracers_AB, k_update_values              prologue / epilogue of the dwarf iteration (row 2)
 //
 // Thread mapping: a CTA owns `cpb` whole columns (nodes or edges), thread = (column, layer).  All
 // caller-visible fields keep the reference layout (level fastest, src/associate_mesh_ass.h:9-79),
@@ -23,11 +27,12 @@
 // so that one 16/32-byte vector access serves the whole chunk.
 //
 // Edge->node scatters of the reference (oce_adv_tra_driver.F90:142-201,:575-633;
-// oce_adv_tra_fct.F90:312-377) are gathers over a node->edge CSR sorted by ascending edge id, which
+// oce_adv_tra_fct.F90:312-377) are gathers over node->edge ELL rows sorted by ascending edge id, which
 // reproduces the serial summation order bit for bit.  Gathers are written as
 // "load a batch of G slots into registers, then accumulate in order" so that G x fields loads are
-// in flight per thread.  Compile with -fmad=false: parity is checked against a non-contracted CPU
-// restatement.
+// in flight per thread; the records the NEXT CTAs will wait for first (node_rec, ELL rows, own columns)
+// are pulled into L2 a few hundred CTAs ahead (node_thread, prefetch_own_columns).  Compile with
+// -fmad=false: parity is checked against a non-contracted CPU restatement.
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>

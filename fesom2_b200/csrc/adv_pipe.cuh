@@ -6,10 +6,14 @@
 //     CTA is loaded ONCE into shared memory, so the dependent chain  index -> metadata -> operands
 //     is paid once per CTA, not once per column;
 //   * the contiguous stream (edge_up_dn_grad, 64 % of the DRAM bytes) arrives by bulk asynchronous
-//     copies (cp.async.bulk / UBLKCP + mbarrier) issued by one thread, the element columns by
-//     per-thread cp.async into thread-private cells, two groups deep: no registers are held while
-//     data is in flight;
-// Measured history (register gather 1.89 ms -> cp.async cells 1.77 -> bulk 1.50) in profiles/r1_tuning.md.
+//     copies (cp.async.bulk / UBLKCP + mbarrier) issued by one thread, two groups deep: no registers
+//     are held while it is in flight; a stage is released through a second mbarrier, so the loop has
+//     no CTA-wide barrier;
+//   * everything several edges share (end values ttf/ttfAB, element columns uv/helem) is a plain load
+//     issued before the wait for the bulk copy (ADV_E1B_DIRECT = 2; the measured alternatives that stage
+//     them in per-thread cp.async cells are kept behind ADV_E1B_DIRECT = 0 / 1).
+// Measured history (register gather 1.89 ms -> cp.async cells 1.77 -> bulk 1.50 -> direct loads 1.43)
+// in profiles/r1_tuning.md.
 #pragma once
 #include "adv_kernels.cuh"
 
@@ -47,13 +51,10 @@ __host__ __device__ constexpr size_t align16(size_t x) { return (x + 15) & ~(siz
 __host__ __device__ inline size_t e1p_meta_bytes(int nge) { return align16((size_t)nge * (16 + 32 + 16 + 8 + 4)); }
 
 // ----------------------------------------------------------------------------------------------
-// E1 (bulk): the contiguous streams of a group -- edge_up_dn_grad of the
-// group's epb consecutive edges (epb * L * 32 bytes per tracer, 64 % of the kernel's DRAM bytes)
-// -- are fetched by ONE bulk asynchronous copy each
+// E1 (bulk): edge_up_dn_grad of the group's epb consecutive edges (up to epb * L * 32 bytes per tracer)
+// is fetched by one bulk asynchronous copy per edge column, trimmed to the column's wet levels
 // (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier), issued by one elected thread.  Bulk
-// copies go through the TMA unit, not through the per-thread load/store path whose outstanding-miss
-// capacity the gather kernels saturate; only the genuine gathers (node columns of ttf/ttfAB,
-// element columns of uv/helem; mostly L1/L2 hits) stay per-thread cp.async cells.
+// copies go through the TMA unit, not through the per-thread load/store path.
 // Stage layout: [grad t=0 | grad t=1] in global order, then the cells [cell][thread].
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(unsigned long long* b, int cnt)
