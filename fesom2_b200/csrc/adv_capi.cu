@@ -475,7 +475,8 @@ struct ChunkSel { int fct, hor, ver, tb; int idx[2]; int buf; };
 // budgets were tuned for (4-5 resident CTAs per SM); one column when a column alone is longer
 inline int cols_per_block(int L)
 {
-    static const int limit = getenv("ADV_CTA_THREADS") ? std::max(32, std::min(kBlock, atoi(getenv("ADV_CTA_THREADS")))) : 224;
+    const char* v = getenv("ADV_CTA_THREADS");                      // experiments only
+    const int limit = v ? std::max(32, std::min(kBlock, atoi(v))) : 224;
     return std::max(1, limit / L);
 }
 inline int nblocks(int count, int cpb) { return (count + cpb - 1) / cpb; }
