@@ -409,13 +409,107 @@ def read_dist(path: str, npes: int) -> Dict[str, object]:
         out["ranks"].append(dict(myDim_nod2D=myN, eDim_nod2D=eN, myList_nod2D=nodes,
                                  myDim_elem2D=myT, eDim_elem2D=eT, eXDim_elem2D=eXT,
                                  myList_elem2D=elems, myDim_edge2D=myE, eDim_edge2D=eE,
-                                 myList_edge2D=edges, com_nod2D=coms[0]))
+                                 myList_edge2D=edges, com_nod2D=coms[0], com_elem2D=coms[1], com_elem2D_full=coms[2]))
     # node -> owning rank
     part = np.empty(int(counts.sum()), np.int32)
     for r, info in enumerate(out["ranks"]):
         part[info["myList_nod2D"][:info["myDim_nod2D"]] - 1] = r
     out["part"] = part
     return out
+
+
+def element_halo(g: Mesh, part: np.ndarray, mype: int) -> Dict[str, object]:
+    """Element halo of rank ``mype``: the reference's ``communication_elemn`` (src/gen_comm.F90:222-527)
+    followed by ``com_global2local`` / ``save_dist_mesh`` (src/oce_local.F90:76-197), vectorised.
+
+    An element is local if any of its nodes is owned (myDim_elem2D, ascending global id).  It is
+    *received* if none of its nodes is owned and it shares an edge (``com_elem2D`` -> eDim_elem2D) or only
+    a node (``com_elem2D_full`` -> eXDim_elem2D) with a local element; its sender is the owner of its first
+    node.  A local element whose first node is owned is *sent* to every rank that owns a node of a
+    neighbouring element and does not itself own a node of the element.  Lists are grouped by rank
+    ascending, ascending global id inside a group, and renumbered locally: own elements 1..myDim, then the
+    eDim elements in ``com_elem2D%rlist`` order, then the eXDim elements in ``com_elem2D_full%rlist`` order.
+
+    Needed by the multi-rank form of tracer_gradient_elements / fill_up_dn_grad (exchange_elem(tr_xy),
+    src/oce_tracer_mod.F90:140); the advection path itself only needs the node halo."""
+    part = np.asarray(part).astype(np.int64)
+    en = g.elem2D_nodes.astype(np.int64) - 1
+    T = en.shape[0]
+    pe_n = part[en]                                              # (T, 3) owner of each element node
+    local = (pe_n == mype).any(axis=1)
+    my_elem = np.flatnonzero(local)
+    main_mine = local & (pe_n[:, 0] == mype)
+
+    # element pairs (el, elem): edge neighbours from edge_tri, node neighbours from nod_in_elem2D
+    et = g.edge_tri.astype(np.int64) - 1
+    inner = et[:, 1] >= 0
+    pair_edge = np.concatenate([et[inner], et[inner][:, ::-1]], axis=0)          # both directions
+    nie, num = build_nod_in_elem(g.elem2D_nodes, g.Nh)
+    nie = nie.astype(np.int64) - 1
+
+    def node_pairs(els):
+        if els.size == 0:
+            return np.zeros((0, 2), np.int64)
+        nb = nie[en[els]]                                        # (n, 3, ld) elements around the element's nodes
+        src = np.broadcast_to(els[:, None, None], nb.shape)
+        ok = nb >= 0
+        return np.stack([src[ok], nb[ok]], axis=1)
+
+    def recv_send(pairs, recv_prev, send_prev):
+        el, elem = pairs[:, 0], pairs[:, 1]
+        # receive: elem has no owned node, el is local
+        r = np.unique(elem[local[el] & ~local[elem]])
+        recv = np.union1d(recv_prev, r)
+        # send: el's main owner is mype, elem has a foreign node; to every owner of elem that owns no node of el
+        m = main_mine[el] & (pe_n[elem] != mype).any(axis=1)
+        el_m, elem_m = el[m], elem[m]
+        out = [send_prev]
+        for i in range(3):
+            ep = pe_n[elem_m, i]
+            need = ~(pe_n[el_m] == ep[:, None]).any(axis=1)
+            out.append(np.stack([ep[need], el_m[need]], axis=1))
+        send = np.unique(np.concatenate(out, axis=0), axis=0) if out else send_prev
+        return recv, send
+
+    empty_send = np.zeros((0, 2), np.int64)
+    recv1, send1 = recv_send(pair_edge, np.zeros(0, np.int64), empty_send)
+    # the full communicator continues from the edge one (the reference does not reset its tables);
+    # only elements near the partition boundary can receive or send: restrict the node-neighbour pairs
+    near = np.zeros(g.Nh, bool)
+    near[en[~local].ravel()] = True                              # nodes of non-local elements ...
+    cand = my_elem[near[en[my_elem]].any(axis=1)]                # ... touched by local elements
+    foreign_node = np.zeros(g.Nh, bool)
+    foreign_node[part != mype] = True
+    ring = np.zeros(g.Nh, bool)
+    ring[en[(foreign_node[en]).any(axis=1)].ravel()] = True      # nodes of elements that have a foreign node
+    cand2 = my_elem[ring[en[my_elem]].any(axis=1)]
+    recv2, send2 = recv_send(node_pairs(np.union1d(cand, cand2)), recv1, send1)
+
+    def order_recv(recv):
+        owner = pe_n[recv, 0]
+        o = np.lexsort((recv, owner))
+        return recv[o], owner[o]
+
+    r1, o1 = order_recv(recv1)
+    r2, o2 = order_recv(recv2)
+    ex = r2[~np.isin(r2, r1)]                                    # full-list order restricted to the new ones
+    loc_of = np.full(T, -1, np.int64)
+    loc_of[my_elem] = np.arange(my_elem.size)
+    loc_of[r1] = my_elem.size + np.arange(r1.size)
+    loc_of[ex] = my_elem.size + r1.size + np.arange(ex.size)
+
+    def com(recv, owner, send):
+        rPE, rc = np.unique(owner, return_counts=True)
+        s = send[np.lexsort((send[:, 1], send[:, 0]))] if send.size else send
+        sPE, sc = np.unique(s[:, 0], return_counts=True) if s.size else (np.zeros(0, np.int64), np.zeros(0, np.int64))
+        return ComStruct(rPE.astype(np.int32), np.concatenate(([1], 1 + np.cumsum(rc))).astype(np.int32),
+                         (loc_of[recv] + 1).astype(np.int32), sPE.astype(np.int32),
+                         np.concatenate(([1], 1 + np.cumsum(sc))).astype(np.int32),
+                         (loc_of[s[:, 1]] + 1).astype(np.int32) if s.size else np.zeros(0, np.int32))
+
+    return dict(myDim_elem2D=int(my_elem.size), eDim_elem2D=int(r1.size), eXDim_elem2D=int(ex.size),
+                myList_elem2D=(np.concatenate([my_elem, r1, ex]) + 1).astype(np.int32),
+                com_elem2D=com(r1, o1, send1), com_elem2D_full=com(r2, o2, send2))
 
 
 # =============================================================================================

@@ -85,3 +85,43 @@ def test_oracle_1rank_vs_nrank_identical_on_owned_nodes(pi_mesh, npes):
             assert np.array_equal(rk.dttf_v[k][:loc.N], one.dttf_v[k][own])
             assert np.array_equal(rk.dttf_h[k][:loc.N], one.dttf_h[k][own])
             assert np.array_equal(rk.values[k], one.values[k][alln])     # halo refreshed by the exchange
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_MESHES), reason="reference fixtures not mounted")
+@pytest.mark.parametrize("name,npes", [("pi", 2), ("pi", 8), ("soufflet", 2), ("soufflet", 8)])
+def test_element_halo_reproduces_reference_dist_files(name, npes):
+    """mesh.element_halo == communication_elemn + com_global2local of the reference: myList_elem2D with its
+    eDim / eXDim tails and both element communicators, against test/meshes/*/dist_N"""
+    g = M.read_fesom_mesh(os.path.join(REF_MESHES, name), cyclic_length_deg=4.5 if name == "soufflet" else 360.0)
+    d = M.read_dist(os.path.join(REF_MESHES, name), npes)
+    for r in range(npes):
+        h, info = M.element_halo(g, d["part"], r), d["ranks"][r]
+        for k in ("myDim_elem2D", "eDim_elem2D", "eXDim_elem2D"):
+            assert h[k] == info[k], k
+        assert np.array_equal(h["myList_elem2D"], info["myList_elem2D"])
+        for cname in ("com_elem2D", "com_elem2D_full"):
+            for a in ("rPE", "rptr", "rlist", "sPE", "sptr", "slist"):
+                assert np.array_equal(getattr(h[cname], a), getattr(info[cname], a)), (cname, a)
+
+
+@pytest.mark.parametrize("npes", [2, 4])
+def test_element_halo_send_and_recv_lists_pair_up(npes):
+    """exchange_elem over these lists is consistent on a mesh the reference ships no partition for: what rank
+    r sends to p is, element by element, what p expects from r (global ids, same order)"""
+    from fesom2_b200 import partition as P
+    g = M.synth_mesh(30, 26, nl=12)
+    part = P.partition(g, npes, "rcb")
+    halos = [M.element_halo(g, part, r) for r in range(npes)]
+    seen = 0
+    for r in range(npes):
+        hr = halos[r]
+        for ci in ("com_elem2D", "com_elem2D_full"):
+            cr = hr[ci]
+            for k, p in enumerate(cr.sPE):
+                sent = hr["myList_elem2D"][cr.slist[cr.sptr[k] - 1:cr.sptr[k + 1] - 1] - 1]
+                cp = halos[int(p)][ci]
+                j = int(np.flatnonzero(cp.rPE == r)[0])
+                want = halos[int(p)]["myList_elem2D"][cp.rlist[cp.rptr[j] - 1:cp.rptr[j + 1] - 1] - 1]
+                assert np.array_equal(sent, want), (r, int(p), ci)
+                seen += sent.size
+    assert seen > 0
