@@ -125,3 +125,48 @@ def test_element_halo_send_and_recv_lists_pair_up(npes):
                 assert np.array_equal(sent, want), (r, int(p), ci)
                 seen += sent.size
     assert seen > 0
+
+
+@pytest.mark.parametrize("mesh_name,npes", [("pi", 2), ("pi", 8), ("soufflet", 8)])
+def test_gradient_producer_is_rank_local_with_the_element_halo(mesh_name, npes, pi_mesh, souf_mesh):
+    """SURVEY 8f row 1 on N ranks (oracle level): with tr_xy exchanged over the eDim + eXDim element halo
+    (exchange_elem, src/oce_tracer_mod.F90:140) and nod_in_elem2D of the halo nodes taken from their owners
+    (src/oce_mesh.F90:2064-2088), fill_up_dn_grad on a rank's local mesh gives, bit for bit, the rows of
+    the 1-rank result for all its edges -- i.e. the element halo of mesh.element_halo is sufficient."""
+    from types import SimpleNamespace
+    from oracle import oracle_py as O
+    g = {"pi": pi_mesh, "soufflet": souf_mesh}[mesh_name]
+    part = g.parts[npes]
+    v, _ = F.make_tracer_values(g, "cpu", kind=0)
+    v = v.numpy()
+    tri = F.find_up_downwind_triangles(g)
+    xy_glob = O.tracer_gradient_elements(g, v)
+    grad_glob = O.fill_up_dn_grad(g, xy_glob, tri)
+    for r in range(npes):
+        loc = M.localize(g, part, r)
+        h = M.element_halo(g, part, r)
+        elist = h["myList_elem2D"].astype(np.int64) - 1               # global ids in local order
+        e_g2l = np.full(g.T, -1, np.int64)
+        e_g2l[elist] = np.arange(elist.size)
+        nodes = loc.myList_nod2D.astype(np.int64) - 1
+        edges = loc.myList_edge2D.astype(np.int64) - 1
+        # element neighbourhoods of ALL local nodes (halo nodes: the owner's list), local element numbers
+        nie_g = g.nod_in_elem2D[nodes].astype(np.int64) - 1
+        assert (e_g2l[nie_g[nie_g >= 0]] >= 0).all(), "an element around a local node is outside the element halo"
+        nie_l = np.where(nie_g >= 0, e_g2l[np.maximum(nie_g, 0)] + 1, 0).astype(np.int32)
+        tri_g = tri[edges].astype(np.int64) - 1
+        assert (e_g2l[tri_g[tri_g >= 0]] >= 0).all(), "an up/down-wind triangle is outside the element halo"
+        tri_l = np.where(tri_g >= 0, e_g2l[np.maximum(tri_g, 0)] + 1, 0).astype(np.int32)
+        # tr_xy: own elements computed locally from the local (owned + halo) nodal values, halo part "exchanged"
+        own = SimpleNamespace(elem2D_nodes=loc.elem2D_nodes, nlevels=loc.nlevels, ulevels=loc.ulevels,
+                              gradient_sca=loc.gradient_sca, nl=g.nl, L=g.L, T=loc.T, eDim_elem2D=elist.size - loc.T)
+        xy = O.tracer_gradient_elements(own, v[nodes])
+        assert np.array_equal(xy[:loc.T], xy_glob[elist[:loc.T]])
+        xy[loc.T:] = xy_glob[elist[loc.T:]]
+        lm = SimpleNamespace(edges=loc.edges, nod_in_elem2D=nie_l, nod_in_elem2D_num=g.nod_in_elem2D_num[nodes],
+                             nlevels=g.nlevels[elist], ulevels=g.ulevels[elist],
+                             nlevels_nod2D=loc.nlevels_nod2D, ulevels_nod2D=loc.ulevels_nod2D,
+                             nlevels_nod2D_min=loc.nlevels_nod2D_min, ulevels_nod2D_max=loc.ulevels_nod2D_max,
+                             elem_area=g.elem_area[elist], nl=g.nl, L=g.L, E=loc.E)
+        got = O.fill_up_dn_grad(lm, xy, tri_l)
+        assert np.array_equal(got, grad_glob[edges]), (mesh_name, npes, r)
