@@ -832,3 +832,49 @@ void ora_fill_up_dn_grad(int nl, int myDim_edge2D, const int *edges, const int *
 #undef G_GRAD
 }
 #undef G_TRXY
+
+
+/* ====================================================================================================
+ * vert_vel_ale, continuity part, src/oce_ale.F90:2164-2310 (linfs, Fer_GM = .false.)
+ * ==================================================================================================== */
+void ora_vert_vel_ale_core(const ora_mesh_t *m, const double *UV, double *Wvel)
+{
+    const int nl = m->nl, L = nl - 1;
+    const int Nh = m->myDim_nod2D + m->eDim_nod2D;
+#define V_UV(c, nz, e) UV[((size_t)((e) - 1) * L + ((nz) - 1)) * 2 + ((c) - 1)]
+#define V_HE(nz, e) m->helem[(size_t)((e) - 1) * L + ((nz) - 1)]
+#define V_W(nz, n) Wvel[(size_t)((n) - 1) * nl + ((nz) - 1)]
+    for (int n = 1; n <= Nh; ++n)
+        for (int nz = 1; nz <= nl; ++nz) V_W(nz, n) = 0.0;                          /* :2165 */
+    for (int ed = 1; ed <= m->myDim_edge2D; ++ed) {                                 /* :2171 */
+        const int n1 = m->edges[2 * (ed - 1)], n2 = m->edges[2 * (ed - 1) + 1];
+        const int el1 = m->edge_tri[2 * (ed - 1)], el2 = m->edge_tri[2 * (ed - 1) + 1];
+        const double dX1 = m->edge_cross_dxdy[4 * (ed - 1)], dY1 = m->edge_cross_dxdy[4 * (ed - 1) + 1];
+        int nzmin = m->ulevels[el1 - 1], nzmax = m->nlevels[el1 - 1] - 1;           /* :2178-2179 */
+        for (int nz = nzmax; nz >= nzmin; --nz) {                                   /* :2180-2185, :2192,:2201 */
+            const double c1 = (V_UV(2, nz, el1) * dX1 - V_UV(1, nz, el1) * dY1) * V_HE(nz, el1);
+            V_W(nz, n1) = V_W(nz, n1) + c1;
+            V_W(nz, n2) = V_W(nz, n2) - c1;
+        }
+        if (el2 > 0) {                                                              /* :2213 */
+            const double dX2 = m->edge_cross_dxdy[4 * (ed - 1) + 2], dY2 = m->edge_cross_dxdy[4 * (ed - 1) + 3];
+            nzmin = m->ulevels[el2 - 1]; nzmax = m->nlevels[el2 - 1] - 1;
+            for (int nz = nzmax; nz >= nzmin; --nz) {                               /* :2218-2223, :2230,:2239 */
+                const double c1 = -(V_UV(2, nz, el2) * dX2 - V_UV(1, nz, el2) * dY2) * V_HE(nz, el2);
+                V_W(nz, n1) = V_W(nz, n1) + c1;
+                V_W(nz, n2) = V_W(nz, n2) - c1;
+            }
+        }
+    }
+    for (int n = 1; n <= m->myDim_nod2D; ++n) {                                     /* :2277-2286 */
+        const int nzmin = m->ulevels_nod2D[n - 1], nzmax = m->nlevels_nod2D[n - 1] - 1;
+        for (int nz = nzmax; nz >= nzmin; --nz) V_W(nz, n) = V_W(nz, n) + V_W(nz + 1, n);
+    }
+    for (int n = 1; n <= m->myDim_nod2D; ++n) {                                     /* :2301-2308 */
+        const int nzmin = m->ulevels_nod2D[n - 1], nzmax = m->nlevels_nod2D[n - 1] - 1;
+        for (int nz = nzmin; nz <= nzmax; ++nz) V_W(nz, n) = V_W(nz, n) / m->area[(size_t)(n - 1) * nl + (nz - 1)];
+    }
+#undef V_UV
+#undef V_HE
+#undef V_W
+}

@@ -112,6 +112,12 @@ void ora_fill_up_dn_grad(int nl, int myDim_edge2D, const int *edges, const int *
                          const int *nlevels_nod2D_min, const int *ulevels_nod2D_max,
                          const double *elem_area, const double *tr_xy, double *edge_up_dn_grad /* (4,nl-1,E) */);
 
+/* ---- SURVEY.md section 8f row 3, oracle first: the continuity part of vert_vel_ale
+ * (src/oce_ale.F90:2164-2310, linfs, no Fer_GM): edge transports scattered to the two end nodes in edge
+ * order (element 1 then element 2 of each edge), bottom-up cumulative sum over the node column, division
+ * by area.  Wvel is (nl, Nh); only owned nodes are completed (the reference exchanges it afterwards). */
+void ora_vert_vel_ale_core(const ora_mesh_t *m, const double *UV /* (2,nl-1,T) */, double *Wvel);
+
 /* do_oce_adv_tra (oce_adv_tra_driver.F90:46-490) for one tracer.  Returns 0, or 1 for an unknown
  * scheme (the reference calls par_ex there). */
 int ora_do_oce_adv_tra(const ora_mesh_t *m, ora_work_t *wk, double dt,

@@ -321,3 +321,33 @@ def fill_up_dn_grad(mesh, tr_xy, edge_up_dn_tri):
         out[:, :, cx] = np.where(shared, tr[t_el, :, 0], np.where(mean, gx[node], 0.0))
         out[:, :, cy] = np.where(shared, tr[t_el, :, 1], np.where(mean, gy[node], 0.0))
     return out
+
+
+def vert_vel_ale_core(mesh, uv, helem):
+    """src/oce_ale.F90:2164-2310 (linfs, no Fer_GM), vectorised over levels, edges in ascending order (the
+    order of the reference's scatter): uv (T, L, 2), helem (T, L) -> Wvel (Nh, nl), owned nodes completed."""
+    L, nl, Nh, N = mesh.L, mesh.nl, mesh.Nh, mesh.N
+    ed = np.asarray(mesh.edges, dtype=np.int64) - 1
+    et = np.asarray(mesh.edge_tri, dtype=np.int64) - 1
+    cr = np.asarray(mesh.edge_cross_dxdy, dtype=np.float64)
+    nlev, ulev = np.asarray(mesh.nlevels), np.asarray(mesh.ulevels)
+    lev = np.arange(1, L + 1)
+    W = np.zeros((Nh, nl))
+    for e in range(mesh.E):
+        for k, sgn in ((0, 1.0), (1, -1.0)):
+            el = et[e, k]
+            if el < 0:
+                continue
+            wet = (lev >= ulev[el]) & (lev <= nlev[el] - 1)
+            c = (uv[el, :, 1] * cr[e, 2 * k] - uv[el, :, 0] * cr[e, 2 * k + 1]) * helem[el]
+            c = np.where(wet, sgn * c, 0.0)
+            W[ed[e, 0], :L] = np.where(wet, W[ed[e, 0], :L] + c, W[ed[e, 0], :L])
+            W[ed[e, 1], :L] = np.where(wet, W[ed[e, 1], :L] - c, W[ed[e, 1], :L])
+    nln, uln = np.asarray(mesh.nlevels_nod2D), np.asarray(mesh.ulevels_nod2D)
+    area = np.asarray(mesh.area, dtype=np.float64)
+    for n in range(N):
+        a, b = uln[n], nln[n] - 1                            # nzmin, nzmax (1-based layers)
+        for nz in range(b, a - 1, -1):
+            W[n, nz - 1] = W[n, nz - 1] + W[n, nz]
+        W[n, a - 1:b] = W[n, a - 1:b] / area[n, a - 1:b]
+    return W

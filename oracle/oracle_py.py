@@ -228,3 +228,14 @@ def fill_up_dn_grad(mesh, tr_xy: np.ndarray, edge_up_dn_tri: np.ndarray, out: Op
     L_.ora_fill_up_dn_grad(mesh.nl, mesh.E, p[0], p[1], p[2], keep[2][0].shape[1], p[3], p[4], p[5], p[6], p[7], p[8], p[9],
                            ea.ctypes.data_as(c_dp), tx.ctypes.data_as(c_dp), out.ctypes.data_as(c_dp))
     return out
+
+
+def vert_vel_ale_core(rank: "OracleRank") -> np.ndarray:
+    """ora_vert_vel_ale_core on a rank's mesh and uv: Wvel (Nh, nl), completed on the owned nodes."""
+    L_ = lib()
+    L_.ora_vert_vel_ale_core.argtypes = [C.POINTER(OraMesh), c_dp, c_dp]
+    L_.ora_vert_vel_ale_core.restype = None
+    m = rank.mesh_py
+    out = np.zeros((m.Nh, m.nl), np.float64)
+    L_.ora_vert_vel_ale_core(C.byref(rank.cmesh), _dp(rank.keep["uv"]), _dp(out))
+    return out

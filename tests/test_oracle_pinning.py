@@ -145,3 +145,18 @@ def test_gradient_producer_restatements_agree(which, pi_mesh, souf_mesh):
     assert np.isfinite(ga).all() and np.array_equal(ga, gb)
     gt = F.fill_up_dn_grad(g, F.tracer_gradient_elements(g, v, "cpu"), tri, "cpu").numpy()
     assert np.abs(ga - gt).max() <= 1e-13 * np.abs(ga).max()
+
+
+def test_vert_vel_ale_core_restatements_agree(pi_mesh):
+    """SURVEY 8f row 3, oracle first: the continuity part of vert_vel_ale -- C restatement vs NumPy restatement
+    bit for bit, and vs the torch generator of the synthetic w (which scatters with index_add) to round-off"""
+    from oracle import numpy_ref as R, oracle_py as O
+    g = pi_mesh
+    st = F.make_state(g, "cpu")
+    trs = F.make_tracers(g, 1, "cpu")
+    rk = O.OracleRank(g, st, trs, M.nboundary_lay(g))
+    a = O.vert_vel_ale_core(rk)
+    b = R.vert_vel_ale_core(g, st.uv.numpy(), st.helem.numpy())
+    assert np.isfinite(a).all() and np.array_equal(a, b)
+    w = st.w.numpy()
+    assert np.abs(a - w).max() <= 1e-12 * np.abs(w).max()
