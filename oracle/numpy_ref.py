@@ -9,8 +9,9 @@ must agree to round-off.  Scatter order is kept serial (``np.add.at`` is unbuffe
 indices in order; node 1 and node 2 of an edge are interleaved), so the agreement is in practice
 exact.
 
-Covers: hor UPW1 / MUSCL / MFCT, ver UPW1 / QR4C / CDIFF, lim FCT / none, use_wsplit = False,
-one rank.  Arrays are (column, level) = transposes of the Fortran shapes; levels are 1-based in
+Covers: hor UPW1 / MUSCL / MFCT, ver UPW1 / QR4C / CDIFF / PPM, lim FCT / none, use_wsplit (the LO
+vertical flux on w and the implicit Thomas sweep adv_tra_vert_impl on w_i, src/oce_adv_tra_ver.F90:90-240,
+:438-631, src/oce_adv_tra_driver.F90:320-334), one rank.  Arrays are (column, level) = transposes of the Fortran shapes; levels are 1-based in
 masks (``lev``).
 """
 from __future__ import annotations
@@ -26,6 +27,8 @@ class NumpyAdv:
         self.L, self.nl, self.N, self.Nh, self.E = m.L, m.nl, m.N, m.Nh, m.E
         f = lambda t: np.asarray(t.detach().cpu().numpy() if hasattr(t, "detach") else t, dtype=np.float64)
         self.uv, self.w, self.we = f(state.uv), f(state.w), f(state.w_e)
+        self.use_wsplit = bool(getattr(state, "use_wsplit", False))
+        self.wi = f(state.w_i) if (self.use_wsplit and getattr(state, "w_i", None) is not None) else None
         self.helem, self.hnode, self.hnode_new = f(state.helem), f(state.hnode), f(state.hnode_new)
         self.zbar, self.Z = f(state.zbar_3d_n), f(state.Z_3d_n)
         self.nb = np.asarray(nboundary_lay)
@@ -150,13 +153,130 @@ class NumpyAdv:
             val = (-0.5 * (1.0 - num_ord) * Tm - num_ord * (0.5 * (T1 + T2)) * W) * A - out
         return np.where(inner, val, out)
 
-    def ver(self, kind, w, ttf, num_ord, flux_in):
+    def ver_ppm(self, dt, w, ttf, flux_in):
+        """adv_tra_vert_ppm (src/oce_adv_tra_ver.F90:487-627), whole-array form.  Arrays carry a guard of 2
+        columns on each side: index k+2 <-> level / interface k (1-based)."""
+        N, L, nl = self.N, self.L, self.nl
+        nzmin, nzmax = self.uln[:N], self.nln[:N]
+        G = 3
+        pad = lambda a, n: np.concatenate([np.zeros((N, G)), a[:N, :n], np.zeros((N, G + nl - n))], 1)
+        t, h, hold = pad(ttf, L), pad(self.hnode_new, L), pad(self.hnode, L)
+        W, A = pad(w, nl), pad(self.m.area, nl)
+        kk = np.arange(1 - G, nl + 1 + G)[None, :]                       # level index of every padded column
+        sh = lambda a, s: np.roll(a, -s, axis=1)                          # a(k+s) at position k
+        with np.errstate(divide="ignore", invalid="ignore"):
+            # interface values tv(nz+1) of the loop :514-581 evaluated at every nz, masked afterwards
+            dm1, dj, dp1, dp2 = sh(h, -1), h, sh(h, 1), sh(h, 2)
+            tm1, t0, tp1, tp2 = sh(t, -1), t, sh(t, 1), sh(t, 2)
+            dlt = dj / (dm1 + dj + dp1) * ((2.0 * dm1 + dj) / (dp1 + dj) * (tp1 - t0) + (dj + 2.0 * dp1) / (dm1 + dj) * (t0 - tm1))
+            dlt1 = dp1 / (dj + dp1 + dp2) * ((2.0 * dj + dp1) / (dp2 + dp1) * (tp2 - tp1) + (dp1 + 2.0 * dp2) / (dj + dp1) * (tp1 - t0))
+            sgn = lambda x: np.where(np.signbit(x), -1.0, 1.0)            # sign(1.0, x)
+            lim = np.minimum(np.minimum(np.abs(dlt), 2.0 * np.abs(tp1 - t0)), 2.0 * np.abs(t0 - tm1)) * sgn(dlt)
+            dlt = np.where((tp1 - t0) * (t0 - tm1) > 0.0, lim, 0.0)
+            lim1 = np.minimum(np.minimum(np.abs(dlt1), 2.0 * np.abs(tp2 - tp1)), 2.0 * np.abs(tp1 - t0)) * sgn(dlt1)
+            dlt1 = np.where((tp2 - tp1) * (tp1 - t0) > 0.0, lim1, 0.0)
+            tvn = t0 + dj / (dj + dp1) * (tp1 - t0) + 1.0 / (dm1 + dj + dp1 + dp2) * (
+                (2.0 * dp1 * dj) / (dj + dp1) * ((dm1 + dj) / (2.0 * dj + dp1) - (dp2 + dp1) / (2.0 * dp1 + dj)) * (tp1 - t0)
+                - dj * (dm1 + dj) / (2.0 * dj + dp1) * dlt1 + dp1 * (dp1 + dp2) / (dj + 2.0 * dp1) * dlt)
+        tv = np.zeros_like(t)
+        inner = (kk >= nzmin + 1) & (kk <= nzmax - 3)                     # loop index nz, writes tv(nz+1)
+        tv = np.where(sh(inner, -1), sh(tvn, -1), tv)
+        # the four special interfaces in the order the reference assigns them (:497-507): later wins
+        rows = np.arange(N)
+        col = lambda k: (k + G - 1).ravel()                               # padded column of level k (1-based)
+        tcol = lambda k: t[rows, col(k)]
+        tv[rows, col(nzmin)] = tcol(nzmin)
+        tv[rows, col(nzmin + 1)] = 0.5 * (tcol(nzmin) + tcol(nzmin + 1))
+        tv[rows, col(nzmax - 1)] = 0.5 * (tcol(nzmax - 2) + tcol(nzmax - 1))
+        tv[rows, col(nzmax)] = tcol(nzmax - 1)
+        # parabola of every layer (:585-604)
+        aL, aR = tv.copy(), sh(tv, 1).copy()
+        flat = (aR - t) * (t - aL) <= 0.0
+        aL = np.where(flat, t, aL); aR = np.where(flat, t, aR)
+        c1 = (aR - aL) * (t - 0.5 * (aL + aR)) > (aR - aL) ** 2 / 6.0
+        aL = np.where(c1, 3.0 * t - 2.0 * aR, aL)
+        c2 = (aR - aL) * (t - 0.5 * (aR + aL)) < -((aR - aL) ** 2) / 6.0
+        aR = np.where(c2, 3.0 * t - 2.0 * aL, aR)
+        aj = 6.0 * (t - 0.5 * (aL + aR))
+        layer = (kk >= nzmin) & (kk <= nzmax - 1)
+        Wn = sh(W, 1)
+        skip = (W <= 0.0) & (Wn >= 0.0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            xu = np.minimum(W * dt / hold, 1.0)
+            fu = (-aL - 0.5 * xu * (aR - aL + (1.0 - 2.0 / 3.0 * xu) * aj)) * A * W          # tvert(nz), W(nz) > 0
+            xd = np.minimum(-Wn * dt / hold, 1.0)
+            fd = (-aR + 0.5 * xd * (aR - aL - (1.0 - 2.0 / 3.0 * xd) * aj)) * sh(A, 1) * Wn   # tvert(nz+1), W(nz+1) < 0
+        tvert = np.zeros_like(t)
+        tvert = np.where(layer & ~skip & (W > 0.0), fu, tvert)
+        dn = layer & ~skip & (Wn < 0.0)
+        tvert = np.where(sh(dn, -1), sh(fd, -1), tvert)
+        tvert[rows, col(nzmin)] = -tv[rows, col(nzmin)] * W[rows, col(nzmin)] * A[rows, col(nzmin)]
+        tvert[rows, col(nzmax)] = 0.0
+        tvert = tvert[:, G:G + nl]
+        k = np.arange(1, nl + 1)[None, :]
+        return np.where((k >= nzmin) & (k <= nzmax), tvert - flux_in, flux_in)
+
+    def vert_impl(self, dt, w, ttf):
+        """adv_tra_vert_impl (src/oce_adv_tra_ver.F90:120-236): implicit upwind vertical advection, Thomas sweep
+        written level by level over all owned columns at once.  Returns the updated (Nh, L) field."""
+        N, L = self.N, self.L
+        m = self.m
+        out = np.array(ttf, dtype=np.float64, copy=True)
+        nzmin = self.uln[:N, 0].astype(np.int64); nzmax = self.nln[:N, 0].astype(np.int64)
+        W, A, AV, H, T = w[:N], m.area[:N], m.areasvol[:N], self.hnode_new[:N], out[:N]
+        rows = np.arange(N)
+        at = lambda a, k: a[rows, np.clip(k - 1, 0, a.shape[1] - 1)]      # a(k) per column, k 1-based arrays
+        a_ = np.zeros((N, L + 2)); b_ = np.zeros((N, L + 2)); c_ = np.zeros((N, L + 2)); tr = np.zeros((N, L + 2))
+        zinv = 1.0 * dt
+        for nz in range(1, L + 1):
+            kz = np.full(N, nz)
+            first, mid, last = kz == nzmin, (kz >= nzmin + 1) & (kz <= nzmax - 2), kz == nzmax - 1
+            act = first | mid | last
+            if not act.any():
+                continue
+            with np.errstate(divide="ignore", invalid="ignore"):
+                v1 = zinv * at(A, kz) / at(AV, kz)
+                v2 = zinv * at(A, kz + 1) / at(AV, kz)
+            wk, wk1, h = at(W, kz), at(W, kz + 1), at(H, kz)
+            a = np.where(first, 0.0, np.minimum(0.0, wk) * v1)
+            b = np.where(first, h + wk * v1, h + np.maximum(0.0, wk) * v1)
+            b = np.where(last & ~first, b, b - np.minimum(0.0, wk1) * v2)
+            c = np.where(last & ~first, 0.0, -np.maximum(0.0, wk1) * v2)
+            tm1, t0, tp1 = at(T, kz - 1), at(T, kz), at(T, kz + 1)
+            r_first = -(b - h) * t0 - c * tp1
+            r_mid = -a * tm1 - (b - h) * t0 - c * tp1
+            r_last = -a * tm1 - (b - h) * t0
+            r = np.where(first, r_first, np.where(mid, r_mid, r_last))
+            a_[:, nz] = np.where(act, a, 0.0); b_[:, nz] = np.where(act, b, 0.0)
+            c_[:, nz] = np.where(act, c, 0.0); tr[:, nz] = np.where(act, r, 0.0)
+        cp = np.zeros((N, L + 2)); tp = np.zeros((N, L + 2))
+        for nz in range(1, L + 1):
+            kz = np.full(N, nz)
+            first = kz == nzmin
+            rest = (kz >= nzmin + 1) & (kz <= nzmax - 1)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                mm = b_[:, nz] - cp[:, nz - 1] * a_[:, nz]
+                cp[:, nz] = np.where(first, c_[:, nz] / b_[:, nz], np.where(rest, c_[:, nz] / mm, 0.0))
+                tp[:, nz] = np.where(first, tr[:, nz] / b_[:, nz], np.where(rest, (tr[:, nz] - tp[:, nz - 1] * a_[:, nz]) / mm, 0.0))
+        x = np.zeros((N, L + 2))
+        for nz in range(L, 0, -1):
+            kz = np.full(N, nz)
+            bottom = kz == nzmax - 1
+            above = (kz >= nzmin) & (kz <= nzmax - 2)
+            x[:, nz] = np.where(bottom, tp[:, nz], np.where(above, tp[:, nz] - cp[:, nz] * x[:, nz + 1], 0.0))
+        valid = self.nvalid[:N]
+        out[:N] = np.where(valid, T + x[:, 1:L + 1], T)
+        return out
+
+    def ver(self, kind, w, ttf, num_ord, flux_in, dt=None):
         if kind == "UPW1":
             return self.ver_upw1(w, ttf, flux_in)
         if kind == "QR4C":
             return self.ver_qr4c(w, ttf, num_ord, flux_in)
         if kind == "CDIFF":
             return self.ver_cdiff(w, ttf, flux_in)
+        if kind == "PPM":
+            return self.ver_ppm(dt, w, ttf, flux_in)
         raise ValueError(kind)
 
     # ------------------------------------------------------------------ FCT limiter
@@ -230,8 +350,11 @@ class NumpyAdv:
                 lo_new = (ttf[:N] * self.hnode[:N] + (lo[:N] + (flo_v[:, :L] - flo_v[:, 1:L + 1])) * dt / av) / self.hnode_new[:N]
             lo = np.where(self.nvalid, 0.0, 0.0)
             lo[:N] = np.where(valid, lo_new, 0.0)
+            if self.use_wsplit:                                          # driver :320-334
+                lo = self.vert_impl(dt, self.wi, lo)
+                flo_v = self.ver_upw1(self.w, ttf, zV)
             adf_h = self.hor_ho(tr.tra_adv_hor.strip(), ttfAB, grad, Q, tr.tra_adv_ph, flo_h)
-            adf_v = self.ver(tr.tra_adv_ver.strip(), self.w, ttfAB, tr.tra_adv_pv, flo_v)
+            adf_v = self.ver(tr.tra_adv_ver.strip(), self.w, ttfAB, tr.tra_adv_pv, flo_v, dt)
             Rp, Rm, adf_v = self.fct(dt, ttf, lo, adf_h, adf_v)
             Rp_all = np.zeros((self.Nh, L)); Rm_all = np.zeros((self.Nh, L))
             Rp_all[:N], Rm_all[:N] = Rp, Rm
@@ -240,7 +363,7 @@ class NumpyAdv:
             self.keep = dict(fct_LO=lo, fct_plus=Rp_all, fct_minus=Rm_all)
         else:
             adf_h = self.hor_ho(tr.tra_adv_hor.strip(), ttfAB, grad, Q, tr.tra_adv_ph, zE)
-            adf_v = self.ver(tr.tra_adv_ver.strip(), self.we, ttfAB, tr.tra_adv_pv, zV)
+            adf_v = self.ver(tr.tra_adv_ver.strip(), self.we, ttfAB, tr.tra_adv_pv, zV, dt)
         with np.errstate(divide="ignore", invalid="ignore"):
             dttf_v[:N] = np.where(valid, dttf_v[:N] + (adf_v[:, :L] - adf_v[:, 1:L + 1]) * dt / av, dttf_v[:N])
         # U3: per edge, node 1 then node 2, addend (flux*dt)/areasvol(nz,node)

@@ -49,6 +49,28 @@ def test_numpy_restatement_agrees_on_pi(pi_mesh, hor, ver, lim):
             assert rel_err(keep[name][:N], ora.keep[name][:N]) <= TOL, name
 
 
+@pytest.mark.parametrize("hor,ver,lim,wsplit", [("MFCT", "PPM", "FCT", False), ("MUSCL", "PPM", "NON", False),
+                                                ("MFCT", "QR4C", "FCT", True), ("MUSCL", "PPM", "FCT", True),
+                                                ("UPW1", "CDIFF", "FCT", True)])
+@pytest.mark.parametrize("which", ["pi", "small"])
+def test_numpy_restatement_ppm_and_wsplit(pi_mesh, small_mesh, which, hor, ver, lim, wsplit):
+    """PPM (src/oce_adv_tra_ver.F90:438-631), adv_tra_vert_impl (:90-240) and the use_wsplit branch of the driver
+    (src/oce_adv_tra_driver.F90:320-334) in the second, vectorised restatement: every scheme now has two
+    independently written CPU restatements that must agree."""
+    mesh = pi_mesh if which == "pi" else small_mesh
+    st, trs, nb, dt = make_case(mesh, 2, hor, ver, lim, ph=0.25, pv=0.75, use_wsplit=wsplit)
+    ora = run_oracle(mesh, st, trs, nb, dt)
+    res = _numpy_run(mesh, st, trs, nb, dt)
+    N = mesh.N
+    for k, (dh, dv, keep) in enumerate(res):
+        assert rel_err(dh[:N], ora.dttf_h[k][:N]) <= TOL, ("dttf_h", k)
+        assert rel_err(dv[:N], ora.dttf_v[k][:N]) <= TOL, ("dttf_v", k)
+    if lim == "FCT":
+        keep = res[-1][2]
+        for name in ("fct_LO", "fct_plus", "fct_minus"):
+            assert rel_err(keep[name][:N], ora.keep[name][:N]) <= TOL, name
+
+
 def test_numpy_restatement_agrees_on_soufflet(souf_mesh):
     st, trs, nb, dt = make_case(souf_mesh, 2, "MFCT", "QR4C", "FCT")
     ora = run_oracle(souf_mesh, st, trs, nb, dt)
