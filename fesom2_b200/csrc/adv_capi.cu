@@ -106,6 +106,7 @@ struct Slot {  // per-tracer staging: host pointers, unaligned device pointers, 
 struct ChunkBuf {
     DevBuf<double> lo, pm, adf_h, adf_v;
     DevBuf<double> sendbuf;                   // send columns x L x 4
+    int tb_last = 0;                          // tracers per chunk of the last use: the [column][level][TB] interleave depends on it
 };
 
 struct TrLoc { int chunk = -1, pos = 0, tb = 1; };  // where tracer i of the last call lives
@@ -143,6 +144,10 @@ struct adv_ctx {
     int i_identity = 1;                       // interior range as identity range + skip flags (ADV_I_IDENTITY)
     int e1_pf = 100;                          // metadata prefetch distance of the bulk edge kernel in CTAs (ADV_E1_PF)
     int force_tb1 = 0;                        // experiments: one tracer per chunk (ADV_TB1)
+    // wet-level compaction: CTA partitions of the node ranges and edge groups (built in adv_ctx_create)
+    int cta_threads = 224;                    // threads per CTA of the FCT node kernels (ADV_CTA_THREADS)
+    struct Part { DevBuf<int> first; int ncta = 0; };
+    Part part_all, part_i, part_s, part_sh;
     int max_smem_optin = 0;
     std::vector<Peer> rpeers, speers;
     int send_cols = 0;
@@ -309,6 +314,8 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
     if (const char* v = getenv("ADV_TB1")) c->force_tb1 = atoi(v);
     if (const char* v = getenv("ADV_I_IDENTITY")) c->i_identity = atoi(v) ? 1 : 0;
     if (const char* v = getenv("ADV_E1_PF")) c->e1_pf = std::max(0, atoi(v));
+    if (const char* v = getenv("ADV_CTA_THREADS")) c->cta_threads = atoi(v);
+    c->cta_threads = std::max(((L + 31) / 32) * 32, std::min(1024, (c->cta_threads / 32) * 32));   // whole warps, at least one column
     cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
 #define CUF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { delete c; return fail(ADV_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
     CUF(c->ne_ptr.upload(ne_ptr)); CUF(c->ne_ent.upload(ne_ent));
@@ -367,6 +374,32 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
         for (int n = N; n < Nh; ++n) SH.push_back(n);
         c->nS = (int)S.size(); c->nI = (int)I.size(); c->nSH = (int)SH.size();
         CUF(c->list_S.upload(S)); CUF(c->list_I.upload(I)); CUF(c->list_SH.upload(SH)); CUF(c->slist.upload(sl));
+    }
+    // ---- wet-level compaction: pack whole columns into CTAs of cta_threads threads (one thread per wet layer) -----
+    {
+        auto pack = [&](int count, auto wet_of, adv_ctx::Part& out) -> cudaError_t {
+            std::vector<int> first(1, 0);
+            int used = 0, ncol = 0;
+            for (int i = 0; i < count; ++i) {
+                const int w = wet_of(i);
+                if (ncol > 0 && (used + w > c->cta_threads || ncol == kMaxCols)) { first.push_back(i); used = 0; ncol = 0; }
+                used += w; ++ncol;
+            }
+            first.push_back(count);
+            out.ncta = count > 0 ? (int)first.size() - 1 : 0;
+            return out.first.upload(first);
+        };
+        auto wet_node = [&](int n) { return d->nlevels_nod2D[n] - d->ulevels_nod2D[n]; };
+        CUF(pack(N, wet_node, c->part_all));
+        if (c->npes > 1) {
+            std::vector<int> S, SH;
+            for (int n = 0; n < N; ++n) if ((node_rec[n].y >> 24) & 1u) S.push_back(n);
+            SH = S;
+            for (int n = N; n < Nh; ++n) SH.push_back(n);
+            CUF(pack(N, [&](int n) { return ((node_rec[n].y >> 24) & 1u) ? 0 : wet_node(n); }, c->part_i));
+            CUF(pack((int)S.size(), [&](int i) { return wet_node(S[i]); }, c->part_s));
+            CUF(pack((int)SH.size(), [&](int i) { return wet_node(SH[i]); }, c->part_sh));
+        }
     }
     c->slots.resize(max_tracers);
     c->trloc.resize(max_tracers);
@@ -471,14 +504,9 @@ namespace {
 struct Group { int fct, hor, ver; std::vector<int> idx; };
 struct ChunkSel { int fct, hor, ver, tb; int idx[2]; int buf; };
 
-// columns per CTA: as many as fit into 224 threads (7 warps) -- the size the per-kernel register
-// budgets were tuned for (4-5 resident CTAs per SM); one column when a column alone is longer
-inline int cols_per_block(int L)
-{
-    const char* v = getenv("ADV_CTA_THREADS");                      // experiments only
-    const int limit = v ? std::max(32, std::min(kBlock, atoi(v))) : 224;
-    return std::max(1, limit / L);
-}
+// columns per CTA of the kernels that keep the fixed (column, level) thread map (non-FCT branch, gradients,
+// register-gather edge kernel): as many as fit into 224 threads; one column when a column alone is longer
+inline int cols_per_block(int L) { return std::max(1, 224 / L); }
 inline int nblocks(int count, int cpb) { return (count + cpb - 1) / cpb; }
 
 struct TrPtrs {   // device pointers of the call's tracers
@@ -536,6 +564,17 @@ static bool chunk_aligned(const MeshDev& m, const Chunk<TB>& b)
     return (x & 15u) == 0;
 }
 
+static NodePart node_part(const adv_ctx* c, int rid)
+{
+    switch (rid) {
+    case R_S: return NodePart{c->part_s.first.p, c->list_S.p, c->part_s.ncta, c->pf_dist, 0};
+    // interior = all owned nodes minus the boundary set: an identity range in which the flagged columns get no threads
+    case R_I: return NodePart{c->part_i.first.p, nullptr, c->part_i.ncta, c->pf_dist, 1};
+    case R_SH: return NodePart{c->part_sh.first.p, c->list_SH.p, c->part_sh.ncta, c->pf_dist, 0};
+    default: return NodePart{c->part_all.first.p, nullptr, c->part_all.ncta, c->pf_dist, 0};
+    }
+}
+
 template <int TB>
 int launch_phase(adv_ctx* c, Phase ph, int hor, int ver, bool q_stored, const Chunk<TB>& b, int rid, double dt)
 {
@@ -544,18 +583,21 @@ int launch_phase(adv_ctx* c, Phase ph, int hor, int ver, bool q_stored, const Ch
     cudaError_t se = cudaSuccess;
     bool piped = false;
     int grid = 0, nthr = 0;
+    size_t smem = 0;
     if (ph == PH_E1) {
         const int epb = cols_per_block(m.L);
         nthr = epb * m.L;
         if (c->bulk && hor != HOR_UPW1 && chunk_aligned<TB>(m, b)) {
+            // fixed (edge column, level) thread map: the compacted variant (groups of edges filling the CTA, measured in
+            // profiles/r4_compaction.md) lost more to the extra shared-memory lookups per group than it gained in lanes
             const int ng = std::max(1, std::min(c->e1_ng, nthr / epb));
             const int nge = epb * ng, D = c->e1_depth;
             grid = nblocks(m.E, nge);
 #define E1B(H, Q, DD) if (!piped && hor == H && (q_stored ? 1 : 0) == Q && D == DD) { \
-                const size_t sm = e1b_smem_bytes<TB, Q>(nge, nthr, DD); \
-                if ((int)sm <= c->max_smem_optin) { \
-                    se = smem_optin(k_edge_flux_b<H, TB, Q, DD>, sm); \
-                    if (se == cudaSuccess) k_edge_flux_b<H, TB, Q, DD><<<grid, nthr, sm, s>>>(m, b, epb, ng, c->e1_il, c->e1_pf); \
+                smem = e1b_smem_bytes<TB, Q>(nge, nthr, DD); \
+                if ((int)smem <= c->max_smem_optin) { \
+                    se = smem_optin(k_edge_flux_b<H, TB, Q, DD>, smem); \
+                    if (se == cudaSuccess) k_edge_flux_b<H, TB, Q, DD><<<grid, nthr, smem, s>>>(m, b, epb, ng, c->e1_il, c->e1_pf); \
                     piped = true; } }
 #define E1BD(H, Q) E1B(H, Q, 2) E1B(H, Q, 3) E1B(H, Q, 4)
             E1BD(HOR_MUSCL, 0) E1BD(HOR_MUSCL, 1) E1BD(HOR_MFCT, 0) E1BD(HOR_MFCT, 1)
@@ -569,46 +611,54 @@ int launch_phase(adv_ctx* c, Phase ph, int hor, int ver, bool q_stored, const Ch
             E1(HOR_UPW1) E1(HOR_MUSCL) E1(HOR_MFCT)
 #undef E1
         }
-    } else {
+    } else if (ph == PH_NOFCT) {
         const NodeRange r = node_range(c, rid, cols_per_block(m.L));
         if (r.count <= 0) return ADV_OK;
         nthr = r.cpb * m.L;
         const size_t sm1 = (size_t)TB * nthr * sizeof(double);
+        grid = nblocks(r.count, r.cpb);
+#define HV(H, V) if (hor == H && ver == V) k_nofct<H, V, TB><<<grid, nthr, sm1, s>>>(m, b, r, dt);
+        HV(HOR_UPW1, VER_UPW1) HV(HOR_UPW1, VER_QR4C) HV(HOR_UPW1, VER_PPM) HV(HOR_UPW1, VER_CDIFF)
+        HV(HOR_MUSCL, VER_UPW1) HV(HOR_MUSCL, VER_QR4C) HV(HOR_MUSCL, VER_PPM) HV(HOR_MUSCL, VER_CDIFF)
+        HV(HOR_MFCT, VER_UPW1) HV(HOR_MFCT, VER_QR4C) HV(HOR_MFCT, VER_PPM) HV(HOR_MFCT, VER_CDIFF)
+#undef HV
+    } else {
+        // FCT node kernels: wet-level compaction, CTA partition of the range built in adv_ctx_create
+        const NodePart r = node_part(c, rid);
+        if (r.ncta <= 0) return ADV_OK;
+        nthr = c->cta_threads;
+        grid = r.ncta;
+        const size_t hdr = node_smem_header(m.ell_w);
+        // dynamic shared memory above 48 KB needs the opt-in attribute (set once per instantiation: cheap, idempotent)
+#define NODE_LAUNCH(K, BYTES) do { smem = (BYTES); if (smem > 48 * 1024) se = smem_optin(K, smem); \
+                                   if (se == cudaSuccess) K<<<grid, nthr, smem, s>>>(m, b, r, dt); } while (0)
         if (ph == PH_N1) {
-            grid = nblocks(r.count, r.cpb);
-#define N1(V) if (ver == V) { const size_t smn = (size_t)n1_smem_arrays<V, TB>() * nthr * sizeof(double); \
-                              if (c->g_lo == 6) k_node_lo<V, TB, 6><<<grid, nthr, smn, s>>>(m, b, r, dt); \
-                              else if (c->g_lo == 2) k_node_lo<V, TB, 2><<<grid, nthr, smn, s>>>(m, b, r, dt); \
-                              else k_node_lo<V, TB, 3><<<grid, nthr, smn, s>>>(m, b, r, dt); }
+#define N1(V) if (ver == V) { const size_t smn = hdr + (size_t)n1_smem_arrays<V, TB>() * nthr * sizeof(double); \
+                              if (c->g_lo == 6) NODE_LAUNCH((k_node_lo<V, TB, 6>), smn); \
+                              else if (c->g_lo == 2) NODE_LAUNCH((k_node_lo<V, TB, 2>), smn); \
+                              else NODE_LAUNCH((k_node_lo<V, TB, 3>), smn); }
             N1(VER_UPW1) N1(VER_QR4C) N1(VER_PPM) N1(VER_CDIFF)
 #undef N1
         } else if (ph == PH_K2) {
-            grid = nblocks(r.count, r.cpb);
-            if (c->g_k2 == 6) k_fct_bounds<TB, 6><<<grid, nthr, 2 * sm1, s>>>(m, b, r, dt);
-            else if (c->g_k2 == 2) k_fct_bounds<TB, 2><<<grid, nthr, 2 * sm1, s>>>(m, b, r, dt);
-            else if (c->g_k2 == 1) k_fct_bounds<TB, 1><<<grid, nthr, 2 * sm1, s>>>(m, b, r, dt);
-            else k_fct_bounds<TB, 3><<<grid, nthr, 2 * sm1, s>>>(m, b, r, dt);
-        } else if (ph == PH_K3) {
-            grid = nblocks(r.count, r.cpb);
-            if (c->g_k3 == 6) k_fct_update<TB, 6><<<grid, nthr, 0, s>>>(m, b, r, dt);
-            else if (c->g_k3 == 2) k_fct_update<TB, 2><<<grid, nthr, 0, s>>>(m, b, r, dt);
-            else if (c->g_k3 == 1) k_fct_update<TB, 1><<<grid, nthr, 0, s>>>(m, b, r, dt);
-            else k_fct_update<TB, 3><<<grid, nthr, 0, s>>>(m, b, r, dt);
+            const size_t sm2 = hdr + (size_t)2 * TB * nthr * sizeof(double);
+            if (c->g_k2 == 6) NODE_LAUNCH((k_fct_bounds<TB, 6>), sm2);
+            else if (c->g_k2 == 3) NODE_LAUNCH((k_fct_bounds<TB, 3>), sm2);
+            else if (c->g_k2 == 1) NODE_LAUNCH((k_fct_bounds<TB, 1>), sm2);
+            else NODE_LAUNCH((k_fct_bounds<TB, 2>), sm2);
         } else {
-            grid = nblocks(r.count, r.cpb);
-#define HV(H, V) if (hor == H && ver == V) k_nofct<H, V, TB><<<grid, nthr, sm1, s>>>(m, b, r, dt);
-            HV(HOR_UPW1, VER_UPW1) HV(HOR_UPW1, VER_QR4C) HV(HOR_UPW1, VER_PPM) HV(HOR_UPW1, VER_CDIFF)
-            HV(HOR_MUSCL, VER_UPW1) HV(HOR_MUSCL, VER_QR4C) HV(HOR_MUSCL, VER_PPM) HV(HOR_MUSCL, VER_CDIFF)
-            HV(HOR_MFCT, VER_UPW1) HV(HOR_MFCT, VER_QR4C) HV(HOR_MFCT, VER_PPM) HV(HOR_MFCT, VER_CDIFF)
-#undef HV
+            if (c->g_k3 == 6) NODE_LAUNCH((k_fct_update<TB, 6>), hdr);
+            else if (c->g_k3 == 3) NODE_LAUNCH((k_fct_update<TB, 3>), hdr);
+            else if (c->g_k3 == 1) NODE_LAUNCH((k_fct_update<TB, 1>), hdr);
+            else NODE_LAUNCH((k_fct_update<TB, 2>), hdr);
         }
+#undef NODE_LAUNCH
     }
     ++c->launches;
     static const char* names[] = {"k_edge_flux", "k_node_lo", "k_fct_bounds", "k_fct_update", "k_nofct"};
-    if (se != cudaSuccess) return fail(ADV_ECUDA, std::string(names[ph]) + "_p attributes: " + cudaGetErrorString(se));
+    if (se != cudaSuccess) return fail(ADV_ECUDA, std::string(names[ph]) + " attributes: " + cudaGetErrorString(se));
     if (cudaError_t e = cudaGetLastError()) {
-        return fail(ADV_ECUDA, std::string("launch ") + names[ph] + (piped ? "_p" : "") + " (grid " + std::to_string(grid) + ", block " + std::to_string(nthr) +
-                                   ", hor " + std::to_string(hor) + ", ver " + std::to_string(ver) + ", tb " + std::to_string(TB) + "): " + cudaGetErrorString(e));
+        return fail(ADV_ECUDA, std::string("launch ") + names[ph] + (piped ? "_b" : "") + " (grid " + std::to_string(grid) + ", block " + std::to_string(nthr) +
+                                   ", smem " + std::to_string(smem) + ", hor " + std::to_string(hor) + ", ver " + std::to_string(ver) + ", tb " + std::to_string(TB) + "): " + cudaGetErrorString(e));
     }
     return ADV_OK;
 }
@@ -681,6 +731,13 @@ static int run_batch(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr
     if (int rc = ensure_chunk_bufs(c, (int)chunks.size())) return rc;
     for (size_t k = 0; k < chunks.size(); ++k) {
         chunks[k].buf = (int)k;
+        // the kernels only write wet levels and rely on the zeros of the allocation below the sea floor; a buffer
+        // reused with another interleave (TB 1 <-> 2) would show stale values there: clear it
+        ChunkBuf& cb = *c->cbufs[k];
+        if (cb.tb_last != 0 && cb.tb_last != chunks[k].tb) {
+            for (DevBuf<double>* x : {&cb.lo, &cb.pm, &cb.adf_h, &cb.adf_v}) CU(cudaMemsetAsync(x->p, 0, x->n * sizeof(double), c->s_comp));
+        }
+        cb.tb_last = chunks[k].tb;
         for (int t = 0; t < chunks[k].tb; ++t) c->trloc[chunks[k].idx[t]] = TrLoc{(int)k, t, chunks[k].tb};
     }
     cudaStream_t sc = c->s_comp, sx = c->s_comm;

@@ -560,31 +560,119 @@ __device__ __forceinline__ NodeThread node_thread(const MeshDev& m, const NodeRa
     return t;
 }
 
-// Own-column prefetch of the CTA `pf` launches ahead: thread 32 + a * cpb + j pulls column j of array a
-// into L2 with ONE bulk prefetch (cp.async.bulk.prefetch.L2, any length).
-struct PfArr { const void* base; unsigned col_bytes; };
-template <int NA>
-__device__ __forceinline__ void prefetch_own_columns(const NodeRange& r, const PfArr (&arr)[NA])
+// ----------------------------------------------------------------------------------------------
+// Wet-level compaction of the FCT node kernels (N1, K2, K3).  A CTA owns a run of WHOLE columns chosen on the
+// host so that their wet layers fill the CTA (adv_ctx_create: NodePartHost), and every wet (column, layer) gets
+// one thread: no lane is spent below the sea floor (round 1: 23-24 of 32 lanes active).  Warp 0 decodes the
+// records of the CTA's columns and a prefix sum of their depths; the adjacency (ELL) rows of all columns are
+// staged in shared memory by the whole CTA at the same time (for identity ranges the node id is known
+// without any load, so record and rows are fetched in parallel: one dependent wait less than round 1's
+// record -> row -> operands chain), then each thread finds its column with a few shared-memory compares.
+// ----------------------------------------------------------------------------------------------
+constexpr int kMaxCols = 16;       // columns per CTA (<= 32: the prefix sum runs in one warp)
+struct NodePart {
+    const int* cta_first;          // (ncta + 1) position in the range of the first column of every CTA
+    const int* list;               // optional position -> node id (0-based); nullptr = identity
+    int ncta;
+    int pf;                        // prefetch distance in CTAs (0 = off)
+    int skip_s;                    // 1: columns flagged "boundary set" in node_rec get no threads
+};
+struct NodeSmem {                  // header of the node kernels' dynamic shared memory
+    uint2 rec[kMaxCols];
+    int n[kMaxCols];
+    int off[kMaxCols + 1];         // first thread of column j; off[ncols] = number of threads in use
+    int pad_[3];
+};
+static_assert(sizeof(NodeSmem) % 16 == 0, "NodeSmem must keep the 16-byte alignment of what follows");
+__host__ __device__ inline size_t node_smem_header(int ell_w) { return sizeof(NodeSmem) + (size_t)kMaxCols * ell_w * sizeof(int4); }
+
+struct NodeCta {
+    int n, nz, nzmin, nzmax;       // node (0-based), layer (1-based), ulevels_nod2D, nlevels_nod2D
+    int pad_lo, pad_hi, self_lo, self_hi, deg;
+    int base;                      // first thread of this thread's column: column-local index of layer k is base + k - nzmin
+    bool valid;                    // this thread owns a wet (column, layer)
+    const int4* ell;               // the column's adjacency row in shared memory
+};
+
+// prefetch (L2) what the CTA `pf` launches ahead will wait for first: its column records and adjacency rows
+// (one contiguous block each for identity ranges) and the wet part of its own columns of `arr`
+struct PfArr { const void* base; unsigned col_bytes, lev_bytes; int iface; };   // column stride, bytes per level, 1: nl interfaces per column
+template <int NA, class F>
+__device__ __forceinline__ void node_cta_prefetch(const MeshDev& m, const NodePart& r, F arr, bool own)
 {
-    const int k = (int)threadIdx.x - 32;                  // warp 1 onwards: warp 0 does the metadata
-    if (r.pf <= 0 || k < 0) return;
-    int a, nf, rows;
-    if (r.list == nullptr) {                              // consecutive nodes: the cpb columns are one block
-        if (k >= NA) return;
-        const long long i0 = ((long long)blockIdx.x + r.pf) * r.cpb;
-        if (i0 >= r.count) return;
-        a = k; nf = r.begin + (int)i0; rows = min(r.cpb, r.count - (int)i0);
-    } else {                                              // list range: one column per thread
-        if (k >= NA * r.cpb) return;
-        a = k / r.cpb;
-        const long long i = ((long long)blockIdx.x + r.pf) * r.cpb + (k - a * r.cpb);
-        if (i >= r.count) return;
-        nf = __ldg(&r.list[r.begin + i]); rows = 1;
-    }
-    const void* base = arr[0].base; unsigned cb = arr[0].col_bytes;
+    if (r.pf <= 0 || (int)threadIdx.x < 32) return;      // warp 1 onwards: warp 0 is busy with the prefix sum
+    const int cta = (int)blockIdx.x + r.pf;
+    if (cta >= r.ncta) return;
+    const int c0 = __ldg(&r.cta_first[cta]), c1 = __ldg(&r.cta_first[cta + 1]);
+    const int na = own ? NA : 0;
+    for (int k = (int)threadIdx.x - 32; k < (na + 1) * kMaxCols; k += (int)blockDim.x - 32) {
+        const int a = k / kMaxCols, j = k - a * kMaxCols;     // a == 0: metadata, a >= 1: array a-1; column j
+        if (c0 + j >= c1) continue;
+        const int n = r.list ? __ldg(&r.list[c0 + j]) : c0 + j;
+        if (a == 0) {
+            const char* row = reinterpret_cast<const char*>(m.ne_ell + (size_t)n * m.ell_w);
+            l2_prefetch_line(&m.node_rec[n]);
+            l2_prefetch_line(row);
+            l2_prefetch_line(row + m.ell_w * 16 - 1);
+            continue;
+        }
+        if (n >= m.N) continue;                                // halo columns (K3): not every array covers them
+        const uint2 rec = __ldg(&m.node_rec[n]);
+        if (r.skip_s && ((rec.y >> 24) & 1u)) continue;
+        const unsigned lo = rec.x & 0xff, hi = (rec.x >> 8) & 0xff;      // layers lo .. hi-1, interfaces lo .. hi
+        PfArr x = arr(0);               // arr(q) with a compile-time q: nothing is materialised in local memory
 #pragma unroll
-    for (int q = 1; q < NA; ++q) if (a == q) { base = arr[q].base; cb = arr[q].col_bytes; }
-    l2_prefetch(reinterpret_cast<const char*>(base) + (size_t)nf * cb, (unsigned)rows * cb);
+        for (int q = 1; q < NA; ++q) if (a - 1 == q) x = arr(q);
+        l2_prefetch(reinterpret_cast<const char*>(x.base) + (size_t)n * x.col_bytes + (size_t)(lo - 1) * x.lev_bytes,
+                    (hi - lo + (x.iface ? 1u : 0u)) * x.lev_bytes);
+    }
+}
+
+__device__ __forceinline__ NodeCta node_cta(const MeshDev& m, const NodePart& r, unsigned char* smem_raw)
+{
+    NodeSmem* h = reinterpret_cast<NodeSmem*>(smem_raw);
+    int4* s_ell = reinterpret_cast<int4*>(smem_raw + sizeof(NodeSmem));
+    const int tid = threadIdx.x, ell_w = m.ell_w;
+    const int c0 = __ldg(&r.cta_first[blockIdx.x]), c1 = __ldg(&r.cta_first[blockIdx.x + 1]);
+    const int ncols = c1 - c0;
+    if (tid < 32) {
+        int n = 0, wet = 0;
+        uint2 rec = make_uint2(0u, 0u);
+        if (tid < ncols) {
+            n = r.list ? __ldg(&r.list[c0 + tid]) : c0 + tid;
+            rec = __ldg(&m.node_rec[n]);
+            wet = (int)((rec.x >> 8) & 0xff) - (int)(rec.x & 0xff);            // layers ulev .. nlev-1
+            if (r.skip_s && ((rec.y >> 24) & 1u)) wet = 0;
+        }
+        int incl = wet;
+#pragma unroll
+        for (int d = 1; d < kMaxCols; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (tid >= d) incl += v;
+        }
+        if (tid < ncols) { h->n[tid] = n; h->rec[tid] = rec; h->off[tid] = incl - wet; }
+        if (tid == ncols - 1) h->off[ncols] = incl;
+    }
+    for (int i = tid; i < ncols * ell_w; i += blockDim.x) {
+        const int col = i / ell_w;
+        const int n = r.list ? __ldg(&r.list[c0 + col]) : c0 + col;
+        s_ell[i] = __ldg(&m.ne_ell[(size_t)n * ell_w + (i - col * ell_w)]);
+    }
+    __syncthreads();
+    int g = 0;
+    for (int j = 1; j < ncols; ++j) g += (tid >= h->off[j]) ? 1 : 0;
+    NodeCta t;
+    const uint2 rec = h->rec[g];
+    t.n = h->n[g];
+    t.base = h->off[g];
+    t.nzmin = rec.x & 0xff; t.nzmax = (rec.x >> 8) & 0xff;
+    t.pad_lo = (rec.x >> 16) & 0xff; t.pad_hi = rec.x >> 24;
+    t.self_lo = rec.y & 0xff; t.self_hi = (rec.y >> 8) & 0xff; t.deg = (rec.y >> 16) & 0xff;
+    t.nz = t.nzmin + (tid - t.base);
+    t.valid = tid < h->off[ncols] && t.nz <= t.nzmax - 1;
+    if (!t.valid) t.deg = 0;
+    t.ell = s_ell + g * ell_w;
+    return t;
 }
 
 // an empty gather slot: lo = 255 > hi = 0, never in range (nl <= 255)
@@ -692,24 +780,29 @@ template <int VER, int TB>
 __host__ __device__ constexpr int n1_smem_arrays() { return 3 * TB + 5 + (VER == VER_PPM ? 2 : 0) + (VER == VER_QR4C && ADV_QR4C_RCP ? 1 : 0); }
 
 template <int VER, int TB, int G>
-__global__ void ADV_N1_BOUNDS k_node_lo(MeshDev m, Chunk<TB> b, NodeRange r, double dt)
+__global__ void ADV_N1_BOUNDS k_node_lo(MeshDev m, Chunk<TB> b, NodePart r, double dt)
 {
-    extern __shared__ double sm[];      // n1_smem_arrays() arrays of [nthr]; element g*L+nz0 == threadIdx.x
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // after the header: n1_smem_arrays() arrays of [nthr] doubles; element index == threadIdx.x (compact wet layers)
+    double* sm = reinterpret_cast<double*>(smem_raw + node_smem_header(m.ell_w));
     const int L = m.L, nl = m.nl, nthr = blockDim.x, tid = threadIdx.x;
-    const NodeThread th = node_thread(m, r);
-    if (ADV_PF_OWN & 1) {
-        PfArr pa[2 * TB + 8];
-#pragma unroll
-        for (int t = 0; t < TB; ++t) { pa[2 * t] = PfArr{b.ttf[t], (unsigned)L * 8u}; pa[2 * t + 1] = PfArr{b.ttfAB[t], (unsigned)L * 8u}; }
-        pa[2 * TB + 0] = PfArr{m.hnode, (unsigned)L * 8u}; pa[2 * TB + 1] = PfArr{m.hnode_new, (unsigned)L * 8u};
-        pa[2 * TB + 2] = PfArr{m.Z3d, (unsigned)L * 8u}; pa[2 * TB + 3] = PfArr{m.zbar3d, (unsigned)nl * 8u};
-        pa[2 * TB + 4] = PfArr{m.w, (unsigned)nl * 8u}; pa[2 * TB + 5] = PfArr{m.we, (unsigned)nl * 8u};
-        pa[2 * TB + 6] = PfArr{m.area, (unsigned)nl * 8u}; pa[2 * TB + 7] = PfArr{m.areasvol, (unsigned)nl * 8u};
-        prefetch_own_columns(r, pa);
-    }
-    const int n = th.n, nz0 = th.nz0, nz = nz0 + 1, nzmin = th.nzmin, nzmax = th.nzmax;
-    const bool active = th.active;
-    const bool valid = active && nz >= nzmin && nz <= nzmax - 1;
+    node_cta_prefetch<2 * TB + 8>(m, r, [&](int q) {
+        const unsigned cl = (unsigned)L * 8u, cn = (unsigned)nl * 8u;
+        if (q < 2 * TB) return PfArr{(q & 1) ? b.ttfAB[q >> 1] : b.ttf[q >> 1], cl, 8u, 0};
+        switch (q - 2 * TB) {
+        case 0: return PfArr{m.hnode, cl, 8u, 0};
+        case 1: return PfArr{m.hnode_new, cl, 8u, 0};
+        case 2: return PfArr{m.Z3d, cl, 8u, 0};
+        case 3: return PfArr{m.zbar3d, cn, 8u, 1};
+        case 4: return PfArr{m.w, cn, 8u, 1};
+        case 5: return PfArr{m.we, cn, 8u, 1};
+        case 6: return PfArr{m.area, cn, 8u, 1};
+        default: return PfArr{m.areasvol, cn, 8u, 1};
+        }
+    }, (ADV_PF_OWN & 1) != 0);
+    const NodeCta th = node_cta(m, r, smem_raw);
+    const int n = th.n, nz = th.nz, nz0 = nz - 1, nzmin = th.nzmin, nzmax = th.nzmax;
+    const bool valid = th.valid;
     const unsigned oL = (unsigned)n * L + nz0;
     const size_t cN = (size_t)n * nl;
     double* s_flo = sm;                               // [TB][nthr] LO vertical flux at the top interface
@@ -730,9 +823,8 @@ __global__ void ADV_N1_BOUNDS k_node_lo(MeshDev m, Chunk<TB> b, NodeRange r, dou
     bool in[G];
     double tn[TB], tab[TB];
     double av = 1.0, hn = 0.0, hnn = 1.0, zz = 0.0, zb = 0.0, ww = 0.0, wwe = 0.0, ar = 0.0;
-    const int4* ell = m.ne_ell + (size_t)n * m.ell_w;
 #pragma unroll
-    for (int j = 0; j < G; ++j) ent[j] = (valid && j < th.deg) ? __ldg(&ell[j]) : ADV_EMPTY_SLOT;
+    for (int j = 0; j < G; ++j) ent[j] = (j < th.deg) ? th.ell[j] : ADV_EMPTY_SLOT;
 #pragma unroll
     for (int t = 0; t < TB; ++t) { tn[t] = 0.0; tab[t] = 0.0; }
     if (valid) {
@@ -788,7 +880,7 @@ __global__ void ADV_N1_BOUNDS k_node_lo(MeshDev m, Chunk<TB> b, NodeRange r, dou
             if (j0 >= th.deg) break;
             // further batches (degree > G)
 #pragma unroll
-            for (int j = 0; j < G; ++j) ent[j] = (j0 + j < th.deg) ? __ldg(&ell[j0 + j]) : ADV_EMPTY_SLOT;
+            for (int j = 0; j < G; ++j) ent[j] = (j0 + j < th.deg) ? th.ell[j0 + j] : ADV_EMPTY_SLOT;
 #pragma unroll
             for (int j = 0; j < G; ++j) {
                 const int lo = ent[j].z & 0xff, hi = (ent[j].z >> 8) & 0xff;
@@ -804,11 +896,12 @@ __global__ void ADV_N1_BOUNDS k_node_lo(MeshDev m, Chunk<TB> b, NodeRange r, dou
     }
 
     // ---- vertical fluxes at the thread's top interface, stencils read from shared memory --------
+    // (the bottom interface nzmax always carries +0.0: every scheme writes 0 - 0 there)
     double flo_top[TB], adfv_top[TB];
 #pragma unroll
     for (int t = 0; t < TB; ++t) { flo_top[t] = 0.0; adfv_top[t] = 0.0; }
-    if (active && nz >= nzmin && nz <= nzmax) {
-        const int c0 = tid - nz0;                 // first element of this thread's column
+    if (valid) {
+        const int c0 = th.base - (nzmin - 1);         // shared-memory index of (level 1) of this thread's column
         ColV c;
         c.area = s_area + c0; c.Z = s_Z + c0; c.zbar = s_zbar + c0;
         c.hnode = s_hn + c0; c.hnode_new = s_hnn + c0;
@@ -828,17 +921,15 @@ __global__ void ADV_N1_BOUNDS k_node_lo(MeshDev m, Chunk<TB> b, NodeRange r, dou
 #pragma unroll
     for (int t = 0; t < TB; ++t) s_flo[t * nthr + tid] = flo_top[t];
     __syncthreads();
-    if (active) {
-        stv<TB>(b.adf_v + (cN + nz0) * TB, adfv_top);
-        if (nz0 == L - 1) {                                  // interface nl is always the (zero) bottom
-            double z[TB];
-#pragma unroll
-            for (int t = 0; t < TB; ++t) z[t] = 0.0;
-            stv<TB>(b.adf_v + (cN + L) * TB, z);
-        }
-    }
     if (!valid) return;
-    const bool has_below = nz0 + 1 < L;
+    stv<TB>(b.adf_v + (cN + nz0) * TB, adfv_top);
+    const bool has_below = nz + 1 <= nzmax - 1;              // the next thread is the layer below of the same column
+    if (!has_below) {                                        // interface nzmax: the (zero) bottom
+        double z[TB];
+#pragma unroll
+        for (int t = 0; t < TB; ++t) z[t] = 0.0;
+        stv<TB>(b.adf_v + (cN + nz0 + 1) * TB, z);
+    }
     const double r_av = 1.0 / av, r_hnn = 1.0 / hnn;
     double lo_out[TB];
 #pragma unroll
@@ -928,32 +1019,33 @@ __global__ void __launch_bounds__(128) k_vert_impl(MeshDev m, double* __restrict
 // Output: pm = {R+, R-} per tracer.
 // ----------------------------------------------------------------------------------------------
 template <int TB, int G>
-__global__ void ADV_K2_BOUNDS k_fct_bounds(MeshDev m, Chunk<TB> b, NodeRange r, double dt)
+__global__ void ADV_K2_BOUNDS k_fct_bounds(MeshDev m, Chunk<TB> b, NodePart r, double dt)
 {
-    extern __shared__ double sm[];  // [2*TB][blockDim]: tvert_max, tvert_min
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sm = reinterpret_cast<double*>(smem_raw + node_smem_header(m.ell_w));   // [2*TB][blockDim]: tvert_max, tvert_min
     const int L = m.L, nl = m.nl;
-    const NodeThread th = node_thread(m, r);
-    if (ADV_PF_OWN & 2) {
-        PfArr pa[TB + 4];
-#pragma unroll
-        for (int t = 0; t < TB; ++t) pa[t] = PfArr{b.ttf[t], (unsigned)L * 8u};
-        pa[TB + 0] = PfArr{b.lo, (unsigned)L * TB * 8u}; pa[TB + 1] = PfArr{b.adf_v, (unsigned)nl * TB * 8u};
-        pa[TB + 2] = PfArr{m.areasvol, (unsigned)nl * 8u}; pa[TB + 3] = PfArr{m.hnode_new, (unsigned)L * 8u};
-        prefetch_own_columns(r, pa);
-    }
-    const int n = th.n, nz0 = th.nz0, nz = nz0 + 1;
-    const bool valid = th.active && nz >= th.nzmin && nz <= th.nzmax - 1;
+    node_cta_prefetch<TB + 4>(m, r, [&](int q) {
+        if (q < TB) return PfArr{b.ttf[q], (unsigned)L * 8u, 8u, 0};
+        switch (q - TB) {
+        case 0: return PfArr{b.lo, (unsigned)L * TB * 8u, TB * 8u, 0};
+        case 1: return PfArr{b.adf_v, (unsigned)nl * TB * 8u, TB * 8u, 1};
+        case 2: return PfArr{m.areasvol, (unsigned)nl * 8u, 8u, 1};
+        default: return PfArr{m.hnode_new, (unsigned)L * 8u, 8u, 0};
+        }
+    }, (ADV_PF_OWN & 2) != 0);
+    const NodeCta th = node_cta(m, r, smem_raw);
+    const int n = th.n, nz = th.nz, nz0 = nz - 1;
+    const bool valid = th.valid;
     const unsigned oL = (unsigned)n * L + nz0;
     double tmax[TB], tmin[TB], pp[TB], pn[TB], lo_n[TB];
     double av = 1.0, hnn = 1.0;
     if (valid) {
         // ---- all global loads of the first batch + the own column ------------------------------
-        const int4* ell = m.ne_ell + (size_t)n * m.ell_w;
         int4 ent[G];
         double lo_o[G][TB], t_o[G][TB], f[G][TB];
         bool in[G];
 #pragma unroll
-        for (int j = 0; j < G; ++j) ent[j] = (j < th.deg) ? __ldg(&ell[j]) : ADV_EMPTY_SLOT;
+        for (int j = 0; j < G; ++j) ent[j] = (j < th.deg) ? th.ell[j] : ADV_EMPTY_SLOT;
         const size_t cN = (size_t)n * nl + nz0;
         double tn[TB], vt[TB], vb[TB];
         ldv<TB>(b.lo + (size_t)oL * TB, lo_n);
@@ -1006,7 +1098,7 @@ __global__ void ADV_K2_BOUNDS k_fct_bounds(MeshDev m, Chunk<TB> b, NodeRange r, 
             j0 += G;
             if (j0 >= th.deg) break;
 #pragma unroll
-            for (int j = 0; j < G; ++j) ent[j] = (j0 + j < th.deg) ? __ldg(&ell[j0 + j]) : ADV_EMPTY_SLOT;
+            for (int j = 0; j < G; ++j) ent[j] = (j0 + j < th.deg) ? th.ell[j0 + j] : ADV_EMPTY_SLOT;
 #pragma unroll
             for (int j = 0; j < G; ++j) {
                 const int lo = ent[j].z & 0xff, hi = (ent[j].z >> 8) & 0xff;
@@ -1034,7 +1126,7 @@ __global__ void ADV_K2_BOUNDS k_fct_bounds(MeshDev m, Chunk<TB> b, NodeRange r, 
 #pragma unroll
     for (int t = 0; t < TB; ++t) {
         double vmax = tmax[t], vmin = tmin[t];
-        if (!edge_layer) {                                               // :238-241
+        if (!edge_layer) {                                               // :238-241 (layers nz-1, nz+1 = the threads before / after)
             const double* smax = sm + (2 * t) * blockDim.x + threadIdx.x;
             const double* smin = sm + (2 * t + 1) * blockDim.x + threadIdx.x;
             vmax = dmax(dmax(smax[-1], vmax), smax[1]);
@@ -1068,35 +1160,37 @@ __device__ __forceinline__ double limit_v(double f, int k, int nzmin, int nzmax,
 //   reference: oce_adv_tra_fct.F90:425-500 (b3), oce_adv_tra_driver.F90:529-633 (U1-U3)
 // ----------------------------------------------------------------------------------------------
 template <int TB, int G>
-__global__ void ADV_K3_BOUNDS k_fct_update(MeshDev m, Chunk<TB> b, NodeRange r, double dt)
+__global__ void ADV_K3_BOUNDS k_fct_update(MeshDev m, Chunk<TB> b, NodePart r, double dt)
 {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int L = m.L, nl = m.nl;
-    const NodeThread th = node_thread(m, r);
-    if (ADV_PF_OWN & 4) {
-        PfArr pa[3 * TB + 6];
-#pragma unroll
-        for (int t = 0; t < TB; ++t) {
-            pa[3 * t] = PfArr{b.dttf_h[t], (unsigned)L * 8u}; pa[3 * t + 1] = PfArr{b.dttf_v[t], (unsigned)L * 8u};
-            pa[3 * t + 2] = PfArr{b.ttf[t], (unsigned)L * 8u};
+    node_cta_prefetch<3 * TB + 6>(m, r, [&](int q) {
+        const unsigned cl = (unsigned)L * 8u;
+        if (q < 3 * TB) {
+            const int t = q / 3, w = q - 3 * t;
+            return PfArr{w == 0 ? (const void*)b.dttf_h[t] : w == 1 ? (const void*)b.dttf_v[t] : (const void*)b.ttf[t], cl, 8u, 0};
         }
-        pa[3 * TB + 0] = PfArr{b.pm, (unsigned)L * TB * 16u}; pa[3 * TB + 1] = PfArr{b.adf_v, (unsigned)nl * TB * 8u};
-        pa[3 * TB + 2] = PfArr{b.lo, (unsigned)L * TB * 8u}; pa[3 * TB + 3] = PfArr{m.areasvol, (unsigned)nl * 8u};
-        pa[3 * TB + 4] = PfArr{m.hnode, (unsigned)L * 8u}; pa[3 * TB + 5] = PfArr{m.hnode_new, (unsigned)L * 8u};
-        prefetch_own_columns(r, pa);
-    }
-    const int n = th.n, nz0 = th.nz0, nz = nz0 + 1;
-    const bool valid = th.active && nz >= th.nzmin && nz <= th.nzmax - 1;
-    if (!valid) return;
+        switch (q - 3 * TB) {
+        case 0: return PfArr{b.pm, (unsigned)L * TB * 16u, TB * 16u, 0};
+        case 1: return PfArr{b.adf_v, (unsigned)nl * TB * 8u, TB * 8u, 1};
+        case 2: return PfArr{b.lo, (unsigned)L * TB * 8u, TB * 8u, 0};
+        case 3: return PfArr{m.areasvol, (unsigned)nl * 8u, 8u, 1};
+        case 4: return PfArr{m.hnode, cl, 8u, 0};
+        default: return PfArr{m.hnode_new, cl, 8u, 0};
+        }
+    }, (ADV_PF_OWN & 4) != 0);
+    const NodeCta th = node_cta(m, r, smem_raw);
+    const int n = th.n, nz = th.nz, nz0 = nz - 1;
+    if (!th.valid) return;
     const bool owned = n < m.N;
     const unsigned oL = (unsigned)n * L + nz0;
     const size_t cN = (size_t)n * nl + nz0;
     // ---- gather metadata first (its latency hides behind the vertical part) ----------------------
-    const int4* ell = m.ne_ell + (size_t)n * m.ell_w;
     int4 ent[G];
     double f[G][TB], po[G][TB], mo[G][TB];
     bool in[G];
 #pragma unroll
-    for (int j = 0; j < G; ++j) ent[j] = (j < th.deg) ? __ldg(&ell[j]) : ADV_EMPTY_SLOT;
+    for (int j = 0; j < G; ++j) ent[j] = (j < th.deg) ? th.ell[j] : ADV_EMPTY_SLOT;
     const double av = __ldg(&m.areasvol[cN]);
     double pk[TB], mk[TB], dh[TB];
     ldpm<TB>(b.pm + (size_t)oL * TB * 2, pk, mk);
@@ -1167,7 +1261,7 @@ __global__ void ADV_K3_BOUNDS k_fct_update(MeshDev m, Chunk<TB> b, NodeRange r, 
         j0 += G;
         if (j0 >= th.deg) break;
 #pragma unroll
-        for (int j = 0; j < G; ++j) ent[j] = (j0 + j < th.deg) ? __ldg(&ell[j0 + j]) : ADV_EMPTY_SLOT;
+        for (int j = 0; j < G; ++j) ent[j] = (j0 + j < th.deg) ? th.ell[j0 + j] : ADV_EMPTY_SLOT;
 #pragma unroll
         for (int j = 0; j < G; ++j) {
             const int lo = ent[j].z & 0xff, hi = (ent[j].z >> 8) & 0xff;

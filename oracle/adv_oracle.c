@@ -878,3 +878,60 @@ void ora_vert_vel_ale_core(const ora_mesh_t *m, const double *UV, double *Wvel)
 #undef V_HE
 #undef V_W
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * find_up_downwind_triangles (src/oce_muscl_adv.F90:162-352), single rank (coord_elem / e_nodes are then
+ * plain gathers of coord_nod2D / elem2D_nodes; the exchange_elem calls of :192-216 only fill halo
+ * elements).  Loop for loop: per edge, the elements around edges(1,e) are tested against -x, those around
+ * edges(2,e) against +x; every element that passes one of the three tests overwrites the previous hit
+ * (`cycle` only skips the remaining tests), so the LAST passing element wins.  Second, independent
+ * restatement of what fesom2_b200/fields.py::find_up_downwind_triangles computes whole-array.
+ * ---------------------------------------------------------------------------------------------- */
+void ora_find_up_downwind_triangles(int myDim_edge2D, const int *edges, const int *elem2D_nodes,
+                                    const int *nod_in_elem2D, int ld, const int *nod_in_elem2D_num,
+                                    const double *coord_nod2D /* (2,N) radians */, double cyclic_length,
+                                    int *edge_up_dn_tri /* (2,E) */)
+{
+    for (int n = 1; n <= myDim_edge2D; ++n) {
+        edge_up_dn_tri[2 * (n - 1)] = 0;
+        edge_up_dn_tri[2 * (n - 1) + 1] = 0;
+        const int ednodes[2] = {edges[2 * (n - 1)], edges[2 * (n - 1) + 1]};
+        double x[2];
+        x[0] = coord_nod2D[2 * (ednodes[1] - 1)] - coord_nod2D[2 * (ednodes[0] - 1)];
+        x[1] = coord_nod2D[2 * (ednodes[1] - 1) + 1] - coord_nod2D[2 * (ednodes[0] - 1) + 1];
+        if (x[0] > cyclic_length / 2.0) x[0] = x[0] - cyclic_length;                 /* :222-223 */
+        if (x[0] < -cyclic_length / 2.0) x[0] = x[0] + cyclic_length;
+        for (int side = 0; side < 2; ++side) {
+            x[0] = -x[0]; x[1] = -x[1];                                              /* :224 and :277 */
+            const int node = ednodes[side];
+            for (int k = 1; k <= nod_in_elem2D_num[node - 1]; ++k) {
+                const int elem = nod_in_elem2D[(size_t)(node - 1) * ld + (k - 1)];
+                const int *en = elem2D_nodes + 3 * (size_t)(elem - 1);
+                int i0, ib, ic;                                                      /* :229-241 */
+                if (en[0] == node) { i0 = 0; ib = 1; ic = 2; }
+                else if (en[1] == node) { i0 = 1; ib = 0; ic = 2; }
+                else { i0 = 2; ib = 0; ic = 1; }
+                double b[2], c[2];
+                for (int d = 0; d < 2; ++d) {
+                    b[d] = coord_nod2D[2 * (size_t)(en[ib] - 1) + d] - coord_nod2D[2 * (size_t)(en[i0] - 1) + d];
+                    c[d] = coord_nod2D[2 * (size_t)(en[ic] - 1) + d] - coord_nod2D[2 * (size_t)(en[i0] - 1) + d];
+                }
+                if (b[0] > cyclic_length / 2.0) b[0] = b[0] - cyclic_length;         /* :242-245 */
+                if (b[0] < -cyclic_length / 2.0) b[0] = b[0] + cyclic_length;
+                if (c[0] > cyclic_length / 2.0) c[0] = c[0] - cyclic_length;
+                if (c[0] < -cyclic_length / 2.0) c[0] = c[0] + cyclic_length;
+                const double cr = c[0] * c[0] + c[1] * c[1];                         /* :247-253 */
+                const double bx = (b[0] * c[0] + b[1] * c[1]) / cr;
+                const double by = (-b[0] * c[1] + b[1] * c[0]) / cr;
+                const double xx = (x[0] * c[0] + x[1] * c[1]) / cr;
+                const double xy = (-x[0] * c[1] + x[1] * c[0]) / cr;
+                const double ab = atan2(by, bx), ax = atan2(xy, xx);
+                int hit = 0;
+                if (ab > 0.0 && ax > 0.0 && ax < ab) hit = 1;                        /* :255-258 */
+                else if (ab < 0.0 && ax < 0.0 && ax > ab) hit = 1;                   /* :260-263 */
+                else if (ab == ax || ax == 0.0) hit = 1;                             /* :265-268 */
+                if (hit) edge_up_dn_tri[2 * (n - 1) + side] = elem;
+            }
+        }
+    }
+}

@@ -112,6 +112,13 @@ void ora_fill_up_dn_grad(int nl, int myDim_edge2D, const int *edges, const int *
                          const int *nlevels_nod2D_min, const int *ulevels_nod2D_max,
                          const double *elem_area, const double *tr_xy, double *edge_up_dn_grad /* (4,nl-1,E) */);
 
+/* find_up_downwind_triangles (src/oce_muscl_adv.F90:162-352), single rank: edge_up_dn_tri(1:2,edge), 0 = none;
+ * the last element around the end node whose sector contains the (reversed) edge direction wins. */
+void ora_find_up_downwind_triangles(int myDim_edge2D, const int *edges, const int *elem2D_nodes,
+                                    const int *nod_in_elem2D, int ld, const int *nod_in_elem2D_num,
+                                    const double *coord_nod2D /* (2,N) */, double cyclic_length,
+                                    int *edge_up_dn_tri /* (2,E) */);
+
 /* ---- SURVEY.md section 8f row 3, oracle first: the continuity part of vert_vel_ale
  * (src/oce_ale.F90:2164-2310, linfs, no Fer_GM): edge transports scattered to the two end nodes in edge
  * order (element 1 then element 2 of each edge), bottom-up cumulative sum over the node column, division

@@ -230,6 +230,22 @@ def fill_up_dn_grad(mesh, tr_xy: np.ndarray, edge_up_dn_tri: np.ndarray, out: Op
     return out
 
 
+def find_up_downwind_triangles(mesh) -> np.ndarray:
+    """ora_find_up_downwind_triangles on a single-rank mesh: edge_up_dn_tri (E, 2), 1-based, 0 = none."""
+    L_ = lib()
+    L_.ora_find_up_downwind_triangles.argtypes = [C.c_int, c_ip, c_ip, c_ip, C.c_int, c_ip, c_dp, C.c_double, c_ip]
+    L_.ora_find_up_downwind_triangles.restype = None
+    ed, edp = _ipk(mesh.edges)
+    en, enp = _ipk(mesh.elem2D_nodes)
+    nie, niep = _ipk(mesh.nod_in_elem2D)
+    num, nump = _ipk(mesh.nod_in_elem2D_num)
+    co = np.ascontiguousarray(mesh.coord_nod2D, dtype=np.float64)
+    out = np.zeros((mesh.E, 2), np.int32)
+    L_.ora_find_up_downwind_triangles(mesh.E, edp, enp, niep, nie.shape[1], nump, co.ctypes.data_as(c_dp),
+                                      float(mesh.cyclic_length), out.ctypes.data_as(c_ip))
+    return out
+
+
 def vert_vel_ale_core(rank: "OracleRank") -> np.ndarray:
     """ora_vert_vel_ale_core on a rank's mesh and uv: Wvel (Nh, nl), completed on the owned nodes."""
     L_ = lib()

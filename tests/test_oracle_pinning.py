@@ -182,3 +182,30 @@ def test_vert_vel_ale_core_restatements_agree(pi_mesh):
     assert np.isfinite(a).all() and np.array_equal(a, b)
     w = st.w.numpy()
     assert np.abs(a - w).max() <= 1e-12 * np.abs(w).max()
+
+
+@pytest.mark.parametrize("which", ["pi", "souf", "small"])
+def test_find_up_downwind_triangles_two_restatements(pi_mesh, souf_mesh, small_mesh, which):
+    """find_up_downwind_triangles (src/oce_muscl_adv.F90:162-352): the whole-array NumPy version that feeds the
+    harness (fesom2_b200/fields.py) against the loop-for-loop C restatement (oracle/adv_oracle.c, libm atan2 as
+    in a gfortran build).  On the reference's unstructured pi mesh they agree exactly.  On structured meshes the
+    edge direction can lie EXACTLY on an element edge around the far node; the reference's test `ab == ax` then
+    depends on the last bit of atan2, and the two restatements may pick different -- adjacent -- triangles: every
+    disagreement must be such a tie (both candidates contain the end node and share the edge the direction lies on)."""
+    from oracle import oracle_py as O
+    mesh = {"pi": pi_mesh, "souf": souf_mesh, "small": small_mesh}[which]
+    a = F.find_up_downwind_triangles(mesh)
+    b = O.find_up_downwind_triangles(mesh)
+    assert a.shape == b.shape == (mesh.E, 2)
+    bad = np.argwhere(a != b)
+    if which == "pi":
+        assert bad.size == 0
+    en = mesh.elem2D_nodes.astype(np.int64)
+    for e, side in bad:
+        ea, eb = int(a[e, side]), int(b[e, side])
+        assert ea > 0 and eb > 0, (e, side, ea, eb)
+        node = int(mesh.edges[e, side])
+        na, nb_ = set(en[ea - 1].tolist()), set(en[eb - 1].tolist())
+        assert node in na and node in nb_
+        assert len(na & nb_) == 2, "candidates are not adjacent triangles"
+    assert bad.shape[0] <= 0.02 * mesh.E
