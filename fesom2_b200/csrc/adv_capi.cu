@@ -10,9 +10,12 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -113,6 +116,37 @@ struct TrLoc { int chunk = -1, pos = 0, tb = 1; };  // where tracer i of the las
 
 struct Peer { int pe; int off, cnt; };  // segment of slist / halo tail, in columns
 
+// one com_struct (src/MOD_PARTIT.F90:18-33) on the device: com_nod2D or com_elem2D_full
+struct HaloSet {
+    DevBuf<int> slist, rlist;                 // 0-based local ids; rlist only when the receive side needs an unpack
+    std::vector<Peer> rpeers, speers;
+    int send_cols = 0, recv_cols = 0;
+    int recv_base = -1;                       // >= 0: the received columns are the contiguous tail starting here (no unpack)
+};
+enum { HALO_NOD = 0, HALO_ELEM = 1 };
+
+// In-process communicator (adv_ctx_comm_init_local): the contexts of one process exchange halos with direct
+// device-to-device copies -- peer copies over NVLink between GPUs, plain copies on one GPU -- ordered by CUDA
+// events; two host rendezvous per exchange make the events visible to the peers.
+struct LocalComm {
+    int n = 0;
+    std::vector<adv_ctx*> ctx;
+    std::mutex mu;
+    std::condition_variable cv;
+    int waiting = 0;
+    unsigned gen = 0;
+    bool broken = false;
+    bool barrier()
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        if (broken) return false;
+        const unsigned g = gen;
+        if (++waiting == n) { waiting = 0; ++gen; cv.notify_all(); return true; }
+        if (!cv.wait_for(lk, std::chrono::seconds(120), [&] { return gen != g || broken; })) { broken = true; cv.notify_all(); return false; }
+        return !broken;
+    }
+};
+
 }  // namespace
 
 struct adv_ctx {
@@ -121,7 +155,8 @@ struct adv_ctx {
     MeshDev m{};
     int mype = 0, npes = 1;
     // topology
-    DevBuf<int> ne_ptr, nboundary_lay, list_S, list_I, list_SH, slist;
+    DevBuf<int> ne_ptr, nboundary_lay, list_S, list_I, list_SH;
+    HaloSet halo[2];                          // HALO_NOD: com_nod2D, HALO_ELEM: com_elem2D_full (adv_ctx_set_gradient_mesh)
     DevBuf<int4> ne_ent;
     DevBuf<int2> edge_el;
     DevBuf<int4> edge_meta;
@@ -135,7 +170,7 @@ struct adv_ctx {
     DevBuf<int> g_nie, g_nie_num, g_nlevels, g_ulevels, g_tri, g_nmin, g_umax, g_elem_nodes;
     DevBuf<double> g_sca, g_earea;
     GradMeshDev gm{};
-    bool grad_mesh_set = false;
+    bool grad_mesh_set = false, elem_halo_set = false;
     int nS = 0, nI = 0, nSH = 0;
     int pf_dist = 200;                        // L2 prefetch distance of the node kernels in CTAs (ADV_PF; 0 = off)
     int g_lo = 3, g_k2 = 2, g_k3 = 2;         // gather batch sizes (tunable: ADV_G_LO / ADV_G_K2 / ADV_G_K3)
@@ -149,8 +184,6 @@ struct adv_ctx {
     struct Part { DevBuf<int> first; int ncta = 0; };
     Part part_all, part_i, part_s, part_sh;
     int max_smem_optin = 0;
-    std::vector<Peer> rpeers, speers;
-    int send_cols = 0;
     // state (ADV_HOST staging)
     DevBuf<double> uv, helem, w, we, wi, hnode, hnode_new, zbar3d, Z3d, zbar_n_bot;
     bool state_set = false, q_valid = false;
@@ -158,7 +191,15 @@ struct adv_ctx {
     std::vector<Slot> slots;
     std::vector<std::unique_ptr<ChunkBuf>> cbufs;
     std::vector<TrLoc> trloc;
-    DevBuf<double> xbuf;  // adv_exchange_nod pack buffer
+    DevBuf<double> xbuf, xrbuf;  // adv_exchange_nod / adv_exchange_elem pack and unpack buffers
+    // in-process communicator
+    std::shared_ptr<LocalComm> lc;
+    cudaEvent_t ev_packed = nullptr, ev_consumed = nullptr, ev_order = nullptr;
+    std::vector<const double*> pub_send;      // send buffers of the exchange in progress, read by the peers
+    // halo-exchange accounting (adv_ctx_halo_stats)
+    int64_t halo_bytes_sent = 0, halo_exchanges = 0, halo_bytes_last = 0;
+    cudaEvent_t ev_x0[2] = {nullptr, nullptr}, ev_x1[2] = {nullptr, nullptr}, ev_w0[2] = {nullptr, nullptr}, ev_w1[2] = {nullptr, nullptr};
+    bool x_valid = false;
     cudaStream_t s_comp = nullptr, s_comm = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     cudaEvent_t ev_ph[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -341,25 +382,28 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
 
     // ---- halo bookkeeping (com_nod2D) ------------------------------------------------------------
     if (c->npes > 1) {
+        HaloSet& hn = c->halo[HALO_NOD];
         std::vector<char> isS(N, 0);
         std::vector<int> sl;
         for (int i = 0; i < d->sPEnum; ++i) {
             Peer p{d->sPE[i], d->sptr[i] - 1, d->sptr[i + 1] - d->sptr[i]};
-            c->speers.push_back(p);
+            hn.speers.push_back(p);
             for (int k = 0; k < p.cnt; ++k) {
                 const int n = d->slist[p.off + k] - 1;
                 if (n < 0 || n >= N) { delete c; return fail(ADV_EINVAL, "slist entry is not an owned node"); }
                 isS[n] = 1; sl.push_back(n);
             }
         }
-        c->send_cols = (int)sl.size();
+        hn.send_cols = (int)sl.size();
         for (int i = 0; i < d->rPEnum; ++i) {
             Peer p{d->rPE[i], d->rptr[i] - 1, d->rptr[i + 1] - d->rptr[i]};
             // the halo tail must be contiguous per source rank: rlist(k) = myDim_nod2D + k (oce_local.F90:41)
             for (int k = 0; k < p.cnt; ++k)
                 if (d->rlist[p.off + k] != N + p.off + k + 1) { delete c; return fail(ADV_EINVAL, "rlist is not the identity on the halo tail"); }
-            c->rpeers.push_back(p);
+            hn.rpeers.push_back(p);
+            hn.recv_cols += p.cnt;
         }
+        hn.recv_base = N;
         // a node also belongs to the boundary set when one of its edge neighbours is a halo node
         for (int e = 0; e < E; ++e) {
             const int n1 = d->edges[2 * e] - 1, n2 = d->edges[2 * e + 1] - 1;
@@ -373,7 +417,7 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
         SH = S;
         for (int n = N; n < Nh; ++n) SH.push_back(n);
         c->nS = (int)S.size(); c->nI = (int)I.size(); c->nSH = (int)SH.size();
-        CUF(c->list_S.upload(S)); CUF(c->list_I.upload(I)); CUF(c->list_SH.upload(SH)); CUF(c->slist.upload(sl));
+        CUF(c->list_S.upload(S)); CUF(c->list_I.upload(I)); CUF(c->list_SH.upload(SH)); CUF(hn.slist.upload(sl));
     }
     // ---- wet-level compaction: pack whole columns into CTAs of cta_threads threads (one thread per wet layer) -----
     {
@@ -408,6 +452,8 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
     for (cudaEvent_t* ev : {&c->ev_a, &c->ev_b, &c->ev_c, &c->ev_d}) CUF(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
     CUF(cudaEventCreate(&c->ev_t0)); CUF(cudaEventCreate(&c->ev_t1));
     for (auto& ev : c->ev_ph) CUF(cudaEventCreate(&ev));
+    CUF(cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming)); CUF(cudaEventCreateWithFlags(&c->ev_consumed, cudaEventDisableTiming)); CUF(cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) { CUF(cudaEventCreate(&c->ev_x0[i])); CUF(cudaEventCreate(&c->ev_x1[i])); CUF(cudaEventCreate(&c->ev_w0[i])); CUF(cudaEventCreate(&c->ev_w1[i])); }
 #undef CUF
     MeshDev& m = c->m;
     m.L = L; m.nl = nl; m.N = N; m.Nh = Nh; m.T = T; m.E = E;
@@ -431,6 +477,13 @@ int adv_ctx_destroy(adv_ctx_t* c)
     if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
     for (cudaEvent_t ev : {c->ev_a, c->ev_b, c->ev_c, c->ev_d, c->ev_t0, c->ev_t1}) if (ev) cudaEventDestroy(ev);
     for (auto ev : c->ev_ph) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : {c->ev_packed, c->ev_consumed, c->ev_order, c->ev_x0[0], c->ev_x0[1], c->ev_x1[0], c->ev_x1[1], c->ev_w0[0], c->ev_w0[1], c->ev_w1[0], c->ev_w1[1]})
+        if (ev) cudaEventDestroy(ev);
+    if (c->lc) {   // a communicator with a destroyed member can no longer rendezvous
+        std::lock_guard<std::mutex> lk(c->lc->mu);
+        c->lc->broken = true;
+        c->lc->cv.notify_all();
+    }
     if (c->s_comp) cudaStreamDestroy(c->s_comp);
     if (c->s_comm) cudaStreamDestroy(c->s_comm);
     delete c;
@@ -456,6 +509,39 @@ int adv_ctx_comm_init(adv_ctx_t* c, const char id[128])
     ncclUniqueId u;
     memcpy(&u, id, 128);
     NC(g_nccl.CommInitRank(&c->comm, c->npes, u, c->mype));
+    return ADV_OK;
+}
+
+int adv_ctx_comm_init_local(adv_ctx_t* const* ctxs, int n)
+{
+    if (!ctxs || n < 1) return fail(ADV_EINVAL, "adv_ctx_comm_init_local: bad argument");
+    for (int r = 0; r < n; ++r) {
+        if (!ctxs[r]) return fail(ADV_EINVAL, "adv_ctx_comm_init_local: null context");
+        if (ctxs[r]->npes != n || ctxs[r]->mype != r) return fail(ADV_EINVAL, "adv_ctx_comm_init_local: context " + std::to_string(r) + " was created with mype/npes = " + std::to_string(ctxs[r]->mype) + "/" + std::to_string(ctxs[r]->npes));
+        if (ctxs[r]->comm || ctxs[r]->lc) return fail(ADV_ESTATE, "adv_ctx_comm_init_local: context already has a communicator");
+    }
+    // what r receives from p must be what p sends to r
+    for (int r = 0; r < n; ++r)
+        for (const Peer& p : ctxs[r]->halo[HALO_NOD].rpeers) {
+            bool ok = p.pe >= 0 && p.pe < n;
+            if (ok) { ok = false; for (const Peer& sp : ctxs[p.pe]->halo[HALO_NOD].speers) ok = ok || (sp.pe == r && sp.cnt == p.cnt); }
+            if (!ok) return fail(ADV_EINVAL, "adv_ctx_comm_init_local: com_nod2D of ranks " + std::to_string(r) + " and " + std::to_string(p.pe) + " do not pair up");
+        }
+    auto lc = std::make_shared<LocalComm>();
+    lc->n = n;
+    lc->ctx.assign(ctxs, ctxs + n);
+    for (int r = 0; r < n; ++r) {
+        for (int q = 0; q < n; ++q) {   // peer copies between different GPUs: direct access where the topology allows it
+            if (ctxs[q]->device == ctxs[r]->device) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, ctxs[r]->device, ctxs[q]->device) == cudaSuccess && can) {
+                cudaSetDevice(ctxs[r]->device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[q]->device, 0);
+                if (e != cudaSuccess) cudaGetLastError();   // already enabled
+            }
+        }
+        ctxs[r]->lc = lc;
+    }
     return ADV_OK;
 }
 
@@ -663,25 +749,62 @@ int launch_phase(adv_ctx* c, Phase ph, int hor, int ver, bool q_stored, const Ch
     return ADV_OK;
 }
 
-// one exchange_nod over NCCL for `nf` fields of nlev[f] doubles per column: pack the send columns
-// per field, then one grouped send/recv per (peer, field); receives land directly in the halo tail.
-int halo_exchange(adv_ctx* c, cudaStream_t s, int nf, double* const* fields, double* const* sendbufs, const int* nlev)
+// one exchange_nod / exchange_elem for `nf` fields of nlev[f] doubles per column over the halo set `kind`:
+// pack the send columns per field, move them (NCCL: one grouped send/recv per (peer, field); in-process
+// communicator: one device-to-device copy per (peer, field), pulled by the receiver), unpack where the
+// received columns are not a contiguous tail.  recvbufs may be null when the set has a contiguous tail.
+int halo_exchange(adv_ctx* c, int kind, cudaStream_t s, int nf, double* const* fields, double* const* sendbufs,
+                  double* const* recvbufs, const int* nlev)
 {
-    const int cols = c->send_cols;
+    HaloSet& h = c->halo[kind];
+    const int cols = h.send_cols;
+    const bool direct = h.recv_base >= 0;
+    if (!direct && !recvbufs) return fail(ADV_EINVAL, "internal: halo set needs receive buffers");
     for (int f = 0; f < nf; ++f) {
         if (cols > 0) {
-            k_pack_halo<<<cols, std::min(kBlock, ((nlev[f] + 31) / 32) * 32), 0, s>>>(fields[f], c->slist.p, nlev[f], sendbufs[f]);
+            k_pack_halo<<<cols, std::min(kBlock, ((nlev[f] + 31) / 32) * 32), 0, s>>>(fields[f], h.slist.p, nlev[f], sendbufs[f]);
+            ++c->launches;
+        }
+        c->halo_bytes_sent += (int64_t)cols * nlev[f] * 8;
+    }
+    ++c->halo_exchanges;
+    auto dst_of = [&](int f, const Peer& p) {
+        return direct ? fields[f] + ((size_t)h.recv_base + p.off) * nlev[f] : recvbufs[f] + (size_t)p.off * nlev[f];
+    };
+    if (c->lc) {
+        LocalComm& lc = *c->lc;
+        CU(cudaEventRecord(c->ev_packed, s));
+        c->pub_send.assign(sendbufs, sendbufs + nf);
+        if (!lc.barrier()) return fail(ADV_ESTATE, "in-process communicator: the peers did not reach the exchange (every context needs its own host thread and the same call sequence)");
+        for (const Peer& p : h.rpeers) {
+            adv_ctx* q = lc.ctx[p.pe];
+            CU(cudaStreamWaitEvent(s, q->ev_packed, 0));
+            int off = -1;
+            for (const Peer& sp : q->halo[kind].speers) if (sp.pe == c->mype) { off = sp.off; if (sp.cnt != p.cnt) off = -1; }
+            if (off < 0 || (int)q->pub_send.size() != nf) return fail(ADV_EINVAL, "in-process communicator: send/recv lists of ranks " + std::to_string(c->mype) + " and " + std::to_string(p.pe) + " do not pair up");
+            for (int f = 0; f < nf; ++f)
+                CU(cudaMemcpyAsync(dst_of(f, p), q->pub_send[f] + (size_t)off * nlev[f], (size_t)p.cnt * nlev[f] * 8, cudaMemcpyDefault, s));
+        }
+        CU(cudaEventRecord(c->ev_consumed, s));
+        if (!lc.barrier()) return fail(ADV_ESTATE, "in-process communicator: the peers did not finish the exchange");
+        for (const Peer& p : h.speers) CU(cudaStreamWaitEvent(s, lc.ctx[p.pe]->ev_consumed, 0));   // the send buffer may be packed again
+    } else {
+        NC(g_nccl.GroupStart());
+        for (int f = 0; f < nf; ++f) {
+            for (const Peer& p : h.rpeers)
+                NC(g_nccl.Recv(dst_of(f, p), (size_t)p.cnt * nlev[f], ncclDouble, p.pe, c->comm, s));
+            for (const Peer& p : h.speers)
+                NC(g_nccl.Send(sendbufs[f] + (size_t)p.off * nlev[f], (size_t)p.cnt * nlev[f], ncclDouble, p.pe, c->comm, s));
+        }
+        NC(g_nccl.GroupEnd());
+    }
+    if (!direct && h.recv_cols > 0) {
+        for (int f = 0; f < nf; ++f) {
+            k_unpack_halo<<<h.recv_cols, std::min(kBlock, ((nlev[f] + 31) / 32) * 32), 0, s>>>(recvbufs[f], h.rlist.p, nlev[f], fields[f]);
             ++c->launches;
         }
     }
-    NC(g_nccl.GroupStart());
-    for (int f = 0; f < nf; ++f) {
-        for (const Peer& p : c->rpeers)
-            NC(g_nccl.Recv(fields[f] + ((size_t)c->m.N + p.off) * nlev[f], (size_t)p.cnt * nlev[f], ncclDouble, p.pe, c->comm, s));
-        for (const Peer& p : c->speers)
-            NC(g_nccl.Send(sendbufs[f] + (size_t)p.off * nlev[f], (size_t)p.cnt * nlev[f], ncclDouble, p.pe, c->comm, s));
-    }
-    NC(g_nccl.GroupEnd());
+    CU(cudaGetLastError());
     return ADV_OK;
 }
 
@@ -695,7 +818,7 @@ static int ensure_chunk_bufs(adv_ctx* c, int count)
         ChunkBuf& b = *c->cbufs.back();
         CU(b.lo.alloc((size_t)m.L * m.Nh * 2)); CU(b.pm.alloc((size_t)m.L * m.Nh * 4));
         CU(b.adf_h.alloc((size_t)m.L * m.E * 2)); CU(b.adf_v.alloc((size_t)m.nl * m.N * 2));
-        if (c->npes > 1) CU(b.sendbuf.alloc((size_t)c->send_cols * m.L * 4));
+        if (c->npes > 1) CU(b.sendbuf.alloc((size_t)c->halo[HALO_NOD].send_cols * m.L * 4));
     }
     return ADV_OK;
 }
@@ -743,7 +866,7 @@ static int run_batch(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr
     cudaStream_t sc = c->s_comp, sx = c->s_comm;
     const int cpb = cols_per_block(m.L);
     const bool multi = c->npes > 1;
-    if (multi && !c->comm) return fail(ADV_ESTATE, "npes > 1 but adv_ctx_comm_init was not called");
+    if (multi && !c->comm && !c->lc) return fail(ADV_ESTATE, "npes > 1 but neither adv_ctx_comm_init nor adv_ctx_comm_init_local was called");
     const bool prof = c->profiling && !multi;
     auto mark = [&](int i) { if (prof) cudaEventRecord(c->ev_ph[i], sc); };
 
@@ -784,14 +907,19 @@ static int run_batch(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr
     if (any_fct) {
         const bool overlap = multi && !m.use_wsplit;
         // ---- phase 1: LO solution (boundary set first, then start exchange 1)
+        const int64_t bytes0 = c->halo_bytes_sent;
         if (overlap) {
             for (auto& ch : chunks) if (ch.fct) run(PH_N1, ch, rS);
             CU(cudaEventRecord(c->ev_a, sc));
             CU(cudaStreamWaitEvent(sx, c->ev_a, 0));
-            if (int rc = halo_exchange(c, sx, (int)f1.size(), f1.data(), s1.data(), n1.data())) return rc;   // driver :335
+            CU(cudaEventRecord(c->ev_x0[0], sx));
+            if (int rc = halo_exchange(c, HALO_NOD, sx, (int)f1.size(), f1.data(), s1.data(), nullptr, n1.data())) return rc;   // driver :335
+            CU(cudaEventRecord(c->ev_x1[0], sx));
             CU(cudaEventRecord(c->ev_b, sx));
             for (auto& ch : chunks) if (ch.fct) run(PH_N1, ch, rI);
+            CU(cudaEventRecord(c->ev_w0[0], sc));
             CU(cudaStreamWaitEvent(sc, c->ev_b, 0));
+            CU(cudaEventRecord(c->ev_w1[0], sc));
         } else {
             for (auto& ch : chunks) if (ch.fct) run(PH_N1, ch, rAll);
             if (m.use_wsplit) {
@@ -802,7 +930,11 @@ static int run_batch(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr
                             ++c->launches;
                         }
             }
-            if (multi) if (int rc = halo_exchange(c, sc, (int)f1.size(), f1.data(), s1.data(), n1.data())) return rc;
+            if (multi) {   // nothing to overlap with: the whole exchange is exposed
+                CU(cudaEventRecord(c->ev_x0[0], sc)); CU(cudaEventRecord(c->ev_w0[0], sc));
+                if (int rc = halo_exchange(c, HALO_NOD, sc, (int)f1.size(), f1.data(), s1.data(), nullptr, n1.data())) return rc;
+                CU(cudaEventRecord(c->ev_x1[0], sc)); CU(cudaEventRecord(c->ev_w1[0], sc));
+            }
         }
         mark(2);
         // ---- phase 2: bounds + R+/R- (boundary set first, then start exchange 2)
@@ -810,13 +942,19 @@ static int run_batch(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr
             for (auto& ch : chunks) if (ch.fct) run(PH_K2, ch, rS);
             CU(cudaEventRecord(c->ev_c, sc));
             CU(cudaStreamWaitEvent(sx, c->ev_c, 0));
-            if (int rc = halo_exchange(c, sx, (int)f2.size(), f2.data(), s2.data(), n2.data())) return rc;   // fct :413
+            CU(cudaEventRecord(c->ev_x0[1], sx));
+            if (int rc = halo_exchange(c, HALO_NOD, sx, (int)f2.size(), f2.data(), s2.data(), nullptr, n2.data())) return rc;   // fct :413
+            CU(cudaEventRecord(c->ev_x1[1], sx));
             CU(cudaEventRecord(c->ev_d, sx));
             for (auto& ch : chunks) if (ch.fct) run(PH_K2, ch, rI);
             // ---- phase 3: interior update overlaps exchange 2
             for (auto& ch : chunks) if (ch.fct) run(PH_K3, ch, rI);
+            CU(cudaEventRecord(c->ev_w0[1], sc));
             CU(cudaStreamWaitEvent(sc, c->ev_d, 0));
+            CU(cudaEventRecord(c->ev_w1[1], sc));
             for (auto& ch : chunks) if (ch.fct) run(PH_K3, ch, rSH);
+            c->halo_bytes_last = c->halo_bytes_sent - bytes0;
+            c->x_valid = true;
         } else {
             for (auto& ch : chunks) if (ch.fct) run(PH_K2, ch, rAll);
             mark(3);
@@ -869,27 +1007,35 @@ static int do_adv(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr, i
             p.ttf[i] = s.ttf.p; p.ttfAB[i] = s.ttfAB.p; p.dh[i] = s.dh.p; p.dv[i] = s.dv.p;
         }
     }
-    // edge_up_dn_grad == NULL for a gradient-based scheme: the library runs the caller's
-    // tracer_gradient_elements + fill_up_dn_grad itself (adv_ctx_set_gradient_mesh; one rank: on more
-    // ranks tr_xy needs the caller's exchange_elem).  Saves the 4 E L words of H2D per tracer.
-    for (int i = 0; i < ntr; ++i) {
-        if (p.grad[i] || !c->grad_mesh_set) continue;
-        char hbuf[16]; int k = 0;
-        for (const char* q = tr[i].tra_adv_hor; q && *q && *q != ' ' && k < 15; ++q) hbuf[k++] = *q;
-        hbuf[k] = 0;
-        if (strcmp(hbuf, "UPW1") == 0) continue;
-        if (c->npes > 1) return fail(ADV_EINVAL, "edge_up_dn_grad = NULL needs the caller's exchange_elem(tr_xy) on more than one rank");
-        Slot& s = c->slots[i];
-        const size_t nxy = (size_t)2 * m.L * c->gm.n_elem;
-        if (s.tr_xy.n != nxy) CU(s.tr_xy.alloc(nxy));
-        if (s.grad.n != 4 * nLE) CU(s.grad.alloc(4 * nLE));
-        const double* ttf1[1] = {p.ttf[i]};
-        double* xy1[1] = {s.tr_xy.p};
-        double* g1[1] = {s.grad.p};
-        if (int rc = adv_tracer_gradient_elements(c, 1, ttf1, xy1)) return rc;
-        const double* cxy1[1] = {s.tr_xy.p};
-        if (int rc = adv_fill_up_dn_grad(c, 1, cxy1, g1)) return rc;
-        p.grad[i] = s.grad.p;
+    // edge_up_dn_grad == NULL for a gradient-based scheme: the library runs the caller's tracer_gradient_elements,
+    // exchange_elem(tr_xy) and fill_up_dn_grad itself (adv_ctx_set_gradient_mesh).  Saves the 4 E L words of
+    // H2D per tracer, and the caller's own gradient sweeps.
+    {
+        std::vector<int> need;
+        for (int i = 0; i < ntr; ++i) {
+            if (p.grad[i] || !c->grad_mesh_set) continue;
+            char hbuf[16]; int k = 0;
+            for (const char* q = tr[i].tra_adv_hor; q && *q && *q != ' ' && k < 15; ++q) hbuf[k++] = *q;
+            hbuf[k] = 0;
+            if (strcmp(hbuf, "UPW1") != 0) need.push_back(i);
+        }
+        if (!need.empty()) {
+            if (c->npes > 1 && !c->elem_halo_set)
+                return fail(ADV_EINVAL, "edge_up_dn_grad = NULL on more than one rank needs com_elem2D_full in adv_ctx_set_gradient_mesh");
+            const size_t nxy = (size_t)2 * m.L * c->gm.n_elem;
+            std::vector<const double*> ttfs, cxy;
+            std::vector<double*> xy, gr;
+            for (int i : need) {
+                Slot& s = c->slots[i];
+                if (s.tr_xy.n != nxy) CU(s.tr_xy.alloc(nxy));
+                if (s.grad.n != 4 * nLE) CU(s.grad.alloc(4 * nLE));
+                ttfs.push_back(p.ttf[i]); xy.push_back(s.tr_xy.p); cxy.push_back(s.tr_xy.p); gr.push_back(s.grad.p);
+                p.grad[i] = s.grad.p;
+            }
+            if (int rc = adv_tracer_gradient_elements(c, (int)need.size(), ttfs.data(), xy.data())) return rc;
+            if (c->npes > 1) if (int rc = adv_exchange_elem(c, (int)need.size(), xy.data(), 2 * m.L)) return rc;
+            if (int rc = adv_fill_up_dn_grad(c, (int)need.size(), cxy.data(), gr.data())) return rc;
+        }
     }
     CU(cudaEventRecord(c->ev_t0, c->s_comp));
     if (int rc = run_batch(c, dt, ntr, tr, p)) return rc;
@@ -915,6 +1061,24 @@ int adv_do_oce_adv_tra_async(adv_ctx_t* c, double dt, int ntr, const adv_tracer_
     return do_adv(c, dt, ntr, tr, ADV_DEVICE, false);
 }
 
+int adv_ctx_wait_for(adv_ctx_t* c, void* stream)
+{
+    if (!c) return fail(ADV_EINVAL, "null ctx");
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventRecord(c->ev_order, (cudaStream_t)stream));
+    CU(cudaStreamWaitEvent(c->s_comp, c->ev_order, 0));
+    return ADV_OK;
+}
+
+int adv_ctx_signal(adv_ctx_t* c, void* stream)
+{
+    if (!c) return fail(ADV_EINVAL, "null ctx");
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventRecord(c->ev_order, c->s_comp));
+    CU(cudaStreamWaitEvent((cudaStream_t)stream, c->ev_order, 0));
+    return ADV_OK;
+}
+
 int adv_ctx_synchronize(adv_ctx_t* c)
 {
     if (!c) return fail(ADV_EINVAL, "null ctx");
@@ -924,18 +1088,37 @@ int adv_ctx_synchronize(adv_ctx_t* c)
     return ADV_OK;
 }
 
+static int exchange_fields(adv_ctx_t* c, int kind, int nfields, double* const* fields, int nlev)
+{
+    CU(cudaSetDevice(c->device));
+    const HaloSet& h = c->halo[kind];
+    const size_t need = (size_t)nfields * h.send_cols * nlev, needr = h.recv_base >= 0 ? 0 : (size_t)nfields * h.recv_cols * nlev;
+    if (c->xbuf.n < need || c->xrbuf.n < needr) {
+        CU(cudaStreamSynchronize(c->s_comp));
+        if (c->xbuf.n < need) CU(c->xbuf.alloc(need, false));
+        if (c->xrbuf.n < needr) CU(c->xrbuf.alloc(needr, false));
+    }
+    std::vector<double*> sb(nfields), rb(nfields);
+    for (int f = 0; f < nfields; ++f) { sb[f] = c->xbuf.p + (size_t)f * h.send_cols * nlev; rb[f] = c->xrbuf.p + (size_t)f * h.recv_cols * nlev; }
+    std::vector<int> nl(nfields, nlev);
+    return halo_exchange(c, kind, c->s_comp, nfields, fields, sb.data(), h.recv_base >= 0 ? nullptr : rb.data(), nl.data());
+}
+
 int adv_exchange_nod(adv_ctx_t* c, int nfields, double* const* fields, int nlev)
 {
     if (!c || !fields || nfields < 1 || nlev < 1) return fail(ADV_EINVAL, "bad argument");
     if (c->npes == 1) return ADV_OK;
-    if (!c->comm) return fail(ADV_ESTATE, "adv_ctx_comm_init was not called");
-    CU(cudaSetDevice(c->device));
-    const size_t need = (size_t)nfields * c->send_cols * nlev;
-    if (c->xbuf.n < need) { CU(cudaStreamSynchronize(c->s_comp)); CU(c->xbuf.alloc(need, false)); }
-    std::vector<double*> sb(nfields);
-    for (int f = 0; f < nfields; ++f) sb[f] = c->xbuf.p + (size_t)f * c->send_cols * nlev;
-    std::vector<int> nl(nfields, nlev);
-    return halo_exchange(c, c->s_comp, nfields, fields, sb.data(), nl.data());
+    if (!c->comm && !c->lc) return fail(ADV_ESTATE, "adv_ctx_comm_init was not called");
+    return exchange_fields(c, HALO_NOD, nfields, fields, nlev);
+}
+
+int adv_exchange_elem(adv_ctx_t* c, int nfields, double* const* fields, int nwords)
+{
+    if (!c || !fields || nfields < 1 || nwords < 1) return fail(ADV_EINVAL, "bad argument");
+    if (c->npes == 1) return ADV_OK;
+    if (!c->comm && !c->lc) return fail(ADV_ESTATE, "adv_ctx_comm_init was not called");
+    if (!c->grad_mesh_set || !c->elem_halo_set) return fail(ADV_ESTATE, "adv_ctx_set_gradient_mesh with com_elem2D_full has not been called");
+    return exchange_fields(c, HALO_ELEM, nfields, fields, nwords);
 }
 
 int adv_update_values(adv_ctx_t* c, int ntr, double* const* values, const double* const* dh, const double* const* dv)
@@ -1017,6 +1200,36 @@ int adv_ctx_set_gradient_mesh(adv_ctx_t* c, const adv_gradient_mesh_desc_t* g)
     gm.nie = c->g_nie.p; gm.nie_num = c->g_nie_num.p; gm.nlevels = c->g_nlevels.p; gm.ulevels = c->g_ulevels.p;
     gm.up_dn_tri = c->g_tri.p; gm.nmin = c->g_nmin.p; gm.umax = c->g_umax.p; gm.elem_nodes = c->g_elem_nodes.p;
     gm.gsca = c->g_sca.p; gm.earea = c->g_earea.p;
+    // com_elem2D_full: halo of tr_xy (exchange_elem, src/oce_tracer_mod.F90:140)
+    c->elem_halo_set = false;
+    if (c->npes > 1 && (g->rPEnum > 0 || g->sPEnum > 0)) {
+        HaloSet& he = c->halo[HALO_ELEM];
+        he.rpeers.clear(); he.speers.clear(); he.send_cols = he.recv_cols = 0; he.recv_base = -1;
+        if ((g->rPEnum > 0 && (!g->rPE || !g->rptr || !g->rlist)) || (g->sPEnum > 0 && (!g->sPE || !g->sptr || !g->slist)))
+            return fail(ADV_EINVAL, "adv_ctx_set_gradient_mesh: com_elem2D_full has null arrays");
+        std::vector<int> sl, rl;
+        for (int i = 0; i < g->sPEnum; ++i) {
+            Peer p{g->sPE[i], g->sptr[i] - 1, g->sptr[i + 1] - g->sptr[i]};
+            he.speers.push_back(p);
+            for (int k = 0; k < p.cnt; ++k) {
+                const int el = g->slist[p.off + k] - 1;
+                if (el < 0 || el >= m.T) return fail(ADV_EINVAL, "com_elem2D_full%slist entry is not an own element");
+                sl.push_back(el);
+            }
+        }
+        for (int i = 0; i < g->rPEnum; ++i) {
+            Peer p{g->rPE[i], g->rptr[i] - 1, g->rptr[i + 1] - g->rptr[i]};
+            he.rpeers.push_back(p);
+            for (int k = 0; k < p.cnt; ++k) {
+                const int el = g->rlist[p.off + k] - 1;
+                if (el < m.T || el >= ne) return fail(ADV_EINVAL, "com_elem2D_full%rlist entry is not a halo element");
+                rl.push_back(el);
+            }
+        }
+        he.send_cols = (int)sl.size(); he.recv_cols = (int)rl.size();
+        CU(he.slist.upload(sl)); CU(he.rlist.upload(rl));
+        c->elem_halo_set = true;
+    }
     c->grad_mesh_set = true;
     return ADV_OK;
 }
@@ -1107,6 +1320,21 @@ int adv_ctx_last_elapsed_ms(adv_ctx_t* c, float* ms)
     CU(cudaSetDevice(c->device));
     CU(cudaEventSynchronize(c->ev_t1));
     CU(cudaEventElapsedTime(ms, c->ev_t0, c->ev_t1));
+    return ADV_OK;
+}
+
+int adv_ctx_halo_stats(adv_ctx_t* c, int64_t* bytes_sent, float comm_ms[2], float exposed_ms[2])
+{
+    if (!c || !bytes_sent || !comm_ms || !exposed_ms) return fail(ADV_EINVAL, "null argument");
+    if (!c->x_valid) return fail(ADV_ESTATE, "no multi-rank FCT call yet");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->s_comp));
+    CU(cudaStreamSynchronize(c->s_comm));
+    *bytes_sent = c->halo_bytes_last;
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaEventElapsedTime(&comm_ms[i], c->ev_x0[i], c->ev_x1[i]));
+        CU(cudaEventElapsedTime(&exposed_ms[i], c->ev_w0[i], c->ev_w1[i]));
+    }
     return ADV_OK;
 }
 

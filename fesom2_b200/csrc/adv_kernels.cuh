@@ -782,7 +782,7 @@ __host__ __device__ constexpr int n1_smem_arrays() { return 3 * TB + 5 + (VER ==
 template <int VER, int TB, int G>
 __global__ void ADV_N1_BOUNDS k_node_lo(MeshDev m, Chunk<TB> b, NodePart r, double dt)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     // after the header: n1_smem_arrays() arrays of [nthr] doubles; element index == threadIdx.x (compact wet layers)
     double* sm = reinterpret_cast<double*>(smem_raw + node_smem_header(m.ell_w));
     const int L = m.L, nl = m.nl, nthr = blockDim.x, tid = threadIdx.x;
@@ -1021,7 +1021,7 @@ __global__ void __launch_bounds__(128) k_vert_impl(MeshDev m, double* __restrict
 template <int TB, int G>
 __global__ void ADV_K2_BOUNDS k_fct_bounds(MeshDev m, Chunk<TB> b, NodePart r, double dt)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw + node_smem_header(m.ell_w));   // [2*TB][blockDim]: tvert_max, tvert_min
     const int L = m.L, nl = m.nl;
     node_cta_prefetch<TB + 4>(m, r, [&](int q) {
@@ -1162,7 +1162,7 @@ __device__ __forceinline__ double limit_v(double f, int k, int nzmin, int nzmax,
 template <int TB, int G>
 __global__ void ADV_K3_BOUNDS k_fct_update(MeshDev m, Chunk<TB> b, NodePart r, double dt)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int L = m.L, nl = m.nl;
     node_cta_prefetch<3 * TB + 6>(m, r, [&](int q) {
         const unsigned cl = (unsigned)L * 8u;
@@ -1377,6 +1377,15 @@ __global__ void __launch_bounds__(kBlock) k_pack_halo(const double* __restrict__
 {
     const size_t src = (size_t)slist[blockIdx.x] * nlev, dst = (size_t)blockIdx.x * nlev;
     for (int k = threadIdx.x; k < nlev; k += blockDim.x) out[dst + k] = field[src + k];
+}
+
+// halo unpack (the MPI_TYPE_INDEXED receive types of the element halo, gen_modules_partitioning.F90:217-410:
+// com_elem2D_full%rlist is not a contiguous tail): field[rlist[i]*nlev + k] = in[i*nlev + k]
+__global__ void __launch_bounds__(kBlock) k_unpack_halo(const double* __restrict__ in, const int* __restrict__ rlist,
+                                                        int nlev, double* __restrict__ field)
+{
+    const size_t dst = (size_t)rlist[blockIdx.x] * nlev, src = (size_t)blockIdx.x * nlev;
+    for (int k = threadIdx.x; k < nlev; k += blockDim.x) field[dst + k] = in[src + k];
 }
 
 // dwarf epilogue (fesom.F90:105-125 with del_ttf reset per step): values += (dh+dv)/hnode_new

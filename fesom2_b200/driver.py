@@ -64,11 +64,14 @@ class GradientMeshDesc(C.Structure):
     _fields_ = [("n_elem", C.c_int32), ("n_nod_in_elem", C.c_int32), ("nod_in_elem2D_ld", C.c_int32),
                 ("nod_in_elem2D", c_ip), ("nod_in_elem2D_num", c_ip), ("nlevels", c_ip), ("ulevels", c_ip),
                 ("edge_up_dn_tri", c_ip), ("nlevels_nod2D_min", c_ip), ("ulevels_nod2D_max", c_ip),
-                ("gradient_sca", c_dp), ("elem_area", c_dp)]
+                ("gradient_sca", c_dp), ("elem_area", c_dp),
+                ("rPEnum", C.c_int32), ("rPE", c_ip), ("rptr", c_ip), ("rlist", c_ip),
+                ("sPEnum", C.c_int32), ("sPE", c_ip), ("sptr", c_ip), ("slist", c_ip)]
 
 
 EXPORTS = ["adv_ctx_create", "adv_ctx_destroy", "adv_last_error", "adv_comm_unique_id",
-           "adv_ctx_comm_init", "adv_ctx_set_state", "adv_do_oce_adv_tra", "adv_do_oce_adv_tra_async",
+           "adv_ctx_comm_init", "adv_ctx_comm_init_local", "adv_exchange_elem", "adv_ctx_halo_stats",
+           "adv_ctx_wait_for", "adv_ctx_signal", "adv_ctx_set_state", "adv_do_oce_adv_tra", "adv_do_oce_adv_tra_async",
            "adv_ctx_synchronize", "adv_exchange_nod", "adv_update_values", "adv_init_tracers_AB",
            "adv_ctx_set_gradient_mesh", "adv_tracer_gradient_elements", "adv_fill_up_dn_grad", "adv_ctx_get_work",
            "adv_ctx_launch_count", "adv_ctx_stream", "adv_ctx_last_elapsed_ms",
@@ -98,7 +101,12 @@ def load_library():
         L.adv_do_oce_adv_tra.argtypes = [C.c_void_p, C.c_double, C.c_int, C.POINTER(TracerDesc), C.c_int]
         L.adv_do_oce_adv_tra_async.argtypes = [C.c_void_p, C.c_double, C.c_int, C.POINTER(TracerDesc)]
         L.adv_ctx_synchronize.argtypes = [C.c_void_p]
+        L.adv_ctx_wait_for.argtypes = [C.c_void_p, C.c_void_p]
+        L.adv_ctx_signal.argtypes = [C.c_void_p, C.c_void_p]
         L.adv_exchange_nod.argtypes = [C.c_void_p, C.c_int, C.POINTER(c_dp), C.c_int]
+        L.adv_exchange_elem.argtypes = [C.c_void_p, C.c_int, C.POINTER(c_dp), C.c_int]
+        L.adv_ctx_comm_init_local.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.adv_ctx_halo_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.adv_update_values.argtypes = [C.c_void_p, C.c_int, C.POINTER(c_dp), C.POINTER(c_dp), C.POINTER(c_dp)]
         L.adv_init_tracers_AB.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double] + [C.POINTER(c_dp)] * 6
         L.adv_ctx_set_gradient_mesh.argtypes = [C.c_void_p, C.POINTER(GradientMeshDesc)]
@@ -147,6 +155,13 @@ def _where(t) -> int:
     if isinstance(t, np.ndarray):
         return ADV_HOST
     return ADV_DEVICE if t.is_cuda else ADV_HOST
+
+
+def comm_init_local(ctxs: Sequence["AdvB200"]):
+    """adv_ctx_comm_init_local: link the contexts of this process (ctxs[r] built from rank r's local mesh) into an
+    in-process communicator; afterwards every context must be driven by its own host thread."""
+    arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    _check(load_library().adv_ctx_comm_init_local(arr, len(ctxs)))
 
 
 class AdvB200:
@@ -198,10 +213,29 @@ class AdvB200:
     def comm_init(self, uid: bytes):
         _check(self.lib.adv_ctx_comm_init(self.h, uid))
 
+    # -- stream ordering against torch ---------------------------------------------------------
+    def _torch_stream(self):
+        import torch
+        return torch.cuda.current_stream(self.device).cuda_stream if torch.cuda.is_available() else None
+
+    def _after_torch(self):
+        """device tensors handed to the library may still be in flight on torch's current stream"""
+        ts = self._torch_stream()
+        if ts is not None:
+            _check(self.lib.adv_ctx_wait_for(self.h, C.c_void_p(ts)))
+
+    def _before_torch(self):
+        """torch work submitted after an asynchronous library call sees its results"""
+        ts = self._torch_stream()
+        if ts is not None:
+            _check(self.lib.adv_ctx_signal(self.h, C.c_void_p(ts)))
+
     # -- per step -----------------------------------------------------------------------------
     def set_state(self, st):
         """``st``: fields.OceanState with torch tensors (all cpu or all cuda)."""
         self._state = st   # keep alive: device pointers are used in place
+        if _where(st.uv) == ADV_DEVICE:
+            self._after_torch()
         sd = StateDesc(uv=_ptr(st.uv), w=_ptr(st.w), w_e=_ptr(st.w_e), w_i=_ptr(st.w_i), helem=_ptr(st.helem),
                        hnode=_ptr(st.hnode), hnode_new=_ptr(st.hnode_new), zbar_3d_n=_ptr(st.zbar_3d_n),
                        Z_3d_n=_ptr(st.Z_3d_n), zbar_n_bot=_ptr(st.zbar_n_bot), use_wsplit=int(bool(st.use_wsplit)))
@@ -225,8 +259,11 @@ class AdvB200:
         are copied to the device and the tendencies copied back (blocking)."""
         arr, keep = self._descs(tracers, dttf_h, dttf_v)
         where = _where(tracers[0].values)
+        if where == ADV_DEVICE:
+            self._after_torch()
         if where == ADV_DEVICE and not sync:
             _check(self.lib.adv_do_oce_adv_tra_async(self.h, float(dt), len(tracers), arr))
+            self._before_torch()
         else:
             _check(self.lib.adv_do_oce_adv_tra(self.h, float(dt), len(tracers), arr, where))
 
@@ -235,13 +272,17 @@ class AdvB200:
 
     def exchange_nod(self, fields: Sequence, nlev: int):
         PA = c_dp * len(fields)
+        self._after_torch()
         _check(self.lib.adv_exchange_nod(self.h, len(fields), PA(*[_ptr(f) for f in fields]), int(nlev)))
+        self._before_torch()
 
     def update_values(self, values: Sequence, dttf_h: Sequence, dttf_v: Sequence):
         n = len(values)
         PA = c_dp * n
+        self._after_torch()
         _check(self.lib.adv_update_values(self.h, n, PA(*[_ptr(v) for v in values]),
                                           PA(*[_ptr(v) for v in dttf_h]), PA(*[_ptr(v) for v in dttf_v])))
+        self._before_torch()
 
     def init_tracers_AB(self, values: Sequence, valuesold: Sequence, valuesAB: Sequence, ab_order: int = 2,
                         epsilon: float = 0.1, del_ttf: Optional[Sequence] = None, dttf_h: Optional[Sequence] = None,
@@ -253,35 +294,66 @@ class AdvB200:
 
         def arr(lst):
             return PA(*[_ptr(v) for v in lst]) if lst is not None else None
+        self._after_torch()
         _check(self.lib.adv_init_tracers_AB(self.h, n, int(ab_order), float(epsilon), arr(values), arr(valuesold),
                                             arr(valuesAB), arr(del_ttf), arr(dttf_h), arr(dttf_v)))
+        self._before_torch()
 
     # -- producer of edge_up_dn_grad ---------------------------------------------
-    def set_gradient_mesh(self, edge_up_dn_tri: np.ndarray):
+    def set_gradient_mesh(self, edge_up_dn_tri: Optional[np.ndarray] = None, gmesh=None):
         """Static inputs of tracer_gradient_elements / fill_up_dn_grad (t_tracer_work%edge_up_dn_tri and the
-        t_mesh fields gradient_sca, elem_area, nlevels_nod2D_min, ulevels_nod2D_max, nod_in_elem2D)."""
+        t_mesh fields gradient_sca, elem_area, nlevels_nod2D_min, ulevels_nod2D_max, nod_in_elem2D).  One rank:
+        ``edge_up_dn_tri`` is enough; a rank of a partitioned mesh passes ``gmesh`` = mesh.gradient_mesh(...),
+        which carries the element halo (eDim + eXDim) and com_elem2D_full."""
         m, k = self.mesh, self._keep
-        d = GradientMeshDesc(n_elem=int(np.asarray(m.elem_area).shape[0]), n_nod_in_elem=int(np.asarray(m.nod_in_elem2D).shape[0]),
-                             nod_in_elem2D_ld=int(np.asarray(m.nod_in_elem2D).shape[1]))
-        for name, src in (("nod_in_elem2D", m.nod_in_elem2D), ("nod_in_elem2D_num", m.nod_in_elem2D_num), ("nlevels", m.nlevels),
-                          ("ulevels", m.ulevels), ("edge_up_dn_tri", edge_up_dn_tri), ("nlevels_nod2D_min", m.nlevels_nod2D_min),
-                          ("ulevels_nod2D_max", m.ulevels_nod2D_max)):
+        if gmesh is None:
+            from .mesh import gradient_mesh
+            gmesh = gradient_mesh(m, edge_up_dn_tri)
+        self.gmesh = gmesh
+        d = GradientMeshDesc(n_elem=int(gmesh.n_elem), n_nod_in_elem=int(gmesh.nod_in_elem2D.shape[0]),
+                             nod_in_elem2D_ld=int(gmesh.nod_in_elem2D.shape[1]))
+        for name, src in (("nod_in_elem2D", gmesh.nod_in_elem2D), ("nod_in_elem2D_num", gmesh.nod_in_elem2D_num),
+                          ("nlevels", gmesh.nlevels), ("ulevels", gmesh.ulevels), ("edge_up_dn_tri", gmesh.edge_up_dn_tri),
+                          ("nlevels_nod2D_min", m.nlevels_nod2D_min), ("ulevels_nod2D_max", m.ulevels_nod2D_max)):
             k["g_" + name] = np.ascontiguousarray(src, dtype=np.int32)
             setattr(d, name, k["g_" + name].ctypes.data_as(c_ip))
-        for name, src in (("gradient_sca", m.gradient_sca), ("elem_area", m.elem_area)):
+        for name, src in (("gradient_sca", m.gradient_sca), ("elem_area", gmesh.elem_area)):
             k["g_" + name] = np.ascontiguousarray(src, dtype=np.float64)
             setattr(d, name, k["g_" + name].ctypes.data_as(c_dp))
+        com = gmesh.com_elem2D_full
+        for name in ("rPE", "rptr", "rlist", "sPE", "sptr", "slist"):
+            k["ge_" + name] = np.ascontiguousarray(getattr(com, name), dtype=np.int32)
+            setattr(d, name, k["ge_" + name].ctypes.data_as(c_ip))
+        d.rPEnum, d.sPEnum = com.rPEnum, com.sPEnum
         _check(self.lib.adv_ctx_set_gradient_mesh(self.h, C.byref(d)))
+
+    def exchange_elem(self, fields: Sequence, nwords: int):
+        """``exchange_elem`` over com_elem2D_full for element fields with ``nwords`` doubles per element column."""
+        PA = c_dp * len(fields)
+        self._after_torch()
+        _check(self.lib.adv_exchange_elem(self.h, len(fields), PA(*[_ptr(f) for f in fields]), int(nwords)))
+        self._before_torch()
+
+    def halo_stats(self):
+        """(bytes sent, comm_ms[2], exposed_ms[2]) of the last multi-rank FCT call."""
+        b = C.c_int64(0)
+        cm, ex = (C.c_float * 2)(), (C.c_float * 2)()
+        _check(self.lib.adv_ctx_halo_stats(self.h, C.byref(b), cm, ex))
+        return int(b.value), [float(x) for x in cm], [float(x) for x in ex]
 
     def tracer_gradient_elements(self, ttf: Sequence, tr_xy: Sequence):
         """``tracer_gradient_elements`` (src/oce_tracer_mod.F90:146-188): ttf[i] (Nh, L) -> tr_xy[i] (n_elem, L, 2)."""
         PA = c_dp * len(ttf)
+        self._after_torch()
         _check(self.lib.adv_tracer_gradient_elements(self.h, len(ttf), PA(*[_ptr(t) for t in ttf]), PA(*[_ptr(t) for t in tr_xy])))
+        self._before_torch()
 
     def fill_up_dn_grad(self, tr_xy: Sequence, edge_up_dn_grad: Sequence):
         """``fill_up_dn_grad`` (src/oce_muscl_adv.F90:356-525): tr_xy[i] -> edge_up_dn_grad[i] (E, L, 4)."""
         PA = c_dp * len(tr_xy)
+        self._after_torch()
         _check(self.lib.adv_fill_up_dn_grad(self.h, len(tr_xy), PA(*[_ptr(t) for t in tr_xy]), PA(*[_ptr(t) for t in edge_up_dn_grad])))
+        self._before_torch()
 
     # -- introspection ------------------------------------------------------------------------
     def get_work(self, name: str, slot: int = 0) -> np.ndarray:

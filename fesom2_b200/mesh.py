@@ -512,6 +512,54 @@ def element_halo(g: Mesh, part: np.ndarray, mype: int) -> Dict[str, object]:
                 com_elem2D=com(r1, o1, send1), com_elem2D_full=com(r2, o2, send2))
 
 
+@dataclass
+class GradientMesh:
+    """Static inputs of tracer_gradient_elements / fill_up_dn_grad on one rank (adv_gradient_mesh_desc_t):
+    the element halo eDim + eXDim appended to the own elements, element neighbourhoods of ALL local nodes."""
+    n_elem: int
+    nod_in_elem2D: np.ndarray        # (Nh, ld) local element numbers, 1-based, 0 padded
+    nod_in_elem2D_num: np.ndarray    # (Nh,)
+    nlevels: np.ndarray              # (n_elem,)
+    ulevels: np.ndarray
+    edge_up_dn_tri: np.ndarray       # (E, 2) local element numbers, 0 = none
+    elem_area: np.ndarray            # (n_elem,)
+    myList_elem2D: np.ndarray        # (n_elem,) global ids, 1-based
+    com_elem2D_full: ComStruct = field(default_factory=ComStruct)
+
+
+def gradient_mesh(g: Mesh, tri_global: np.ndarray, part: Optional[np.ndarray] = None, loc: Optional[Mesh] = None) -> GradientMesh:
+    """Gradient mesh of the 1-rank mesh ``g`` (part is None) or of rank ``loc.mype``'s local mesh ``loc`` cut from
+    ``g``: own elements, then the eDim and eXDim halo elements of ``element_halo`` (communication_elemn,
+    src/gen_comm.F90:222-527); nod_in_elem2D of halo nodes is the owner's list (src/oce_mesh.F90:2064-2088);
+    edge_up_dn_tri is the global table (find_up_downwind_triangles is evaluated on the whole mesh by the
+    reference as well: its coord_elem / e_nodes arrays are halo-exchanged, src/oce_muscl_adv.F90:192-216)."""
+    if part is None:
+        nie = np.asarray(g.nod_in_elem2D)
+        return GradientMesh(n_elem=int(g.T), nod_in_elem2D=nie.astype(np.int32), nod_in_elem2D_num=np.asarray(g.nod_in_elem2D_num, np.int32),
+                            nlevels=np.asarray(g.nlevels, np.int32), ulevels=np.asarray(g.ulevels, np.int32),
+                            edge_up_dn_tri=np.asarray(tri_global, np.int32), elem_area=np.asarray(g.elem_area, np.float64),
+                            myList_elem2D=np.arange(1, g.T + 1, dtype=np.int32))
+    h = element_halo(g, part, loc.mype)
+    elist = h["myList_elem2D"].astype(np.int64) - 1
+    assert np.array_equal(elist[:loc.T], loc.myList_elem2D.astype(np.int64) - 1)
+    e_g2l = np.full(g.T, -1, np.int64)
+    e_g2l[elist] = np.arange(elist.size)
+    nodes = loc.myList_nod2D.astype(np.int64) - 1
+    edges = loc.myList_edge2D.astype(np.int64) - 1
+    nie_g = np.asarray(g.nod_in_elem2D)[nodes].astype(np.int64) - 1
+    if (e_g2l[nie_g[nie_g >= 0]] < 0).any():
+        raise ValueError("an element around a local node is outside the element halo")
+    nie_l = np.where(nie_g >= 0, e_g2l[np.maximum(nie_g, 0)] + 1, 0).astype(np.int32)
+    tri_g = np.asarray(tri_global)[edges].astype(np.int64) - 1
+    if (e_g2l[tri_g[tri_g >= 0]] < 0).any():
+        raise ValueError("an up/down-wind triangle is outside the element halo")
+    tri_l = np.where(tri_g >= 0, e_g2l[np.maximum(tri_g, 0)] + 1, 0).astype(np.int32)
+    return GradientMesh(n_elem=int(elist.size), nod_in_elem2D=nie_l, nod_in_elem2D_num=np.asarray(g.nod_in_elem2D_num)[nodes].astype(np.int32),
+                        nlevels=np.asarray(g.nlevels)[elist].astype(np.int32), ulevels=np.asarray(g.ulevels)[elist].astype(np.int32),
+                        edge_up_dn_tri=tri_l, elem_area=np.asarray(g.elem_area)[elist].astype(np.float64),
+                        myList_elem2D=(elist + 1).astype(np.int32), com_elem2D_full=h["com_elem2D_full"])
+
+
 # =============================================================================================
 # synthetic meshes (configs 3-5 of BASELINE.json; SURVEY.md section 8d)
 # =============================================================================================

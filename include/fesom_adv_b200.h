@@ -113,6 +113,13 @@ const char *adv_last_error(void);
 int adv_comm_unique_id(char id[128]);
 int adv_ctx_comm_init(adv_ctx_t *ctx, const char id[128]);
 
+/* In-process alternative to adv_ctx_comm_init: the n contexts of ONE process (ctxs[r] created with mype = r,
+ * npes = n; one per GPU, or several on one GPU) exchange their halos with direct device-to-device copies --
+ * peer copies over NVLink between GPUs -- ordered by CUDA events, without NCCL.  Every context must then be
+ * driven by its own host thread, all threads making the same sequence of calls (each exchange is a
+ * rendezvous of the n threads, like the MPI exchange it replaces). */
+int adv_ctx_comm_init_local(adv_ctx_t *const *ctxs, int n);
+
 /* --- per step ------------------------------------------------------------------------------- */
 int adv_ctx_set_state(adv_ctx_t *ctx, const adv_state_desc_t *st, int where);
 
@@ -128,9 +135,25 @@ int adv_do_oce_adv_tra(adv_ctx_t *ctx, double dt, int ntr, const adv_tracer_desc
 int adv_do_oce_adv_tra_async(adv_ctx_t *ctx, double dt, int ntr, const adv_tracer_desc_t *tr);
 int adv_ctx_synchronize(adv_ctx_t *ctx);
 
+/* Stream ordering.  The library computes on its own non-blocking stream (adv_ctx_stream), which is NOT ordered
+ * against any stream of the caller.  DEVICE-pointer inputs that the caller produces asynchronously (OpenACC
+ * async queues -- acc_get_cuda_stream --, torch streams) must be ordered before the call with
+ * adv_ctx_wait_for(ctx, stream): the context waits for everything submitted so far to `stream` (0 = the legacy
+ * default stream).  Outputs of the *_async entry points are ordered into a caller stream with
+ * adv_ctx_signal(ctx, stream): `stream` waits for the context's work submitted so far; or call
+ * adv_ctx_synchronize.  The blocking entry points with HOST pointers need neither. */
+int adv_ctx_wait_for(adv_ctx_t *ctx, void *stream);
+int adv_ctx_signal(adv_ctx_t *ctx, void *stream);
+
 /* Replaces `exchange_nod(field, partit)` for nfields 3-D node fields with nlev levels
  * (src/gen_halo_exchange.F90:432-633): packed-halo NCCL send/recv.  DEVICE pointers. */
 int adv_exchange_nod(adv_ctx_t *ctx, int nfields, double *const *fields, int nlev);
+
+/* Replaces `exchange_elem(field, partit)` for nfields element fields with nwords doubles per element column
+ * and myDim+eDim+eXDim columns (src/gen_halo_exchange.F90:769-980, the com_elem2D_full branch), e.g. tr_xy with
+ * nwords = 2*(nl-1) (src/oce_tracer_mod.F90:140).  Needs com_elem2D_full from adv_ctx_set_gradient_mesh.
+ * DEVICE pointers. */
+int adv_exchange_elem(adv_ctx_t *ctx, int nfields, double *const *fields, int nwords);
 
 /* The dwarf's epilogue (dwarf/dwarf_tracer/dwarf_ini/fesom.F90:105-127) with del_ttf reset per
  * step as in the model (src/oce_tracer_mod.F90:28-34): values += (advhoriz+advvert)/hnode_new on
@@ -165,6 +188,11 @@ typedef struct {
     const int32_t *ulevels_nod2D_max;   /* (myDim_nod2D + eDim_nod2D)                                           */
     const double *gradient_sca;         /* (6, myDim_elem2D)                                                    */
     const double *elem_area;            /* (n_elem)                                                             */
+    /* com_elem2D_full (src/MOD_PARTIT.F90:18-33,:62; built by communication_elemn, src/gen_comm.F90:222-527): the
+     * halo of tr_xy, i.e. what exchange_elem3D moves for an array with myDim+eDim+eXDim element columns
+     * (src/gen_halo_exchange.F90:769-980).  All NULL / 0 on a single rank. */
+    int32_t rPEnum; const int32_t *rPE, *rptr, *rlist;
+    int32_t sPEnum; const int32_t *sPE, *sptr, *slist;
 } adv_gradient_mesh_desc_t;
 int adv_ctx_set_gradient_mesh(adv_ctx_t *ctx, const adv_gradient_mesh_desc_t *g);
 
@@ -179,8 +207,9 @@ int adv_tracer_gradient_elements(adv_ctx_t *ctx, int ntr, const double *const *t
  * does not write are left untouched.  DEVICE pointers, asynchronous on the context's stream. */
 int adv_fill_up_dn_grad(adv_ctx_t *ctx, int ntr, const double *const *tr_xy, double *const *edge_up_dn_grad);
 /* After adv_ctx_set_gradient_mesh a tracer descriptor may also carry edge_up_dn_grad = NULL (gradient-based
- * scheme, one rank): adv_do_oce_adv_tra then runs the two routines above on `values` itself before the
- * step, which saves the 4 E (nl-1) words of host-to-device copy per tracer on the HOST-pointer path. */
+ * scheme): adv_do_oce_adv_tra then runs the two routines above on `values` itself before the step -- with
+ * adv_exchange_elem(tr_xy) between them on more than one rank -- which saves the caller's gradient sweeps and
+ * the 4 E (nl-1) words of host-to-device copy per tracer on the HOST-pointer path. */
 
 /* --- introspection (tests, profiling) -------------------------------------------------------- */
 /* Copies an internal work array of tracer slot `slot` to a HOST buffer.  name is one of
@@ -194,6 +223,11 @@ void *adv_ctx_stream(adv_ctx_t *ctx);
 /* device-side duration [ms] of the last adv_do_oce_adv_tra[_async] call, measured with CUDA
  * events on the context's compute stream (valid after synchronisation) */
 int adv_ctx_last_elapsed_ms(adv_ctx_t *ctx, float *ms);
+/* Halo-exchange accounting of the last adv_do_oce_adv_tra[_async] call with an FCT tracer on more than one rank
+ * (synchronises): bytes this rank sent in the call's two exchanges (fct_LO: 0; fct_plus/fct_minus: 1), the
+ * duration of each on the communication stream (pack + transfer), and the time the compute stream had to wait for
+ * it after running out of interior work (the exposed part; 0 = fully hidden). */
+int adv_ctx_halo_stats(adv_ctx_t *ctx, int64_t *bytes_sent, float comm_ms[2], float exposed_ms[2]);
 /* per-phase kernel time of the last call [ms]: 0 edge fluxes (+Q), 1 LO solution, 2 bounds/R, 3 update; valid only when profiling was switched on with adv_ctx_set_profiling(ctx, 1) */
 int adv_ctx_set_profiling(adv_ctx_t *ctx, int on);
 int adv_ctx_phase_ms(adv_ctx_t *ctx, float ms[8]);
