@@ -14,8 +14,10 @@
 #include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -187,6 +189,12 @@ struct adv_ctx {
     // state (ADV_HOST staging)
     DevBuf<double> uv, helem, w, we, wi, hnode, hnode_new, zbar3d, Z3d, zbar_n_bot;
     bool state_set = false, q_valid = false;
+    int64_t state_step = -1;                  // adv_ctx_set_state_step: step number of the resident state (-1: none)
+    int state_where = -1;
+    adv_state_desc_t state_desc{};
+    bool host_register = true;                // page-lock ADV_HOST arrays on first use (adv_ctx_set_host_register)
+    std::map<const void*, size_t> registered; // ranges this context registered (0 bytes: left alone)
+    std::set<const void*> registered_foreign;
     DevBuf<double> impl_cp, impl_tp;
     std::vector<Slot> slots;
     std::vector<std::unique_ptr<ChunkBuf>> cbufs;
@@ -475,6 +483,7 @@ int adv_ctx_destroy(adv_ctx_t* c)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
+    for (auto& kv : c->registered) if (kv.second) cudaHostUnregister(const_cast<void*>(kv.first));
     for (cudaEvent_t ev : {c->ev_a, c->ev_b, c->ev_c, c->ev_d, c->ev_t0, c->ev_t1}) if (ev) cudaEventDestroy(ev);
     for (auto ev : c->ev_ph) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : {c->ev_packed, c->ev_consumed, c->ev_order, c->ev_x0[0], c->ev_x0[1], c->ev_x1[0], c->ev_x1[1], c->ev_w0[0], c->ev_w0[1], c->ev_w1[0], c->ev_w1[1]})
@@ -546,7 +555,51 @@ int adv_ctx_comm_init_local(adv_ctx_t* const* ctxs, int n)
 }
 
 // ------------------------------------------------------------------------------------------------
+// ADV_HOST arrays are pageable allocatables of the Fortran host: page-lock each range the first time it is seen
+// (cudaHostRegister) so that the per-step copies run at pinned-memory speed and asynchronously.  Ranges that are
+// already pinned (or cannot be registered) are simply used as they are.
+static void host_register(adv_ctx* c, const void* p, size_t bytes)
+{
+    if (!c->host_register || !p || bytes < (size_t)1 << 16) return;
+    auto it = c->registered.find(p);
+    if (it != c->registered.end() && it->second >= bytes) return;
+    if (it != c->registered.end()) { cudaHostUnregister(const_cast<void*>(p)); c->registered.erase(it); }
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) { c->registered[p] = 0; c->registered_foreign.insert(p); return; }
+    cudaGetLastError();
+    if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) c->registered[p] = bytes;
+    else { cudaGetLastError(); c->registered[p] = 0; c->registered_foreign.insert(p); }
+}
+
+int adv_ctx_set_host_register(adv_ctx_t* c, int on)
+{
+    if (!c) return fail(ADV_EINVAL, "null ctx");
+    c->host_register = on != 0;
+    return ADV_OK;
+}
+
+static int set_state_impl(adv_ctx_t* c, const adv_state_desc_t* st, int where);
+
 int adv_ctx_set_state(adv_ctx_t* c, const adv_state_desc_t* st, int where)
+{
+    if (c) c->state_step = -1;
+    return set_state_impl(c, st, where);
+}
+
+int adv_ctx_set_state_step(adv_ctx_t* c, const adv_state_desc_t* st, int where, int64_t step)
+{
+    if (!c || !st) return fail(ADV_EINVAL, "null argument");
+    if (step < 0) return fail(ADV_EINVAL, "adv_ctx_set_state_step: step must be >= 0");
+    const bool same = c->state_set && c->state_step == step && c->state_where == where &&
+                      memcmp(&c->state_desc, st, sizeof(adv_state_desc_t)) == 0;
+    if (same) return ADV_OK;            // the tracer loop of one model step: state, uploads and Q stay valid
+    if (int rc = set_state_impl(c, st, where)) return rc;
+    c->state_step = step; c->state_where = where;
+    memcpy(&c->state_desc, st, sizeof(adv_state_desc_t));
+    return ADV_OK;
+}
+
+static int set_state_impl(adv_ctx_t* c, const adv_state_desc_t* st, int where)
 {
     if (!c || !st) return fail(ADV_EINVAL, "null argument");
     CU(cudaSetDevice(c->device));
@@ -572,6 +625,7 @@ int adv_ctx_set_state(adv_ctx_t* c, const adv_state_desc_t* st, int where)
             {&c->zbar3d, st->zbar_3d_n, nl * Nh, &m.zbar3d}, {&c->Z3d, st->Z_3d_n, L * Nh, &m.Z3d}};
         for (auto& x : cp) {
             if (x.n == 0) { *x.dst = nullptr; continue; }
+            host_register(c, x.src, x.n * sizeof(double));
             if (x.b->n != x.n) CU(x.b->alloc(x.n, false));
             CU(cudaMemcpyAsync(x.b->p, x.src, x.n * sizeof(double), cudaMemcpyHostToDevice, c->s_comp));
             *x.dst = x.b->p;
@@ -993,6 +1047,9 @@ static int do_adv(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr, i
             }
         } else {
             Slot& s = c->slots[i];
+            host_register(c, tr[i].values, nLN * 8); host_register(c, tr[i].valuesAB, nLN * 8);
+            host_register(c, tr[i].del_ttf_advhoriz, nLN * 8); host_register(c, tr[i].del_ttf_advvert, nLN * 8);
+            if (tr[i].edge_up_dn_grad) host_register(c, tr[i].edge_up_dn_grad, 4 * nLE * 8);
             if (s.ttf.n != nLN) { CU(s.ttf.alloc(nLN, false)); CU(s.ttfAB.alloc(nLN, false)); CU(s.dh.alloc(nLN, false)); CU(s.dv.alloc(nLN, false)); }
             CU(cudaMemcpyAsync(s.ttf.p, tr[i].values, nLN * 8, cudaMemcpyHostToDevice, c->s_comp));
             CU(cudaMemcpyAsync(s.ttfAB.p, tr[i].valuesAB, nLN * 8, cudaMemcpyHostToDevice, c->s_comp));

@@ -3,7 +3,8 @@
  * Restates the single-level branch of the reference's `do_partit` (src/fort_part.c:46-241, built
  * with METIS_VERSION=5, PART_WEIGHTED, METISRANDOMSEED=35243: mesh_part/CMakeLists.txt:80-82):
  * METIS_PartGraphRecursive on the node graph with two balance constraints (2-D node count and
- * nlevels+100), NCUTS=10, NITER=15, UFACTOR=1, Fortran numbering.  Links the METIS 5 that ships
+ * nlevels+100), edge weights nlev(i)+nlev(j) (USE_EDGE_WEIGHTS is defined unconditionally, fort_part.c:11,
+ * :191-205), NCUTS=10, NITER=15, UFACTOR=1, Fortran numbering.  Links the METIS 5 that ships
  * with the CUDA toolkit (libmetis_static.a, 64-bit idx_t) instead of the vendored lib/metis-5.1.0.
  */
 #include <stdint.h>
@@ -42,12 +43,15 @@ long long fesom_partit(int n, const int32_t *ptr, const int32_t *adj, const int3
     idx_t *adjn = malloc(sizeof(idx_t) * (nnz ? nnz : 1));
     idx_t *vw = malloc(sizeof(idx_t) * 2 * (size_t)n);
     idx_t *p = malloc(sizeof(idx_t) * (size_t)n);
-    if (!xadj || !adjn || !vw || !p) return -1;
+    idx_t *ew = malloc(sizeof(idx_t) * (nnz ? nnz : 1));
+    if (!xadj || !adjn || !vw || !p || !ew) return -1;
     for (int i = 0; i <= n; ++i) xadj[i] = ptr[i];
     for (size_t k = 0; k < nnz; ++k) adjn[k] = adj[k];
     for (int i = 0; i < n; ++i) { vw[2 * i] = 1; vw[2 * i + 1] = wgt ? wgt[i] + 100 : 100; }  /* :176-179 */
-    int rc = METIS_PartGraphRecursive(&nn, &ncon, xadj, adjn, vw, NULL, NULL, &npp, NULL, NULL, opt, &ec, p); /* :233 */
+    for (int i = 0; i < n; ++i)                                                                /* :202-204 */
+        for (int j = ptr[i] - 1; j < ptr[i + 1] - 1; ++j) ew[j] = wgt ? wgt[i] + wgt[adj[j] - 1] : 1;
+    int rc = METIS_PartGraphRecursive(&nn, &ncon, xadj, adjn, vw, NULL, ew, &npp, NULL, NULL, opt, &ec, p); /* :233 */
     if (rc == 1) for (int i = 0; i < n; ++i) part[i] = (int32_t)(p[i] - 1);   /* :240 */
-    free(xadj); free(adjn); free(vw); free(p);
+    free(xadj); free(adjn); free(vw); free(p); free(ew);
     return rc == 1 ? (long long)ec : -1;
 }

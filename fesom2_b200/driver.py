@@ -71,7 +71,7 @@ class GradientMeshDesc(C.Structure):
 
 EXPORTS = ["adv_ctx_create", "adv_ctx_destroy", "adv_last_error", "adv_comm_unique_id",
            "adv_ctx_comm_init", "adv_ctx_comm_init_local", "adv_exchange_elem", "adv_ctx_halo_stats",
-           "adv_ctx_wait_for", "adv_ctx_signal", "adv_ctx_set_state", "adv_do_oce_adv_tra", "adv_do_oce_adv_tra_async",
+           "adv_ctx_wait_for", "adv_ctx_signal", "adv_ctx_set_state_step", "adv_ctx_set_host_register", "adv_ctx_set_state", "adv_do_oce_adv_tra", "adv_do_oce_adv_tra_async",
            "adv_ctx_synchronize", "adv_exchange_nod", "adv_update_values", "adv_init_tracers_AB",
            "adv_ctx_set_gradient_mesh", "adv_tracer_gradient_elements", "adv_fill_up_dn_grad", "adv_ctx_get_work",
            "adv_ctx_launch_count", "adv_ctx_stream", "adv_ctx_last_elapsed_ms",
@@ -98,6 +98,8 @@ def load_library():
         L.adv_comm_unique_id.argtypes = [C.c_char_p]
         L.adv_ctx_comm_init.argtypes = [C.c_void_p, C.c_char_p]
         L.adv_ctx_set_state.argtypes = [C.c_void_p, C.POINTER(StateDesc), C.c_int]
+        L.adv_ctx_set_state_step.argtypes = [C.c_void_p, C.POINTER(StateDesc), C.c_int, C.c_int64]
+        L.adv_ctx_set_host_register.argtypes = [C.c_void_p, C.c_int]
         L.adv_do_oce_adv_tra.argtypes = [C.c_void_p, C.c_double, C.c_int, C.POINTER(TracerDesc), C.c_int]
         L.adv_do_oce_adv_tra_async.argtypes = [C.c_void_p, C.c_double, C.c_int, C.POINTER(TracerDesc)]
         L.adv_ctx_synchronize.argtypes = [C.c_void_p]
@@ -231,15 +233,22 @@ class AdvB200:
             _check(self.lib.adv_ctx_signal(self.h, C.c_void_p(ts)))
 
     # -- per step -----------------------------------------------------------------------------
-    def set_state(self, st):
-        """``st``: fields.OceanState with torch tensors (all cpu or all cuda)."""
+    def set_host_register(self, on: bool):
+        _check(self.lib.adv_ctx_set_host_register(self.h, int(on)))
+
+    def set_state(self, st, step: Optional[int] = None):
+        """``st``: fields.OceanState with torch tensors (all cpu or all cuda).  ``step``: the model's step counter --
+        repeated calls with the same step and the same arrays are no-ops (adv_ctx_set_state_step)."""
         self._state = st   # keep alive: device pointers are used in place
         if _where(st.uv) == ADV_DEVICE:
             self._after_torch()
         sd = StateDesc(uv=_ptr(st.uv), w=_ptr(st.w), w_e=_ptr(st.w_e), w_i=_ptr(st.w_i), helem=_ptr(st.helem),
                        hnode=_ptr(st.hnode), hnode_new=_ptr(st.hnode_new), zbar_3d_n=_ptr(st.zbar_3d_n),
                        Z_3d_n=_ptr(st.Z_3d_n), zbar_n_bot=_ptr(st.zbar_n_bot), use_wsplit=int(bool(st.use_wsplit)))
-        _check(self.lib.adv_ctx_set_state(self.h, C.byref(sd), _where(st.uv)))
+        if step is None:
+            _check(self.lib.adv_ctx_set_state(self.h, C.byref(sd), _where(st.uv)))
+        else:
+            _check(self.lib.adv_ctx_set_state_step(self.h, C.byref(sd), _where(st.uv), int(step)))
 
     def _descs(self, tracers, dttf_h, dttf_v):
         n = len(tracers)

@@ -200,9 +200,57 @@ def tracer_gradient_elements(m: Mesh, ttf: torch.Tensor, device) -> torch.Tensor
     return torch.stack([torch.where(emask, tx, z), torch.where(emask, ty, z)], dim=2)
 
 
-def find_up_downwind_triangles(m: Mesh) -> np.ndarray:
+def _find_up_downwind_triangles_torch(m: Mesh, device) -> np.ndarray:
+    """The same search with torch ops on ``device`` (large synthetic meshes: seconds instead of a minute).  atan2
+    of the device may differ from libm in the last bit, which only matters where the edge direction lies exactly on
+    an element edge (the reference's `ab == ax` tie, see tests/test_oracle_pinning.py): a synthetic-input generator,
+    not the pinned restatement."""
+    cyc = float(m.cyclic_length)
+    coord = _t(m.coord_nod2D, device)
+    ed = _t(m.edges, device, torch.int64) - 1
+    en = _t(m.elem2D_nodes, device, torch.int64) - 1
+    nie = _t(m.nod_in_elem2D, device, torch.int64)
+    num = _t(m.nod_in_elem2D_num, device, torch.int64)
+    out = torch.zeros((m.E, 2), dtype=torch.int32, device=device)
+
+    def trim(v):
+        v = torch.where(v > cyc / 2, v - cyc, v)
+        return torch.where(v < -cyc / 2, v + cyc, v)
+
+    xvec = coord[ed[:, 1]] - coord[ed[:, 0]]
+    xvec = torch.stack([trim(xvec[:, 0]), xvec[:, 1]], dim=1)
+    rows = torch.arange(m.E, device=device)
+    for side in (0, 1):
+        node = ed[:, side]
+        x = -xvec if side == 0 else xvec
+        res = torch.zeros(m.E, dtype=torch.int32, device=device)
+        for k in range(nie.shape[1]):
+            have = k < num[node]
+            elem = torch.where(have, nie[node, k] - 1, torch.zeros_like(node))
+            nodes = en[elem]
+            pos = torch.where(nodes[:, 0] == node, 0, torch.where(nodes[:, 1] == node, 1, 2))
+            bi = torch.where(pos == 0, 1, 0)
+            ci = torch.where(pos == 2, 1, 2)
+            p0 = coord[nodes[rows, pos]]
+            b = coord[nodes[rows, bi]] - p0
+            c = coord[nodes[rows, ci]] - p0
+            b0, c0 = trim(b[:, 0]), trim(c[:, 0])
+            b1, c1 = b[:, 1], c[:, 1]
+            cr = c0 * c0 + c1 * c1
+            ab = torch.atan2((-b0 * c1 + b1 * c0) / cr, (b0 * c0 + b1 * c1) / cr)
+            ax = torch.atan2((-x[:, 0] * c1 + x[:, 1] * c0) / cr, (x[:, 0] * c0 + x[:, 1] * c1) / cr)
+            hit = (((ab > 0) & (ax > 0) & (ax < ab)) | ((ab < 0) & (ax < 0) & (ax > ab)) | (ab == ax) | (ax == 0)) & have
+            res = torch.where(hit, (elem + 1).to(torch.int32), res)
+        out[:, side] = res
+    return out.cpu().numpy()
+
+
+def find_up_downwind_triangles(m: Mesh, device=None) -> np.ndarray:
     """edge_up_dn_tri(2,E), 1-based, 0 = none (oce_muscl_adv.F90:240-333).  The reference's loop
-    keeps the LAST element of nod_in_elem2D that satisfies the test."""
+    keeps the LAST element of nod_in_elem2D that satisfies the test.  ``device``: evaluate with torch there
+    (input generation for the large bench meshes); default: NumPy, the version pinned against the C restatement."""
+    if device is not None:
+        return _find_up_downwind_triangles_torch(m, device)
     cyc = m.cyclic_length
     coord = m.coord_nod2D
     ed = m.edges.astype(np.int64) - 1

@@ -11,20 +11,44 @@
 ! solve_tracers_ale (src/oce_ale_tracer.F90:312) and the dwarf (dwarf_ini/fesom.F90:97) call it as
 ! before.
 !
-! Derived types with allocatable components are not C-interoperable, so this wrapper passes
-! c_loc() of every component the path reads plus the scalar dimensions.  It is shipped as source;
-! this image has no Fortran compiler, so it is compiled by the FESOM build (INTEGRATION.md).
+! Derived types with allocatable components are not C-interoperable, so this wrapper passes the
+! ADDRESS of every component the path reads plus the scalar dimensions.  Which address is decided in
+! ONE place, the macro ADV_ADDR: c_loc(x) in a host build, acc_deviceptr(x) (OpenACC >= 2.6 Fortran
+! API, module openacc) in the reference's GPU build, where the operands live in the enclosing
+! `!$ACC DATA` / `!$ACC ENTER DATA` regions (dwarf_ini/fesom.F90:71-83, src/fesom_module.F90:759-805).
+! acc_deviceptr is an ordinary function: unlike `!$ACC HOST_DATA USE_DEVICE`, which is lexical to the
+! region it is written in, it returns the device address in any scope.
 !
-! Batched entry: do_oce_adv_tra_b200_batch(dt, ..., tr_first, tr_last, ...) hands several tracers
-! to one library call so that geometry / volume-flux reads are amortised (RECOM-style runs).
+! State upload: the reference refreshes uv/w/thicknesses once per step (src/oce_ale_tracer.F90:260-262)
+! and then calls do_oce_adv_tra once per tracer (:280-312).  The wrapper hands the state over with
+! adv_ctx_set_state_step and the model's step counter mstep (src/oce_modules.F90:23): only the first
+! tracer of a step uploads it and computes the edge volume flux, the others reuse both.
+!
+! Batched entry: do_oce_adv_tra_b200_batch hands tracers tr_first..tr_last to ONE library call so that
+! geometry reads are amortised (RECOM-style runs).  The reference owns ONE tracers%work set
+! (edge_up_dn_grad, del_ttf_advhoriz, del_ttf_advvert: src/MOD_TRACER.F90:36,64), which cannot serve
+! several tracers at once: a batch of more than one tracer must bring per-tracer arrays (the optional
+! arguments grad_b, dh_b, dv_b); without them the call is refused.
+!
+! This image has no Fortran compiler: the file is shipped as source and compiled by the FESOM build
+! (INTEGRATION.md); tests/test_fortran_shim.py checks every bind(C) type and interface of this file
+! field by field against include/fesom_adv_b200.h.
 !===============================================================================
+#ifdef ENABLE_OPENACC
+#define ADV_ADDR(x) acc_deviceptr(x)
+#define ADV_WHERE ADV_DEVICE
+#else
+#define ADV_ADDR(x) c_loc(x)
+#define ADV_WHERE ADV_HOST
+#endif
+
 module oce_adv_tra_b200
   use, intrinsic :: iso_c_binding
   implicit none
   private
   public :: adv_b200_init, adv_b200_finalize, do_oce_adv_tra_b200_batch, adv_b200_ctx
 
-  integer(c_int), parameter :: ADV_OK = 0, ADV_ESCHEME = -3
+  integer(c_int), parameter :: ADV_OK = 0, ADV_EINVAL = -1, ADV_ESCHEME = -3
   integer(c_int), parameter :: ADV_HOST = 0, ADV_DEVICE = 1
 
   ! adv_mesh_desc_t (include/fesom_adv_b200.h)
@@ -57,6 +81,21 @@ module oce_adv_tra_b200
      real(c_double) :: tra_adv_ph, tra_adv_pv
   end type adv_tracer_desc_t
 
+  ! adv_gradient_mesh_desc_t
+  type, bind(C) :: adv_gradient_mesh_desc_t
+     integer(c_int32_t) :: n_elem
+     integer(c_int32_t) :: n_nod_in_elem
+     integer(c_int32_t) :: nod_in_elem2D_ld
+     type(c_ptr) :: nod_in_elem2D, nod_in_elem2D_num
+     type(c_ptr) :: nlevels, ulevels
+     type(c_ptr) :: edge_up_dn_tri, nlevels_nod2D_min, ulevels_nod2D_max
+     type(c_ptr) :: gradient_sca, elem_area
+     integer(c_int32_t) :: rPEnum
+     type(c_ptr) :: rPE, rptr, rlist
+     integer(c_int32_t) :: sPEnum
+     type(c_ptr) :: sPE, sptr, slist
+  end type adv_gradient_mesh_desc_t
+
   interface
      integer(c_int) function adv_ctx_create(ctx, mesh, device, max_tracers) bind(C, name='adv_ctx_create')
        import :: c_int, c_ptr, adv_mesh_desc_t
@@ -86,6 +125,13 @@ module oce_adv_tra_b200
        type(adv_state_desc_t), intent(in) :: st
        integer(c_int), value :: where
      end function
+     integer(c_int) function adv_ctx_set_state_step(ctx, st, where, step) bind(C, name='adv_ctx_set_state_step')
+       import :: c_int, c_int64_t, c_ptr, adv_state_desc_t
+       type(c_ptr), value :: ctx
+       type(adv_state_desc_t), intent(in) :: st
+       integer(c_int), value :: where
+       integer(c_int64_t), value :: step
+     end function
      integer(c_int) function adv_do_oce_adv_tra(ctx, dt, ntr, tr, where) bind(C, name='adv_do_oce_adv_tra')
        import :: c_int, c_ptr, c_double, adv_tracer_desc_t
        type(c_ptr), value :: ctx
@@ -94,23 +140,30 @@ module oce_adv_tra_b200
        type(adv_tracer_desc_t), intent(in) :: tr(*)
        integer(c_int), value :: where
      end function
-     ! the producer of edge_up_dn_grad on the device (tracer_gradient_elements, fill_up_dn_grad)
+     ! the producer of edge_up_dn_grad on the device (tracer_gradient_elements, exchange_elem, fill_up_dn_grad)
      integer(c_int) function adv_ctx_set_gradient_mesh(ctx, g) bind(C, name='adv_ctx_set_gradient_mesh')
-       import :: c_ptr, c_int
+       import :: c_ptr, c_int, adv_gradient_mesh_desc_t
        type(c_ptr), value :: ctx
-       type(c_ptr), value :: g       ! c_loc of an adv_gradient_mesh_desc_t (include/fesom_adv_b200.h)
+       type(adv_gradient_mesh_desc_t), intent(in) :: g
      end function
      integer(c_int) function adv_tracer_gradient_elements(ctx, ntr, ttf, tr_xy) bind(C, name='adv_tracer_gradient_elements')
        import :: c_ptr, c_int
        type(c_ptr), value    :: ctx
        integer(c_int), value :: ntr
-       type(c_ptr), value    :: ttf, tr_xy          ! arrays of ntr device pointers
+       type(c_ptr), intent(in) :: ttf(*), tr_xy(*)            ! arrays of ntr device pointers
      end function
      integer(c_int) function adv_fill_up_dn_grad(ctx, ntr, tr_xy, edge_up_dn_grad) bind(C, name='adv_fill_up_dn_grad')
        import :: c_ptr, c_int
        type(c_ptr), value    :: ctx
        integer(c_int), value :: ntr
-       type(c_ptr), value    :: tr_xy, edge_up_dn_grad
+       type(c_ptr), intent(in) :: tr_xy(*), edge_up_dn_grad(*)
+     end function
+     integer(c_int) function adv_exchange_elem(ctx, nfields, fields, nwords) bind(C, name='adv_exchange_elem')
+       import :: c_ptr, c_int
+       type(c_ptr), value    :: ctx
+       integer(c_int), value :: nfields
+       type(c_ptr), intent(in) :: fields(*)
+       integer(c_int), value :: nwords
      end function
      ! device-resident dwarf loop (dwarf_ini/fesom.F90:85-128): prologue, epilogue, halo exchange
      integer(c_int) function adv_init_tracers_AB(ctx, ntr, ab_order, epsilon, values, valuesold, valuesAB, &
@@ -119,19 +172,32 @@ module oce_adv_tra_b200
        type(c_ptr), value    :: ctx
        integer(c_int), value :: ntr, ab_order
        real(c_double), value :: epsilon
-       type(c_ptr), value    :: values, valuesold, valuesAB, del_ttf, del_ttf_advhoriz, del_ttf_advvert   ! arrays of ntr device pointers
+       type(c_ptr), intent(in) :: values(*), valuesold(*), valuesAB(*), del_ttf(*), del_ttf_advhoriz(*), del_ttf_advvert(*)
      end function
      integer(c_int) function adv_update_values(ctx, ntr, values, del_ttf_advhoriz, del_ttf_advvert) bind(C, name='adv_update_values')
        import :: c_ptr, c_int
        type(c_ptr), value    :: ctx
        integer(c_int), value :: ntr
-       type(c_ptr), value    :: values, del_ttf_advhoriz, del_ttf_advvert
+       type(c_ptr), intent(in) :: values(*), del_ttf_advhoriz(*), del_ttf_advvert(*)
      end function
      integer(c_int) function adv_exchange_nod(ctx, nfields, fields, nlev) bind(C, name='adv_exchange_nod')
        import :: c_ptr, c_int
        type(c_ptr), value    :: ctx
-       integer(c_int), value :: nfields, nlev
-       type(c_ptr), value    :: fields
+       integer(c_int), value :: nfields
+       type(c_ptr), intent(in) :: fields(*)
+       integer(c_int), value :: nlev
+     end function
+     integer(c_int) function adv_ctx_wait_for(ctx, stream) bind(C, name='adv_ctx_wait_for')
+       import :: c_ptr, c_int
+       type(c_ptr), value :: ctx, stream
+     end function
+     integer(c_int) function adv_ctx_signal(ctx, stream) bind(C, name='adv_ctx_signal')
+       import :: c_ptr, c_int
+       type(c_ptr), value :: ctx, stream
+     end function
+     integer(c_int) function adv_ctx_synchronize(ctx) bind(C, name='adv_ctx_synchronize')
+       import :: c_ptr, c_int
+       type(c_ptr), value :: ctx
      end function
   end interface
 
@@ -141,7 +207,8 @@ contains
 
   !-----------------------------------------------------------------------------
   ! Call once after oce_adv_tra_fct_init / muscl_adv_init (src/oce_setup_step.F90:239): uploads the
-  ! static mesh slice, builds the gather lists and the NCCL communicator.
+  ! static mesh slice, builds the gather lists and the NCCL communicator.  The descriptor's arrays are
+  ! always HOST arrays (the library copies them).
   !-----------------------------------------------------------------------------
   subroutine adv_b200_init(tracers, partit, mesh, device)
     use MOD_MESH
@@ -193,16 +260,22 @@ contains
   end subroutine adv_b200_finalize
 
   !-----------------------------------------------------------------------------
-  ! tracers tr_first..tr_last in ONE library call.  use_device=.true.: the arrays are resident on
-  ! the GPU (OpenACC build: call inside `!$ACC HOST_DATA USE_DEVICE(...)`, the dwarf's convention,
-  ! fesom.F90:71-83); .false.: host arrays, the library copies in and out.
+  ! tracers tr_first..tr_last in ONE library call.  One tracer: the reference's single work set
+  ! tracers%work%{edge_up_dn_grad, del_ttf_advhoriz, del_ttf_advvert} is used, exactly like
+  ! do_oce_adv_tra.  More than one: the caller supplies per-tracer arrays
+  !     grad_b(4, nl-1, myDim_edge2D, n), dh_b(nl-1, myDim_nod2D+eDim_nod2D, n), dv_b(same)
+  ! (n = tr_last-tr_first+1; in an OpenACC build they must be present on the device).
   !-----------------------------------------------------------------------------
-  subroutine do_oce_adv_tra_b200_batch(dt, vel, w, wi, we, tr_first, tr_last, dynamics, tracers, partit, mesh, use_device)
+  subroutine do_oce_adv_tra_b200_batch(dt, vel, w, wi, we, tr_first, tr_last, dynamics, tracers, partit, mesh, grad_b, dh_b, dv_b)
     use MOD_MESH
     use MOD_TRACER
     use MOD_PARTIT
     use MOD_PARSUP
     use MOD_DYN
+    use o_PARAM, only: mstep
+#ifdef ENABLE_OPENACC
+    use openacc
+#endif
     real(kind=WP),  intent(in),    target :: dt
     integer,        intent(in)            :: tr_first, tr_last
     type(t_partit), intent(inout), target :: partit
@@ -213,39 +286,59 @@ contains
     real(kind=WP),  intent(in),    target :: W(mesh%nl,  partit%myDim_nod2D+partit%eDim_nod2D)
     real(kind=WP),  intent(in),    target :: WI(mesh%nl, partit%myDim_nod2D+partit%eDim_nod2D)
     real(kind=WP),  intent(in),    target :: WE(mesh%nl, partit%myDim_nod2D+partit%eDim_nod2D)
-    logical,        intent(in)            :: use_device
+    real(kind=WP),  intent(in),    target, optional :: grad_b(:,:,:,:)
+    real(kind=WP),  intent(inout), target, optional :: dh_b(:,:,:), dv_b(:,:,:)
     type(adv_state_desc_t) :: st
     type(adv_tracer_desc_t), allocatable :: td(:)
     character(kind=c_char, len=21), allocatable, target :: hs(:), vs(:), ls(:)
+    real(kind=WP), pointer :: helem(:,:), hnode(:,:), hnode_new(:,:), zbar_3d_n(:,:), Z_3d_n(:,:), zbar_n_bot(:)
+    real(kind=WP), pointer :: values(:,:), valuesAB(:,:), grad1(:,:,:), dh1(:,:), dv1(:,:)
     integer :: i, k, n, rc
-    integer(c_int) :: where
-
-    where = merge(ADV_DEVICE, ADV_HOST, use_device)
-    st%uv = c_loc(vel); st%w = c_loc(W); st%w_e = c_loc(WE); st%w_i = c_loc(WI)
-    st%helem = c_loc(mesh%helem); st%hnode = c_loc(mesh%hnode); st%hnode_new = c_loc(mesh%hnode_new)
-    st%zbar_3d_n = c_loc(mesh%zbar_3d_n); st%Z_3d_n = c_loc(mesh%Z_3d_n); st%zbar_n_bot = c_loc(mesh%zbar_n_bot)
-    st%use_wsplit = merge(1, 0, dynamics%use_wsplit)
-    call check(adv_ctx_set_state(adv_b200_ctx, st, where), partit)
 
     n = tr_last - tr_first + 1
+    if (n > 1 .and. .not. (present(grad_b) .and. present(dh_b) .and. present(dv_b))) then
+       if (partit%mype == 0) write(*,*) 'fesom_adv_b200: a batch of ', n, ' tracers needs per-tracer work arrays ', &
+                                        '(grad_b, dh_b, dv_b): tracers%work holds one set only (MOD_TRACER.F90:36,64)'
+       call par_ex(partit%MPI_COMM_FESOM, partit%mype, 1)
+    end if
+
+    helem => mesh%helem; hnode => mesh%hnode; hnode_new => mesh%hnode_new
+    zbar_3d_n => mesh%zbar_3d_n; Z_3d_n => mesh%Z_3d_n; zbar_n_bot => mesh%zbar_n_bot
+    st%uv = ADV_ADDR(vel); st%w = ADV_ADDR(W); st%w_e = ADV_ADDR(WE); st%w_i = ADV_ADDR(WI)
+    st%helem = ADV_ADDR(helem); st%hnode = ADV_ADDR(hnode); st%hnode_new = ADV_ADDR(hnode_new)
+    st%zbar_3d_n = ADV_ADDR(zbar_3d_n); st%Z_3d_n = ADV_ADDR(Z_3d_n); st%zbar_n_bot = ADV_ADDR(zbar_n_bot)
+    st%use_wsplit = merge(1, 0, dynamics%use_wsplit)
+    ! once per model step: a repeated call with the same mstep and the same arrays is a no-op
+    call check(adv_ctx_set_state_step(adv_b200_ctx, st, ADV_WHERE, int(mstep, c_int64_t)), partit)
+
     allocate(td(n), hs(n), vs(n), ls(n))
     do k = 1, n
        i = tr_first + k - 1
        hs(k) = trim(tracers%data(i)%tra_adv_hor)//c_null_char
        vs(k) = trim(tracers%data(i)%tra_adv_ver)//c_null_char
        ls(k) = trim(tracers%data(i)%tra_adv_lim)//c_null_char
-       td(k)%values   = c_loc(tracers%data(i)%values)
-       td(k)%valuesAB = c_loc(tracers%data(i)%valuesAB)
-       ! one edge_up_dn_grad / del_ttf_adv* work array exists per t_tracer in the reference
-       ! (MOD_TRACER.F90:36,64); a batched host keeps one per tracer of the batch
-       td(k)%edge_up_dn_grad  = c_loc(tracers%work%edge_up_dn_grad)
-       td(k)%del_ttf_advhoriz = c_loc(tracers%work%del_ttf_advhoriz)
-       td(k)%del_ttf_advvert  = c_loc(tracers%work%del_ttf_advvert)
+       values => tracers%data(i)%values; valuesAB => tracers%data(i)%valuesAB
+       td(k)%values   = ADV_ADDR(values)
+       td(k)%valuesAB = ADV_ADDR(valuesAB)
+       if (n == 1 .and. .not. present(grad_b)) then
+          grad1 => tracers%work%edge_up_dn_grad
+          dh1 => tracers%work%del_ttf_advhoriz; dv1 => tracers%work%del_ttf_advvert
+       else
+          grad1 => grad_b(:,:,:,k)                    ! contiguous: the tracer index is the last one
+          dh1 => dh_b(:,:,k); dv1 => dv_b(:,:,k)
+       end if
+       td(k)%edge_up_dn_grad  = ADV_ADDR(grad1)
+       td(k)%del_ttf_advhoriz = ADV_ADDR(dh1)
+       td(k)%del_ttf_advvert  = ADV_ADDR(dv1)
        td(k)%tra_adv_hor = c_loc(hs(k)); td(k)%tra_adv_ver = c_loc(vs(k)); td(k)%tra_adv_lim = c_loc(ls(k))
        td(k)%tra_adv_ph = tracers%data(i)%tra_adv_ph
        td(k)%tra_adv_pv = tracers%data(i)%tra_adv_pv
     end do
-    rc = adv_do_oce_adv_tra(adv_b200_ctx, real(dt, c_double), int(n, c_int), td, where)
+#ifdef ENABLE_OPENACC
+    ! the operands may still be in flight on the OpenACC queues: order the library's stream behind them
+    !$ACC WAIT
+#endif
+    rc = adv_do_oce_adv_tra(adv_b200_ctx, real(dt, c_double), int(n, c_int), td, ADV_WHERE)
     call check(rc, partit)
     deallocate(td, hs, vs, ls)
   end subroutine do_oce_adv_tra_b200_batch
@@ -276,7 +369,8 @@ end module oce_adv_tra_b200
 
 !===============================================================================
 ! The reference's seam, unchanged: same external procedure name and argument list as
-! src/oce_adv_tra_driver.F90:46.  One tracer per call, like the reference.
+! src/oce_adv_tra_driver.F90:46.  One tracer per call, like the reference; the state upload and the
+! volume flux are shared by the calls of one model step (mstep).
 !===============================================================================
 subroutine do_oce_adv_tra(dt, vel, w, wi, we, tr_num, dynamics, tracers, partit, mesh)
   use MOD_MESH
@@ -292,18 +386,9 @@ subroutine do_oce_adv_tra(dt, vel, w, wi, we, tr_num, dynamics, tracers, partit,
   type(t_mesh),   intent(in),    target :: mesh
   type(t_tracer), intent(inout), target :: tracers
   type(t_dyn),    intent(inout), target :: dynamics
-  real(kind=WP),  intent(in)            :: vel(2, mesh%nl-1, partit%myDim_elem2D+partit%eDim_elem2D)
+  real(kind=WP),  intent(in), target    :: vel(2, mesh%nl-1, partit%myDim_elem2D+partit%eDim_elem2D)
   real(kind=WP),  intent(in), target    :: W(mesh%nl,    partit%myDim_nod2D+partit%eDim_nod2D)
   real(kind=WP),  intent(in), target    :: WI(mesh%nl,   partit%myDim_nod2D+partit%eDim_nod2D)
   real(kind=WP),  intent(in), target    :: WE(mesh%nl,   partit%myDim_nod2D+partit%eDim_nod2D)
-#ifdef ENABLE_OPENACC
-  ! operands live in the enclosing `!$ACC DATA` region (fesom.F90:71-83 / fesom_module.F90:759-805)
-  !$ACC HOST_DATA USE_DEVICE(vel, W, WI, WE, mesh%helem, mesh%hnode, mesh%hnode_new, mesh%zbar_3d_n, mesh%Z_3d_n) &
-  !$ACC           USE_DEVICE(tracers%data(tr_num)%values, tracers%data(tr_num)%valuesAB) &
-  !$ACC           USE_DEVICE(tracers%work%edge_up_dn_grad, tracers%work%del_ttf_advhoriz, tracers%work%del_ttf_advvert)
-  call do_oce_adv_tra_b200_batch(dt, vel, W, WI, WE, tr_num, tr_num, dynamics, tracers, partit, mesh, .true.)
-  !$ACC END HOST_DATA
-#else
-  call do_oce_adv_tra_b200_batch(dt, vel, W, WI, WE, tr_num, tr_num, dynamics, tracers, partit, mesh, .false.)
-#endif
+  call do_oce_adv_tra_b200_batch(dt, vel, W, WI, WE, tr_num, tr_num, dynamics, tracers, partit, mesh)
 end subroutine do_oce_adv_tra

@@ -121,7 +121,21 @@ int adv_ctx_comm_init(adv_ctx_t *ctx, const char id[128]);
 int adv_ctx_comm_init_local(adv_ctx_t *const *ctxs, int n);
 
 /* --- per step ------------------------------------------------------------------------------- */
+/* Hands over the state of a model step.  HOST pointers: uploaded now (asynchronously; the arrays are page-locked
+ * with cudaHostRegister the first time they are seen, see adv_ctx_set_host_register).  DEVICE pointers: used in
+ * place.  RULE: the volume flux Q(nz,edge) derived from uv/helem is cached from the first tracer call after
+ * adv_ctx_set_state until the next adv_ctx_set_state[_step]; a caller that changes uv/helem/w... -- also in place
+ * on the device -- MUST call adv_ctx_set_state again before the next adv_do_oce_adv_tra (with DEVICE pointers the
+ * call copies nothing). */
 int adv_ctx_set_state(adv_ctx_t *ctx, const adv_state_desc_t *st, int where);
+/* Same with the model's step counter (mstep, src/oce_modules.F90:23): a repeated call with the same `step`, the
+ * same `where` and the same pointers is a no-op.  The reference refreshes the state once per step
+ * (src/oce_ale_tracer.F90:260-262) and then calls do_oce_adv_tra once per tracer (:280-312); the drop-in wrapper
+ * of that signature calls this function every time, so that upload and Q are shared by the tracer loop. */
+int adv_ctx_set_state_step(adv_ctx_t *ctx, const adv_state_desc_t *st, int where, int64_t step);
+/* on = 0: never page-lock the caller's HOST arrays (default 1: cudaHostRegister on first use, undone by
+ * adv_ctx_destroy; ranges that are already pinned are left alone). */
+int adv_ctx_set_host_register(adv_ctx_t *ctx, int on);
 
 /* Replaces `do_oce_adv_tra(dt, vel, w, wi, we, tr_num, dynamics, tracers, partit, mesh)`
  * (src/oce_adv_tra_driver.F90:46-490) for a BATCH of ntr tracers (ntr = 1 reproduces one Fortran

@@ -255,3 +255,73 @@ def vert_vel_ale_core(rank: "OracleRank") -> np.ndarray:
     out = np.zeros((m.Nh, m.nl), np.float64)
     L_.ora_vert_vel_ale_core(C.byref(rank.cmesh), _dp(rank.keep["uv"]), _dp(out))
     return out
+
+
+# ---- memory-lean single-rank driver with an exchange callback (bench.py parity leg) ---------------
+XCHG = C.CFUNCTYPE(None, C.c_void_p, c_dp, C.c_int)
+
+
+class LeanOracle:
+    """ora_do_oce_adv_tra for one rank, one tracer at a time: the mesh, the state and ONE set of work arrays are
+    held (AUX aliases the tracer's edge_up_dn_grad, as the reference does, oce_adv_tra_driver.F90:383-384), so a
+    3.0M-node x 70-layer rank needs ~40 words per (node, layer) instead of ~70.  ``exchange(field, nlev)``: the
+    rank's exchange_nod3D (None on one rank); ``field`` is the (Nh, nlev) NumPy view of the C array."""
+
+    def __init__(self, mesh, state_np: dict, nboundary_lay, use_wsplit: bool = False, fast: bool = False):
+        m = mesh
+        self.m = m
+        L, nl, Nh, N, E = m.L, m.nl, m.Nh, m.N, m.E
+        k = self.keep = {}
+        ints = ("edges", "edge_tri", "elem2D_nodes", "nod_in_elem2D", "nod_in_elem2D_num", "nlevels", "ulevels",
+                "nlevels_nod2D", "ulevels_nod2D")
+        for name in ints:
+            k[name] = np.ascontiguousarray(getattr(m, name), dtype=np.int32)
+        for name in ("edge_cross_dxdy", "edge_dxdy", "elem_cos", "area", "areasvol"):
+            k[name] = np.ascontiguousarray(getattr(m, name), dtype=np.float64)
+        for name in ("helem", "hnode", "hnode_new", "zbar_3d_n", "Z_3d_n", "zbar_n_bot", "uv", "w", "w_e", "w_i"):
+            k[name] = np.ascontiguousarray(state_np[name], dtype=np.float64)
+        k["nboundary_lay"] = np.ascontiguousarray(nboundary_lay, dtype=np.int32)
+        om = OraMesh(nl=nl, myDim_nod2D=N, eDim_nod2D=m.eDim_nod2D, myDim_elem2D=m.T, eDim_elem2D=m.eDim_elem2D,
+                     myDim_edge2D=E, nod_in_elem_ld=k["nod_in_elem2D"].shape[1])
+        for name in ints:
+            setattr(om, name, _ip(k[name]))
+        for name in ("edge_cross_dxdy", "edge_dxdy", "elem_cos", "area", "areasvol", "helem", "hnode", "hnode_new",
+                     "zbar_3d_n", "Z_3d_n", "zbar_n_bot"):
+            setattr(om, name, _dp(k[name]))
+        self.cmesh = om
+        wk = OraWork()
+        for name, shape in (("fct_LO", (Nh, L)), ("adv_flux_hor", (E, L)), ("adv_flux_ver", (N, nl)),
+                            ("fct_ttf_min", (Nh, L)), ("fct_ttf_max", (Nh, L)), ("fct_plus", (Nh, L)),
+                            ("fct_minus", (Nh, L)), ("tvert_max", (Nh, L)), ("tvert_min", (Nh, L))):
+            k[name] = np.zeros(shape)
+            setattr(wk, name, _dp(k[name]))
+        wk.nboundary_lay = _ip(k["nboundary_lay"])
+        self.cwork = wk
+        self.use_wsplit = int(bool(use_wsplit))
+        self.L_ = lib(fast)
+        self.L_.ora_do_oce_adv_tra.argtypes = [C.POINTER(OraMesh), C.POINTER(OraWork), C.c_double, c_dp, c_dp, c_dp, c_dp,
+                                               C.c_int, c_dp, c_dp, c_dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                               c_dp, c_dp, XCHG, C.c_void_p]
+
+    def run_tracer(self, values, valuesAB, grad, hor: str, ver: str, lim: str, ph: float, pv: float, dt: float,
+                   dttf_h=None, dttf_v=None, exchange=None):
+        """One do_oce_adv_tra.  ``grad`` (E, L, 4) is CLOBBERED (it doubles as the FCT scratch AUX); may be None for
+        UPW1.  Returns (dttf_h, dttf_v), accumulated into the arrays passed in (zeros by default)."""
+        m, k = self.m, self.keep
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        vab = np.ascontiguousarray(valuesAB, dtype=np.float64)
+        if grad is None:
+            grad = np.zeros((m.E, m.L, 4))
+        assert grad.dtype == np.float64 and grad.flags.c_contiguous and grad.shape == (m.E, m.L, 4)
+        self.cwork.AUX = _dp(grad)
+        dh = np.zeros((m.Nh, m.L)) if dttf_h is None else dttf_h
+        dv = np.zeros((m.Nh, m.L)) if dttf_v is None else dttf_v
+        Nh = m.Nh
+
+        def _cb(user, p, nlev):
+            exchange(np.ctypeslib.as_array(p, shape=(Nh, nlev)), nlev)
+        cb = XCHG(_cb) if exchange is not None else C.cast(None, XCHG)
+        self.L_.ora_do_oce_adv_tra(C.byref(self.cmesh), C.byref(self.cwork), float(dt), _dp(k["uv"]), _dp(k["w"]),
+                                   _dp(k["w_i"]), _dp(k["w_e"]), self.use_wsplit, _dp(v), _dp(vab), _dp(grad),
+                                   HOR[hor], VER[ver], LIM.get(lim, 0), float(ph), float(pv), _dp(dh), _dp(dv), cb, None)
+        return dh, dv

@@ -113,6 +113,43 @@ def test_host_pointer_call(pi_mesh):
     ctx.close()
 
 
+@pytest.mark.parametrize("host", [True, False])
+def test_reference_call_order_one_tracer_per_call(souf_mesh, host):
+    """The reference's own sequence (src/oce_ale_tracer.F90:260-312): state refreshed once per step, then
+    do_oce_adv_tra once PER TRACER.  The drop-in wrapper calls adv_ctx_set_state_step with the model's step counter
+    before every tracer: only the first call of a step uploads the state and computes the volume flux Q; a new step
+    number takes the new state.  HOST arrays are pageable here (page-locked by the library on first use)."""
+    from fesom2_b200.driver import AdvB200
+    from fesom2_b200 import fields as F
+    mesh = souf_mesh
+    st, trs, nb, dt = make_case(mesh, 3, "MFCT", "QR4C", "FCT")
+    ora = run_oracle(mesh, st, trs, nb, dt)
+    st2 = F.OceanState(**{k: (v.clone() if torch.is_tensor(v) else v) for k, v in st.__dict__.items()})
+    st2.uv *= 0.5
+    st2.w *= 0.5
+    st2.w_e *= 0.5
+    ora2 = run_oracle(mesh, st2, trs, nb, dt)
+    dev = "cpu" if host else torch.device("cuda:0")
+    if host:
+        st_d, st2_d, trs_d = st, st2, trs
+    else:
+        from common import to_device
+        st_d, trs_d = to_device(st, trs, dev)
+        st2_d, _ = to_device(st2, [], dev)
+    ctx = AdvB200(mesh, nb, max_tracers=1)
+    for step, (s_d, ref) in enumerate(((st_d, ora), (st2_d, ora2))):
+        n0 = ctx.launch_count
+        for k, t in enumerate(trs_d):
+            dh = [torch.zeros((mesh.Nh, mesh.L), dtype=torch.float64, device=dev)]
+            dv = [torch.zeros((mesh.Nh, mesh.L), dtype=torch.float64, device=dev)]
+            ctx.set_state(s_d, step=step + 1)
+            ctx.do_oce_adv_tra(dt, [t], dh, dv)
+            assert np.array_equal(dh[0].cpu().numpy(), ref.dttf_h[k]), (step, k)
+            assert np.array_equal(dv[0].cpu().numpy(), ref.dttf_v[k]), (step, k)
+        assert ctx.launch_count - n0 == 3 * 4      # four launches per tracer call: Q is fused into the first edge kernel
+    ctx.close()
+
+
 def test_accumulates_into_del_ttf(small_mesh):
     """do_oce_adv_tra ACCUMULATES into del_ttf_advhoriz/advvert (driver :535,:556,:607)"""
     from fesom2_b200.driver import AdvB200

@@ -152,3 +152,20 @@ def test_bench_size_batch_position_is_irrelevant(bench_case):
     assert torch.equal(dh_a[0], dh_b[1]) and torch.equal(dv_a[0], dv_b[1])
     assert torch.equal(dh_a[1], dh_b[0]) and torch.equal(dv_a[1], dv_b[0])
     assert torch.equal(dh_a[0], dh_c[0]) and torch.equal(dv_a[0], dv_c[0])
+
+
+def test_bench_size_against_the_oracle(bench_case):
+    """The measured workload itself (config 4 per-GPU share, 376k nodes x 70 layers, T+S MFCT + QR4C + FCT): one step
+    against the C oracle (serial, memory-lean driver: ~10 s), bit for bit on every node."""
+    from oracle import oracle_py as O
+    g, st, dt, nb, tri = bench_case
+    dev = torch.device("cuda:0")
+    trs = [F.make_tracers_kind(g, k, dev, tri)[0] for k in range(2)]
+    ctx, dh, dv = _step(g, st, nb, dt, trs)
+    lo = O.LeanOracle(g, {k: v.cpu().numpy() for k, v in st.__dict__.items() if torch.is_tensor(v)}, nb)
+    for k, t in enumerate(trs):
+        rh, rv = lo.run_tracer(t.values.cpu().numpy(), t.valuesAB.cpu().numpy(), t.edge_up_dn_grad.cpu().numpy(),
+                               t.tra_adv_hor, t.tra_adv_ver, t.tra_adv_lim, t.tra_adv_ph, t.tra_adv_pv, dt)
+        assert np.array_equal(dh[k].cpu().numpy(), rh)
+        assert np.array_equal(dv[k].cpu().numpy(), rv)
+    ctx.close()
