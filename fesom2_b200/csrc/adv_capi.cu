@@ -195,7 +195,6 @@ struct adv_ctx {
     bool host_register = true;                // page-lock ADV_HOST arrays on first use (adv_ctx_set_host_register)
     std::map<const void*, size_t> registered; // ranges this context registered (0 bytes: left alone)
     std::set<const void*> registered_foreign;
-    DevBuf<double> impl_cp, impl_tp;
     std::vector<Slot> slots;
     std::vector<std::unique_ptr<ChunkBuf>> cbufs;
     std::vector<TrLoc> trloc;
@@ -632,7 +631,6 @@ static int set_state_impl(adv_ctx_t* c, const adv_state_desc_t* st, int where)
         }
     }
     m.use_wsplit = st->use_wsplit ? 1 : 0;
-    if (m.use_wsplit && c->impl_cp.n == 0) { CU(c->impl_cp.alloc(L * m.N)); CU(c->impl_tp.alloc(L * m.N)); }
     c->state_set = true;
     c->q_valid = false;
     return ADV_OK;
@@ -959,11 +957,25 @@ static int run_batch(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr
         if (!ch.fct) run(PH_NOFCT, ch, multi ? rAllH : rAll);
     mark(1);
     if (any_fct) {
-        const bool overlap = multi && !m.use_wsplit;
-        // ---- phase 1: LO solution (boundary set first, then start exchange 1)
+        const bool overlap = multi;
+        // adv_tra_vert_impl on fct_LO (driver :320-333, use_wsplit only), same node range as the LO launch before it
+        auto vimpl = [&](int rid) {
+            if (!m.use_wsplit) return;
+            for (auto& ch : chunks) {
+                if (!ch.fct) continue;
+                const NodeRange r = node_range(c, rid, cpb);
+                if (r.count <= 0) continue;
+                const int nthr = r.cpb * m.L;
+                double* lo = c->cbufs[ch.buf]->lo.p;
+                if (ch.tb == 2) k_vert_impl<2><<<nblocks(r.count, r.cpb), nthr, (size_t)(3 + 2) * nthr * sizeof(double), sc>>>(m, lo, r, dt);
+                else k_vert_impl<1><<<nblocks(r.count, r.cpb), nthr, (size_t)(3 + 1) * nthr * sizeof(double), sc>>>(m, lo, r, dt);
+                ++c->launches;
+            }
+        };
         const int64_t bytes0 = c->halo_bytes_sent;
         if (overlap) {
             for (auto& ch : chunks) if (ch.fct) run(PH_N1, ch, rS);
+            vimpl(rS);
             CU(cudaEventRecord(c->ev_a, sc));
             CU(cudaStreamWaitEvent(sx, c->ev_a, 0));
             CU(cudaEventRecord(c->ev_x0[0], sx));
@@ -971,24 +983,13 @@ static int run_batch(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr
             CU(cudaEventRecord(c->ev_x1[0], sx));
             CU(cudaEventRecord(c->ev_b, sx));
             for (auto& ch : chunks) if (ch.fct) run(PH_N1, ch, rI);
+            vimpl(rI);
             CU(cudaEventRecord(c->ev_w0[0], sc));
             CU(cudaStreamWaitEvent(sc, c->ev_b, 0));
             CU(cudaEventRecord(c->ev_w1[0], sc));
         } else {
             for (auto& ch : chunks) if (ch.fct) run(PH_N1, ch, rAll);
-            if (m.use_wsplit) {
-                for (auto& ch : chunks)
-                    if (ch.fct)
-                        for (int t = 0; t < ch.tb; ++t) {
-                            k_vert_impl<<<(m.N + 127) / 128, 128, 0, sc>>>(m, c->cbufs[ch.buf]->lo.p, ch.tb, t, c->impl_cp.p, c->impl_tp.p, dt);
-                            ++c->launches;
-                        }
-            }
-            if (multi) {   // nothing to overlap with: the whole exchange is exposed
-                CU(cudaEventRecord(c->ev_x0[0], sc)); CU(cudaEventRecord(c->ev_w0[0], sc));
-                if (int rc = halo_exchange(c, HALO_NOD, sc, (int)f1.size(), f1.data(), s1.data(), nullptr, n1.data())) return rc;
-                CU(cudaEventRecord(c->ev_x1[0], sc)); CU(cudaEventRecord(c->ev_w1[0], sc));
-            }
+            vimpl(rAll);
         }
         mark(2);
         // ---- phase 2: bounds + R+/R- (boundary set first, then start exchange 2)
@@ -1176,6 +1177,29 @@ int adv_exchange_elem(adv_ctx_t* c, int nfields, double* const* fields, int nwor
     if (!c->comm && !c->lc) return fail(ADV_ESTATE, "adv_ctx_comm_init was not called");
     if (!c->grad_mesh_set || !c->elem_halo_set) return fail(ADV_ESTATE, "adv_ctx_set_gradient_mesh with com_elem2D_full has not been called");
     return exchange_fields(c, HALO_ELEM, nfields, fields, nwords);
+}
+
+int adv_vert_vel_ale(adv_ctx_t* c, double dt, int use_wsplit, double wsplit_maxcfl, double* w, double* w_e, double* w_i, double* cfl_z)
+{
+    if (!c || !w || !w_e || !w_i) return fail(ADV_EINVAL, "adv_vert_vel_ale: null argument");
+    if (!c->state_set) return fail(ADV_ESTATE, "adv_ctx_set_state has not been called");
+    if (c->npes > 1 && !c->comm && !c->lc) return fail(ADV_ESTATE, "adv_ctx_comm_init was not called");
+    CU(cudaSetDevice(c->device));
+    const MeshDev& m = c->m;
+    const int cpb = cols_per_block(m.L);
+    const NodeRange rAll{nullptr, 0, m.N, cpb, 0, 0};
+    k_vert_vel_ale<<<nblocks(m.N, cpb), cpb * m.L, (size_t)cpb * m.L * sizeof(double), c->s_comp>>>(m, rAll, w);
+    ++c->launches;
+    CU(cudaGetLastError());
+    if (c->npes > 1) {                                            // exchange_nod(Wvel), src/oce_ale.F90:2654
+        double* f[1] = {w};
+        if (int rc = exchange_fields(c, HALO_NOD, 1, f, m.nl)) return rc;
+    }
+    const size_t n = (size_t)m.Nh * m.nl;
+    k_cflz_wsplit<<<(unsigned)((n + 255) / 256), 256, 0, c->s_comp>>>(m, dt, use_wsplit ? 1 : 0, wsplit_maxcfl, w, w_e, w_i, cfl_z);
+    ++c->launches;
+    CU(cudaGetLastError());
+    return ADV_OK;
 }
 
 int adv_update_values(adv_ctx_t* c, int ntr, double* const* values, const double* const* dh, const double* const* dv)

@@ -943,71 +943,187 @@ __global__ void ADV_N1_BOUNDS k_node_lo(MeshDev m, Chunk<TB> b, NodePart r, doub
 }
 
 // ----------------------------------------------------------------------------------------------
-// adv_tra_vert_impl (oce_adv_tra_ver.F90:120-236): one thread per owned column, Thomas algorithm.
-// cp/tp are kept in the (L,N) scratch arrays `cp`,`tp`; ttf is tracer t of a tb-interleaved array.
+// adv_tra_vert_impl (oce_adv_tra_ver.F90:120-236) on the TB tracer-interleaved fct_LO columns of a chunk.
+// Thread = (column, layer) like the other node kernels, three phases:
+//   A  every thread evaluates the tridiagonal coefficients a, b, c of its layer (tracer-independent) and the
+//      right-hand sides tr[t] from coalesced loads and parks them in shared memory;
+//   B  ONE thread per column runs the Thomas recurrences -- the forward elimination cp(nz) = c/(b - cp(nz-1) a),
+//      tp(nz) = (tr - tp(nz-1) a)/(b - cp(nz-1) a) and the back substitution -- in the reference's order: the
+//      chain is serial by definition and any reassociation (cyclic reduction) would change the rounding;
+//      cp is shared by the TB tracers;
+//   C  every thread adds its layer's increment to fct_LO with a coalesced store.
+// Replaces round 1's one-thread-per-column kernel (stride-L accesses, scratch arrays in global memory).
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_vert_impl(MeshDev m, double* __restrict__ ttf, int tb, int t,
-                                                   double* __restrict__ cp, double* __restrict__ tp, double dt)
+template <int TB>
+__global__ void __launch_bounds__(kBlock) k_vert_impl(MeshDev m, double* __restrict__ lo, NodeRange r, double dt)
 {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= m.N) return;
-    const int L = m.L, nl = m.nl;
-    const uchar4 lv = m.node_lev[n];
-    const int nzmin = lv.x, nzmax = lv.y;
-    const double* W = m.wi + (size_t)n * nl;
-    const double* area = m.area + (size_t)n * nl;
-    const double* avol = m.areasvol + (size_t)n * nl;
-    const double* hnn = m.hnode_new + (size_t)n * L;
-    double* T = ttf + (size_t)n * L * tb + t;   // tracer-interleaved fct_LO
-    double* CP = cp + (size_t)n * L;
-    double* TP = tp + (size_t)n * L;
-    const double zinv = 1.0 * dt;
-#define AW(k) W[(k)-1]
-#define AA(k) area[(k)-1]
-#define AV(k) avol[(k)-1]
-#define AH(k) hnn[(k)-1]
-#define AT(k) T[((k)-1) * tb]
-    double cp_prev = 0.0, tp_prev = 0.0;
-    for (int nz = nzmin; nz <= nzmax - 1; ++nz) {
-        double a, bb, c, tr, v_adv;
-        if (nz == nzmin) {                                      // :154-170, :198-200
-            a = 0.0;
-            v_adv = zinv * AA(nz) / AV(nz);
-            bb = AH(nz) + AW(nz) * v_adv;
-            v_adv = zinv * AA(nz + 1) / AV(nz);
-            bb = bb - dmin(0.0, AW(nz + 1)) * v_adv;
-            c = -dmax(0.0, AW(nz + 1)) * v_adv;
-            tr = -(bb - AH(nz)) * AT(nz) - c * AT(nz + 1);
-        } else if (nz <= nzmax - 2) {                           // :174-183, :202-205
-            v_adv = zinv * AA(nz) / AV(nz);
-            a = dmin(0.0, AW(nz)) * v_adv;
-            bb = AH(nz) + dmax(0.0, AW(nz)) * v_adv;
-            v_adv = zinv * AA(nz + 1) / AV(nz);
-            bb = bb - dmin(0.0, AW(nz + 1)) * v_adv;
-            c = -dmax(0.0, AW(nz + 1)) * v_adv;
-            tr = -a * AT(nz - 1) - (bb - AH(nz)) * AT(nz) - c * AT(nz + 1);
-        } else {                                                // :187-195, :206-208
-            v_adv = zinv * AA(nz) / AV(nz);
-            a = dmin(0.0, AW(nz)) * v_adv;
-            bb = AH(nz) + dmax(0.0, AW(nz)) * v_adv;
-            c = 0.0;
-            tr = -a * AT(nz - 1) - (bb - AH(nz)) * AT(nz);
+    extern __shared__ double sm[];            // [3 + TB][blockDim]: a, b, c (later cp), tr[t] (later tp[t], then the increment)
+    const int L = m.L, nl = m.nl, nthr = blockDim.x, tid = threadIdx.x;
+    const NodeThread th = node_thread(m, r);
+    const int n = th.n, nz0 = th.nz0, nz = nz0 + 1, nzmin = th.nzmin, nzmax = th.nzmax;   // nzmax = nlevels_nod2D
+    const bool valid = th.active && n < m.N && nz >= nzmin && nz <= nzmax - 1;
+    double* s_a = sm; double* s_b = sm + nthr; double* s_c = sm + 2 * nthr; double* s_t = sm + 3 * nthr;
+    const size_t oL = (size_t)n * L + nz0, cN = (size_t)n * nl + nz0;
+    if (valid) {
+        const double zinv = 1.0 * dt;
+        const double hn = __ldg(&m.hnode_new[oL]), av = __ldg(&m.areasvol[cN]);
+        const double w0 = __ldg(&m.wi[cN]), a0 = __ldg(&m.area[cN]);
+        double a, bb, c;
+        double tm[TB], t0[TB], tp[TB], tr[TB];
+#pragma unroll
+        for (int t = 0; t < TB; ++t) {
+            t0[t] = lo[oL * TB + t];
+            tm[t] = nz > nzmin ? lo[(oL - 1) * TB + t] : 0.0;
+            tp[t] = nz <= nzmax - 2 ? lo[(oL + 1) * TB + t] : 0.0;
         }
-        if (nz == nzmin) { cp_prev = c / bb; tp_prev = tr / bb; }                       // :211-213
-        else { const double mm = bb - cp_prev * a; cp_prev = c / mm; tp_prev = (tr - tp_prev * a) / mm; }
-        CP[nz - 1] = cp_prev; TP[nz - 1] = tp_prev;
+        if (nz == nzmin) {                                      // :154-170, :198-200
+            const double w1 = __ldg(&m.wi[cN + 1]), a1 = __ldg(&m.area[cN + 1]);
+            a = 0.0;
+            double v_adv = zinv * a0 / av;
+            bb = hn + w0 * v_adv;
+            v_adv = zinv * a1 / av;
+            bb = bb - dmin(0.0, w1) * v_adv;
+            c = -dmax(0.0, w1) * v_adv;
+#pragma unroll
+            for (int t = 0; t < TB; ++t) tr[t] = -(bb - hn) * t0[t] - c * tp[t];
+        } else if (nz <= nzmax - 2) {                           // :174-183, :202-205
+            const double w1 = __ldg(&m.wi[cN + 1]), a1 = __ldg(&m.area[cN + 1]);
+            double v_adv = zinv * a0 / av;
+            a = dmin(0.0, w0) * v_adv;
+            bb = hn + dmax(0.0, w0) * v_adv;
+            v_adv = zinv * a1 / av;
+            bb = bb - dmin(0.0, w1) * v_adv;
+            c = -dmax(0.0, w1) * v_adv;
+#pragma unroll
+            for (int t = 0; t < TB; ++t) tr[t] = -a * tm[t] - (bb - hn) * t0[t] - c * tp[t];
+        } else {                                                // :187-195, :206-208
+            const double v_adv = zinv * a0 / av;
+            a = dmin(0.0, w0) * v_adv;
+            bb = hn + dmax(0.0, w0) * v_adv;
+            c = 0.0;
+#pragma unroll
+            for (int t = 0; t < TB; ++t) tr[t] = -a * tm[t] - (bb - hn) * t0[t];
+        }
+        s_a[tid] = a; s_b[tid] = bb; s_c[tid] = c;
+#pragma unroll
+        for (int t = 0; t < TB; ++t) s_t[t * nthr + tid] = tr[t];
     }
-    double trn = TP[nzmax - 2];                                                         // :224
-    AT(nzmax - 1) = AT(nzmax - 1) + trn;
-    for (int nz = nzmax - 2; nz >= nzmin; --nz) {                                       // :227-235
-        trn = TP[nz - 1] - CP[nz - 1] * trn;
-        AT(nz) = AT(nz) + trn;
+    __syncthreads();
+    if (valid && nz == nzmin) {                                 // the column's serial part
+        const int nlay = nzmax - nzmin;                         // layers nzmin .. nzmax-1 live at tid .. tid+nlay-1
+        double cp_prev = 0.0, tp_prev[TB];
+#pragma unroll
+        for (int t = 0; t < TB; ++t) tp_prev[t] = 0.0;
+        for (int k = 0; k < nlay; ++k) {                        // :211-221
+            const double a = s_a[tid + k], bb = s_b[tid + k], c = s_c[tid + k];
+            if (k == 0) {
+                cp_prev = c / bb;
+#pragma unroll
+                for (int t = 0; t < TB; ++t) tp_prev[t] = s_t[t * nthr + tid] / bb;
+            } else {
+                const double mm = bb - cp_prev * a;
+                cp_prev = c / mm;
+#pragma unroll
+                for (int t = 0; t < TB; ++t) tp_prev[t] = (s_t[t * nthr + tid + k] - tp_prev[t] * a) / mm;
+            }
+            s_c[tid + k] = cp_prev;
+#pragma unroll
+            for (int t = 0; t < TB; ++t) s_t[t * nthr + tid + k] = tp_prev[t];
+        }
+#pragma unroll
+        for (int t = 0; t < TB; ++t) {                          // :224-235: the last layer's increment is tp itself
+            double trn = s_t[t * nthr + tid + nlay - 1];
+            for (int k = nlay - 2; k >= 0; --k) {
+                trn = s_t[t * nthr + tid + k] - s_c[tid + k] * trn;
+                s_t[t * nthr + tid + k] = trn;
+            }
+        }
     }
-#undef AW
-#undef AA
-#undef AV
-#undef AH
-#undef AT
+    __syncthreads();
+    if (valid) {
+#pragma unroll
+        for (int t = 0; t < TB; ++t) lo[oL * TB + t] = lo[oL * TB + t] + s_t[t * nthr + tid];
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// vert_vel_ale, continuity part for the linear free surface (src/oce_ale.F90:2164-2310, no Fer_GM):
+// the reference scatters, edge after edge, the transport through the two half-edges (element 1, then element 2)
+// into Wvel of both end nodes, sums each column bottom-up and divides by the cell area.  Here: an ordered gather
+// over the node's edge slots (ascending edge = the serial scatter order; per edge first the element-1 term, then
+// the element-2 term, each its own addition), the bottom-up running sum by one thread per column (a serial
+// chain, kept in the reference's order), the division in parallel.  Owned columns; every other entry of the
+// column is zeroed like :2165.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_vert_vel_ale(MeshDev m, NodeRange r, double* __restrict__ W)
+{
+    extern __shared__ double sm[];            // [blockDim]
+    const int L = m.L, nl = m.nl, tid = threadIdx.x;
+    const NodeThread th = node_thread(m, r);
+    const int n = th.n, nz0 = th.nz0, nz = nz0 + 1, nzmin = th.nzmin, nzmax = th.nzmax - 1;   // nzmax: last layer
+    const bool wet = th.active && nz >= nzmin && nz <= nzmax;
+    double acc = 0.0;
+    if (wet) {
+        const int4* ell = m.ne_ell + (size_t)n * m.ell_w;
+        for (int j = 0; j < th.deg; ++j) {
+            const int4 ent = __ldg(&ell[j]);
+            const int e = ent.x;
+            const bool second = (ent.z >> 16) & 1;
+            const uchar4 lv = __ldg(&m.edge_lev[e]);
+            const int2 el = __ldg(&m.edge_el[e]);
+            const double2 cr12 = __ldg(reinterpret_cast<const double2*>(&m.edge_cross[e]));
+            const double2 cr34 = __ldg(reinterpret_cast<const double2*>(&m.edge_cross[e]) + 1);
+            if (nz >= (int)lv.x && nz <= (int)lv.y) {                                   // :2178-2202
+                const unsigned o = (unsigned)el.x * L + nz0;
+                const double2 uv = __ldg(reinterpret_cast<const double2*>(m.uv) + o);
+                const double c1 = (uv.y * cr12.x - uv.x * cr12.y) * __ldg(&m.helem[o]);
+                acc = second ? acc - c1 : acc + c1;
+            }
+            if (el.y >= 0 && nz >= (int)lv.z && nz <= (int)lv.w) {                      // :2213-2240
+                const unsigned o = (unsigned)el.y * L + nz0;
+                const double2 uv = __ldg(reinterpret_cast<const double2*>(m.uv) + o);
+                const double c1 = -(uv.y * cr34.x - uv.x * cr34.y) * __ldg(&m.helem[o]);
+                acc = second ? acc - c1 : acc + c1;
+            }
+        }
+    }
+    sm[tid] = acc;
+    __syncthreads();
+    if (wet && nz == nzmin) {                                   // :2277-2286: W(nz) = W(nz) + W(nz+1), bottom-up
+        double below = 0.0;
+        for (int k = nzmax - nzmin; k >= 0; --k) { below = sm[tid + k] + below; sm[tid + k] = below; }
+    }
+    __syncthreads();
+    if (!th.active) return;
+    const size_t cN = (size_t)n * nl + nz0;
+    W[cN] = wet ? sm[tid] / __ldg(&m.area[cN]) : 0.0;           // :2301-2308
+    if (nz0 == L - 1) W[cN + 1] = 0.0;                          // interface nl
+}
+
+// compute_CFLz (src/oce_ale.F90:2933-2952, without the diagnostic print) and compute_Wvel_split (:3033-3047):
+// one thread per (interface, node) over all myDim+eDim columns.  CFL_z(nz) = c2 of the layer above, then + c1 of
+// the layer below, in that order; W_e / W_i are written for nzmin..nlevels_nod2D only, like the reference.
+__global__ void __launch_bounds__(256) k_cflz_wsplit(MeshDev m, double dt, int use_wsplit, double maxcfl, const double* __restrict__ W,
+                                                     double* __restrict__ We, double* __restrict__ Wi, double* __restrict__ cflz)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)m.Nh * m.nl) return;
+    const int n = (int)(idx / m.nl), nz = (int)(idx - (size_t)n * m.nl) + 1;
+    const uchar4 lv = __ldg(&m.node_lev[n]);
+    const int nzmin = lv.x, nlev = lv.y, nzmax = nlev - 1;
+    const double w = W[idx];
+    double cfl = 0.0;
+    if (nz - 1 >= nzmin && nz - 1 <= nzmax) cfl = fabs(w * dt / __ldg(&m.hnode_new[(size_t)n * m.L + nz - 2]));            // c2 of layer nz-1
+    if (nz >= nzmin && nz <= nzmax) cfl = cfl + fabs(w * dt / __ldg(&m.hnode_new[(size_t)n * m.L + nz - 1]));              // + c1 of layer nz
+    if (cflz) cflz[idx] = cfl;
+    if (nz < nzmin || nz > nlev) return;
+    double we = w, wi = 0.0;
+    if (use_wsplit && cfl > maxcfl) {
+        const double dd = dmax(cfl - maxcfl, 0.0) / dmax(maxcfl, 1.e-12);
+        we = (1.0 / (1.0 + dd)) * w;
+        wi = (dd / (1.0 + dd)) * w;
+    }
+    We[idx] = we; Wi[idx] = wi;
 }
 
 // ----------------------------------------------------------------------------------------------

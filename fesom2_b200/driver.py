@@ -71,7 +71,7 @@ class GradientMeshDesc(C.Structure):
 
 EXPORTS = ["adv_ctx_create", "adv_ctx_destroy", "adv_last_error", "adv_comm_unique_id",
            "adv_ctx_comm_init", "adv_ctx_comm_init_local", "adv_exchange_elem", "adv_ctx_halo_stats",
-           "adv_ctx_wait_for", "adv_ctx_signal", "adv_ctx_set_state_step", "adv_ctx_set_host_register", "adv_ctx_set_state", "adv_do_oce_adv_tra", "adv_do_oce_adv_tra_async",
+           "adv_ctx_wait_for", "adv_ctx_signal", "adv_vert_vel_ale", "adv_ctx_set_state_step", "adv_ctx_set_host_register", "adv_ctx_set_state", "adv_do_oce_adv_tra", "adv_do_oce_adv_tra_async",
            "adv_ctx_synchronize", "adv_exchange_nod", "adv_update_values", "adv_init_tracers_AB",
            "adv_ctx_set_gradient_mesh", "adv_tracer_gradient_elements", "adv_fill_up_dn_grad", "adv_ctx_get_work",
            "adv_ctx_launch_count", "adv_ctx_stream", "adv_ctx_last_elapsed_ms",
@@ -98,6 +98,7 @@ def load_library():
         L.adv_comm_unique_id.argtypes = [C.c_char_p]
         L.adv_ctx_comm_init.argtypes = [C.c_void_p, C.c_char_p]
         L.adv_ctx_set_state.argtypes = [C.c_void_p, C.POINTER(StateDesc), C.c_int]
+        L.adv_vert_vel_ale.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double, c_dp, c_dp, c_dp, c_dp]
         L.adv_ctx_set_state_step.argtypes = [C.c_void_p, C.POINTER(StateDesc), C.c_int, C.c_int64]
         L.adv_ctx_set_host_register.argtypes = [C.c_void_p, C.c_int]
         L.adv_do_oce_adv_tra.argtypes = [C.c_void_p, C.c_double, C.c_int, C.POINTER(TracerDesc), C.c_int]
@@ -283,6 +284,14 @@ class AdvB200:
         PA = c_dp * len(fields)
         self._after_torch()
         _check(self.lib.adv_exchange_nod(self.h, len(fields), PA(*[_ptr(f) for f in fields]), int(nlev)))
+        self._before_torch()
+
+    def vert_vel_ale(self, dt: float, use_wsplit: bool, wsplit_maxcfl: float, w, w_e, w_i, cfl_z=None):
+        """``vert_vel_ale`` continuity part (linfs) + exchange_nod(Wvel) + ``compute_CFLz`` + ``compute_Wvel_split``
+        (src/oce_ale.F90:2164-2310, :2654, :2906-3049) from the state's uv / helem / hnode_new; (Nh, nl) device tensors."""
+        self._after_torch()
+        _check(self.lib.adv_vert_vel_ale(self.h, float(dt), int(bool(use_wsplit)), float(wsplit_maxcfl), _ptr(w), _ptr(w_e),
+                                         _ptr(w_i), _ptr(cfl_z)))
         self._before_torch()
 
     def update_values(self, values: Sequence, dttf_h: Sequence, dttf_v: Sequence):

@@ -175,6 +175,16 @@ int adv_exchange_elem(adv_ctx_t *ctx, int nfields, double *const *fields, int nw
 int adv_update_values(adv_ctx_t *ctx, int ntr, double *const *values,
                       const double *const *del_ttf_advhoriz, const double *const *del_ttf_advvert);
 
+/* The vertical velocities the path consumes, for the linear free surface: the continuity
+ * part of `vert_vel_ale` (src/oce_ale.F90:2164-2310, which_ALE = 'linfs', no Fer_GM) on the owned nodes, its
+ * exchange_nod(Wvel) (:2654), `compute_CFLz` (:2906-2998 without the diagnostic print) and `compute_Wvel_split`
+ * (:3001-3049) on all myDim+eDim nodes: from uv / helem / hnode_new of the last adv_ctx_set_state to w, w_e, w_i and
+ * cfl_z (each (nl, Nh); cfl_z may be NULL).  dt = g_config dt, wsplit_maxcfl = dynamics%wsplit_maxcfl.  Entries the
+ * reference leaves alone in w_e / w_i stay untouched.  DEVICE pointers, asynchronous on the context's stream.
+ * The result becomes the path's input with the next adv_ctx_set_state. */
+int adv_vert_vel_ale(adv_ctx_t *ctx, double dt, int use_wsplit, double wsplit_maxcfl,
+                     double *w, double *w_e, double *w_i, double *cfl_z);
+
 /* The prologue of the tracer step, `init_tracers_AB(tr_num, tracers, partit, mesh)`
  * (src/oce_tracer_mod.F90:13-123) without its gradient calls, for ntr tracers: zeroes del_ttf /
  * del_ttf_advhoriz / del_ttf_advvert (each may be NULL), sets valuesAB from the Adams-Bashforth

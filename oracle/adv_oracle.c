@@ -935,3 +935,50 @@ void ora_find_up_downwind_triangles(int myDim_edge2D, const int *edges, const in
         }
     }
 }
+
+/* ====================================================================================================
+ * compute_CFLz (src/oce_ale.F90:2906-2998, without the diagnostic print) and compute_Wvel_split
+ * (src/oce_ale.F90:3001-3049) for all myDim+eDim nodes.  CFL_z, Wvel, Wvel_e, Wvel_i are (nl, Nh).
+ * ==================================================================================================== */
+void ora_compute_cflz(const ora_mesh_t *m, double dt, const double *Wvel, double *CFL_z)
+{
+    const int nl = m->nl, L = nl - 1;
+    const int Nh = m->myDim_nod2D + m->eDim_nod2D;
+#define C_W(nz, n) Wvel[(size_t)((n) - 1) * nl + ((nz) - 1)]
+#define C_C(nz, n) CFL_z[(size_t)((n) - 1) * nl + ((nz) - 1)]
+#define C_H(nz, n) m->hnode_new[(size_t)((n) - 1) * L + ((nz) - 1)]
+    for (int n = 1; n <= Nh; ++n)
+        for (int nz = 1; nz <= nl; ++nz) C_C(nz, n) = 0.0;                          /* :2933 */
+    for (int n = 1; n <= Nh; ++n) {                                                 /* :2939-2952 */
+        const int nzmin = m->ulevels_nod2D[n - 1], nzmax = m->nlevels_nod2D[n - 1] - 1;
+        for (int nz = nzmin; nz <= nzmax; ++nz) {
+            const double c1 = fabs(C_W(nz, n) * dt / C_H(nz, n));
+            const double c2 = fabs(C_W(nz + 1, n) * dt / C_H(nz, n));
+            C_C(nz, n) = C_C(nz, n) + c1;
+            C_C(nz + 1, n) = c2;
+        }
+    }
+#undef C_H
+}
+
+void ora_compute_wvel_split(const ora_mesh_t *m, int use_wsplit, double wsplit_maxcfl, const double *Wvel,
+                            const double *CFL_z, double *Wvel_e, double *Wvel_i)
+{
+    const int nl = m->nl;
+    const int Nh = m->myDim_nod2D + m->eDim_nod2D;
+    for (int n = 1; n <= Nh; ++n) {                                                 /* :3033-3047 */
+        const int nzmin = m->ulevels_nod2D[n - 1], nzmax = m->nlevels_nod2D[n - 1];
+        for (int nz = nzmin; nz <= nzmax; ++nz) {
+            const size_t i = (size_t)(n - 1) * nl + (nz - 1);
+            Wvel_e[i] = C_W(nz, n);
+            Wvel_i[i] = 0.0;
+            if (use_wsplit && C_C(nz, n) > wsplit_maxcfl) {
+                const double dd = fmax(C_C(nz, n) - wsplit_maxcfl, 0.0) / fmax(wsplit_maxcfl, 1.e-12);
+                Wvel_e[i] = (1.0 / (1.0 + dd)) * C_W(nz, n);
+                Wvel_i[i] = (dd / (1.0 + dd)) * C_W(nz, n);
+            }
+        }
+    }
+#undef C_W
+#undef C_C
+}

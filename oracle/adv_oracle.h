@@ -160,6 +160,12 @@ typedef struct {
  * del_ttf, advect, values += (dttf_h+dttf_v)/hnode_new, exchange values). */
 double ora_run_ranks(int nranks, ora_rank_t *ranks, double dt, int nsteps, int mode);
 
+/* compute_CFLz (src/oce_ale.F90:2906-2998, no print) and compute_Wvel_split (:3001-3049), all myDim+eDim nodes;
+ * every array (nl, Nh) */
+void ora_compute_cflz(const ora_mesh_t *m, double dt, const double *Wvel, double *CFL_z);
+void ora_compute_wvel_split(const ora_mesh_t *m, int use_wsplit, double wsplit_maxcfl, const double *Wvel,
+                            const double *CFL_z, double *Wvel_e, double *Wvel_i);
+
 #ifdef __cplusplus
 }
 #endif

@@ -474,3 +474,29 @@ def vert_vel_ale_core(mesh, uv, helem):
             W[n, nz - 1] = W[n, nz - 1] + W[n, nz]
         W[n, a - 1:b] = W[n, a - 1:b] / area[n, a - 1:b]
     return W
+
+
+def compute_cflz_and_split(mesh, hnode_new, dt, W, use_wsplit, wsplit_maxcfl):
+    """compute_CFLz (src/oce_ale.F90:2939-2952) and compute_Wvel_split (:3033-3047), whole-array: the loop's
+    CFL_z(nz) = c2 of the layer above + c1 of the layer itself collapses to |W(nz) dt/h(nz-1)| + |W(nz) dt/h(nz)|
+    (first interface: c1 only, interface below the last layer: c2 only).  W (Nh, nl) -> (CFL_z, W_e, W_i)."""
+    L, nl, Nh = mesh.L, mesh.nl, mesh.Nh
+    nln, uln = np.asarray(mesh.nlevels_nod2D)[:, None], np.asarray(mesh.ulevels_nod2D)[:, None]
+    k = np.arange(1, nl + 1)[None, :]
+    h = np.asarray(hnode_new, dtype=np.float64)
+    lay = (k[:, :L] >= uln) & (k[:, :L] <= nln - 1)                       # wet layers
+    with np.errstate(divide="ignore", invalid="ignore"):
+        c1 = np.where(lay, np.abs(W[:, :L] * dt / h), 0.0)                 # own layer below interface nz
+        c2 = np.where(lay, np.abs(W[:, 1:] * dt / h), 0.0)                 # layer above interface nz+1
+    cfl = np.zeros((Nh, nl))
+    cfl[:, 1:] = c2
+    cfl[:, :L] = cfl[:, :L] + c1
+    wet_i = (k >= uln) & (k <= nln)
+    we = np.where(wet_i, W, 0.0)
+    wi = np.zeros_like(W)
+    if use_wsplit:
+        big = wet_i & (cfl > wsplit_maxcfl)
+        dd = np.maximum(cfl - wsplit_maxcfl, 0.0) / max(wsplit_maxcfl, 1.e-12)
+        we = np.where(big, (1.0 / (1.0 + dd)) * W, we)
+        wi = np.where(big, (dd / (1.0 + dd)) * W, wi)
+    return cfl, we, wi

@@ -325,3 +325,19 @@ class LeanOracle:
                                    _dp(k["w_i"]), _dp(k["w_e"]), self.use_wsplit, _dp(v), _dp(vab), _dp(grad),
                                    HOR[hor], VER[ver], LIM.get(lim, 0), float(ph), float(pv), _dp(dh), _dp(dv), cb, None)
         return dh, dv
+
+
+def compute_cflz_and_split(rank: "OracleRank", dt: float, Wvel: np.ndarray, use_wsplit: bool, wsplit_maxcfl: float):
+    """ora_compute_cflz + ora_compute_wvel_split on a rank's mesh: returns (CFL_z, Wvel_e, Wvel_i), each (Nh, nl);
+    entries the reference does not write are zero (CFL_z) / keep the zero of the allocation (Wvel_e, Wvel_i)."""
+    L_ = lib()
+    L_.ora_compute_cflz.argtypes = [C.POINTER(OraMesh), C.c_double, c_dp, c_dp]
+    L_.ora_compute_cflz.restype = None
+    L_.ora_compute_wvel_split.argtypes = [C.POINTER(OraMesh), C.c_int, C.c_double, c_dp, c_dp, c_dp, c_dp]
+    L_.ora_compute_wvel_split.restype = None
+    m = rank.mesh_py
+    W = np.ascontiguousarray(Wvel, dtype=np.float64)
+    cfl = np.zeros((m.Nh, m.nl)); we = np.zeros((m.Nh, m.nl)); wi = np.zeros((m.Nh, m.nl))
+    L_.ora_compute_cflz(C.byref(rank.cmesh), float(dt), _dp(W), _dp(cfl))
+    L_.ora_compute_wvel_split(C.byref(rank.cmesh), int(bool(use_wsplit)), float(wsplit_maxcfl), _dp(W), _dp(cfl), _dp(we), _dp(wi))
+    return cfl, we, wi

@@ -209,3 +209,22 @@ def test_find_up_downwind_triangles_two_restatements(pi_mesh, souf_mesh, small_m
         assert node in na and node in nb_
         assert len(na & nb_) == 2, "candidates are not adjacent triangles"
     assert bad.shape[0] <= 0.02 * mesh.E
+
+
+@pytest.mark.parametrize("use_wsplit", [False, True])
+def test_cflz_and_wvel_split_two_restatements(pi_mesh, use_wsplit):
+    """compute_CFLz + compute_Wvel_split (src/oce_ale.F90:2906-3049): loop-for-loop C restatement against the
+    whole-array NumPy one, on a w large enough that part of it goes implicit."""
+    from oracle import numpy_ref as R, oracle_py as O
+    g = pi_mesh
+    st, trs, nb, dt = make_case(g, 1)
+    rk = O.OracleRank(g, st, trs, nb)
+    W = O.vert_vel_ale_core(rk)
+    dtc = 40.0 * dt                                  # CFL_z well above the threshold somewhere
+    a = O.compute_cflz_and_split(rk, dtc, W, use_wsplit, 0.5)
+    b = R.compute_cflz_and_split(g, st.hnode_new.numpy(), dtc, W, use_wsplit, 0.5)
+    for x, y in zip(a, b):
+        assert np.isfinite(x).all() and np.array_equal(x, y)
+    if use_wsplit:
+        assert (a[2] != 0.0).any(), "nothing went implicit: the test does not exercise the split"
+        assert np.abs(a[1] + a[2] - np.where(a[1] != 0, W, 0.0)).max() <= 1e-15 * np.abs(W).max()
