@@ -103,7 +103,7 @@ struct DevBuf {
 };
 
 struct Slot {  // per-tracer staging: host pointers, unaligned device pointers, library-computed gradients
-    DevBuf<double> ttf, ttfAB, grad, dh, dv, tr_xy;
+    DevBuf<double> ttf, ttfAB, grad, dh, dv, tr_xy, gmean;
 };
 
 // work arrays of one chunk of <= 2 tracers (t_tracer_work, allocated by oce_adv_tra_fct_init in the
@@ -171,6 +171,8 @@ struct adv_ctx {
     // gradient producer (adv_ctx_set_gradient_mesh)
     DevBuf<int> g_nie, g_nie_num, g_nlevels, g_ulevels, g_tri, g_nmin, g_umax, g_elem_nodes;
     DevBuf<double> g_sca, g_earea;
+    DevBuf<int4> edge_g;
+    int fuse_grad = 1;                        // edge_up_dn_grad = NULL: reconstruct the gradients inside the edge kernel (ADV_FUSE_GRAD)
     GradMeshDev gm{};
     bool grad_mesh_set = false, elem_halo_set = false;
     int nS = 0, nI = 0, nSH = 0;
@@ -363,6 +365,7 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
     if (const char* v = getenv("ADV_I_IDENTITY")) c->i_identity = atoi(v) ? 1 : 0;
     if (const char* v = getenv("ADV_E1_PF")) c->e1_pf = std::max(0, atoi(v));
     if (const char* v = getenv("ADV_CTA_THREADS")) c->cta_threads = atoi(v);
+    if (const char* v = getenv("ADV_FUSE_GRAD")) c->fuse_grad = atoi(v) ? 1 : 0;
     c->cta_threads = std::max(((L + 31) / 32) * 32, std::min(1024, (c->cta_threads / 32) * 32));   // whole warps, at least one column
     cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
 #define CUF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { delete c; return fail(ADV_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
@@ -639,8 +642,8 @@ static int set_state_impl(adv_ctx_t* c, const adv_state_desc_t* st, int where)
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-struct Group { int fct, hor, ver; std::vector<int> idx; };
-struct ChunkSel { int fct, hor, ver, tb; int idx[2]; int buf; };
+struct Group { int fct, hor, ver, gs; std::vector<int> idx; };
+struct ChunkSel { int fct, hor, ver, gs, tb; int idx[2]; int buf; };
 
 // columns per CTA of the kernels that keep the fixed (column, level) thread map (non-FCT branch, gradients,
 // register-gather edge kernel): as many as fit into 224 threads; one column when a column alone is longer
@@ -648,7 +651,7 @@ inline int cols_per_block(int L) { return std::max(1, 224 / L); }
 inline int nblocks(int count, int cpb) { return (count + cpb - 1) / cpb; }
 
 struct TrPtrs {   // device pointers of the call's tracers
-    std::vector<const double*> ttf, ttfAB, grad;
+    std::vector<const double*> ttf, ttfAB, grad, txy, gmean;   // grad == nullptr && txy != nullptr: fused gradients
     std::vector<double*> dh, dv;
 };
 
@@ -659,7 +662,7 @@ Chunk<TB> make_chunk(adv_ctx* c, const TrPtrs& p, const adv_tracer_desc_t* tr, c
     ChunkBuf& cb = *c->cbufs[ch.buf];
     for (int t = 0; t < TB; ++t) {
         const int i = ch.idx[t];
-        b.ttf[t] = p.ttf[i]; b.ttfAB[t] = p.ttfAB[i]; b.grad[t] = p.grad[i];
+        b.ttf[t] = p.ttf[i]; b.ttfAB[t] = p.ttfAB[i]; b.grad[t] = p.grad[i]; b.txy[t] = p.txy[i]; b.gmean[t] = p.gmean[i];
         b.dttf_h[t] = p.dh[i]; b.dttf_v[t] = p.dv[i];
         b.ph[t] = tr[i].tra_adv_ph; b.pv[t] = tr[i].tra_adv_pv;
     }
@@ -698,7 +701,7 @@ template <int TB>
 static bool chunk_aligned(const MeshDev& m, const Chunk<TB>& b)
 {
     uintptr_t x = (uintptr_t)m.uv;
-    for (int t = 0; t < TB; ++t) x |= (uintptr_t)b.grad[t];
+    for (int t = 0; t < TB; ++t) x |= (uintptr_t)b.grad[t] | (uintptr_t)b.txy[t] | (uintptr_t)b.gmean[t];
     return (x & 15u) == 0;
 }
 
@@ -731,17 +734,19 @@ int launch_phase(adv_ctx* c, Phase ph, int hor, int ver, bool q_stored, const Ch
             const int ng = std::max(1, std::min(c->e1_ng, nthr / epb));
             const int nge = epb * ng, D = c->e1_depth;
             grid = nblocks(m.E, nge);
-#define E1B(H, Q, DD) if (!piped && hor == H && (q_stored ? 1 : 0) == Q && D == DD) { \
-                smem = e1b_smem_bytes<TB, Q>(nge, nthr, DD); \
+            const int gs = b.grad[0] ? 0 : 1;
+#define E1B(H, Q, DD, GS) if (!piped && hor == H && (q_stored ? 1 : 0) == Q && D == DD && gs == GS) { \
+                smem = e1b_smem_bytes<TB, Q, GS>(nge, nthr, DD); \
                 if ((int)smem <= c->max_smem_optin) { \
-                    se = smem_optin(k_edge_flux_b<H, TB, Q, DD>, smem); \
-                    if (se == cudaSuccess) k_edge_flux_b<H, TB, Q, DD><<<grid, nthr, smem, s>>>(m, b, epb, ng, c->e1_il, c->e1_pf); \
+                    se = smem_optin(k_edge_flux_b<H, TB, Q, DD, GS>, smem); \
+                    if (se == cudaSuccess) k_edge_flux_b<H, TB, Q, DD, GS><<<grid, nthr, smem, s>>>(m, b, epb, ng, c->e1_il, c->e1_pf); \
                     piped = true; } }
-#define E1BD(H, Q) E1B(H, Q, 2) E1B(H, Q, 3) E1B(H, Q, 4)
+#define E1BD(H, Q) E1B(H, Q, 2, 0) E1B(H, Q, 3, 0) E1B(H, Q, 4, 0) E1B(H, Q, 2, 1) E1B(H, Q, 3, 1) E1B(H, Q, 4, 1)
             E1BD(HOR_MUSCL, 0) E1BD(HOR_MUSCL, 1) E1BD(HOR_MFCT, 0) E1BD(HOR_MFCT, 1)
 #undef E1BD
 #undef E1B
         }
+        if (!piped && hor != HOR_UPW1 && !b.grad[0]) return fail(ADV_ECUDA, "internal: fused-gradient chunk cannot run on the bulk edge kernel");
         if (!piped) {
             grid = nblocks(m.E, epb);
 #define E1(H) if (hor == H) { if (q_stored) k_edge_flux<H, TB, 1><<<grid, nthr, 0, s>>>(m, b, epb); \
@@ -891,17 +896,19 @@ static int run_batch(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr
         static const char* ln[] = {"FCT"};
         static const int lc[] = {1};
         const int fct = parse_scheme(tr[i].tra_adv_lim, ln, lc, 1) == 1 ? 1 : 0;   // driver :111: anything else = no limiter
-        if (hor != HOR_UPW1 && !p.grad[i]) return fail(ADV_EINVAL, "edge_up_dn_grad is NULL for a gradient-based scheme");
+        if (hor != HOR_UPW1 && !p.grad[i] && !p.txy[i]) return fail(ADV_EINVAL, "edge_up_dn_grad is NULL for a gradient-based scheme");
+        const int gs = (hor != HOR_UPW1 && !p.grad[i]) ? 1 : 0;
+        if (gs && !fct) return fail(ADV_EINVAL, "internal: fused gradients are for FCT tracers only");
         bool found = false;
         for (auto& g : groups)
-            if (g.fct == fct && g.hor == hor && g.ver == ver) { g.idx.push_back(i); found = true; break; }
-        if (!found) groups.push_back(Group{fct, hor, ver, {i}});
+            if (g.fct == fct && g.hor == hor && g.ver == ver && g.gs == gs) { g.idx.push_back(i); found = true; break; }
+        if (!found) groups.push_back(Group{fct, hor, ver, gs, {i}});
     }
     std::vector<ChunkSel> chunks;
     for (auto& g : groups) {
         size_t i = 0;
-        for (; !c->force_tb1 && i + 2 <= g.idx.size(); i += 2) chunks.push_back(ChunkSel{g.fct, g.hor, g.ver, 2, {g.idx[i], g.idx[i + 1]}, 0});
-        for (; i < g.idx.size(); ++i) chunks.push_back(ChunkSel{g.fct, g.hor, g.ver, 1, {g.idx[i], g.idx[i]}, 0});
+        for (; !c->force_tb1 && i + 2 <= g.idx.size(); i += 2) chunks.push_back(ChunkSel{g.fct, g.hor, g.ver, g.gs, 2, {g.idx[i], g.idx[i + 1]}, 0});
+        for (; i < g.idx.size(); ++i) chunks.push_back(ChunkSel{g.fct, g.hor, g.ver, g.gs, 1, {g.idx[i], g.idx[i]}, 0});
     }
     if (int rc = ensure_chunk_bufs(c, (int)chunks.size())) return rc;
     for (size_t k = 0; k < chunks.size(); ++k) {
@@ -1032,7 +1039,7 @@ static int do_adv(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr, i
     MeshDev& m = c->m;
     const size_t nLN = (size_t)m.L * m.Nh, nLE = (size_t)m.L * m.E;
     TrPtrs p;
-    p.ttf.resize(ntr); p.ttfAB.resize(ntr); p.grad.resize(ntr); p.dh.resize(ntr); p.dv.resize(ntr);
+    p.ttf.resize(ntr); p.ttfAB.resize(ntr); p.grad.resize(ntr); p.txy.assign(ntr, nullptr); p.gmean.assign(ntr, nullptr); p.dh.resize(ntr); p.dv.resize(ntr);
     for (int i = 0; i < ntr; ++i) {
         if (!tr[i].values || !tr[i].valuesAB || !tr[i].del_ttf_advhoriz || !tr[i].del_ttf_advvert)
             return fail(ADV_EINVAL, "tracer " + std::to_string(i + 1) + ": null field");
@@ -1080,19 +1087,39 @@ static int do_adv(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr, i
         if (!need.empty()) {
             if (c->npes > 1 && !c->elem_halo_set)
                 return fail(ADV_EINVAL, "edge_up_dn_grad = NULL on more than one rank needs com_elem2D_full in adv_ctx_set_gradient_mesh");
-            const size_t nxy = (size_t)2 * m.L * c->gm.n_elem;
+            const size_t nxy = (size_t)2 * m.L * c->gm.n_elem, nmean = (size_t)2 * m.L * m.Nh;
+            const int cpb = cols_per_block(m.L);
             std::vector<const double*> ttfs, cxy;
             std::vector<double*> xy, gr;
+            std::vector<int> fused;
             for (int i : need) {
                 Slot& s = c->slots[i];
                 if (s.tr_xy.n != nxy) CU(s.tr_xy.alloc(nxy));
-                if (s.grad.n != 4 * nLE) CU(s.grad.alloc(4 * nLE));
-                ttfs.push_back(p.ttf[i]); xy.push_back(s.tr_xy.p); cxy.push_back(s.tr_xy.p); gr.push_back(s.grad.p);
-                p.grad[i] = s.grad.p;
+                ttfs.push_back(p.ttf[i]); xy.push_back(s.tr_xy.p);
+                // FCT tracers: the edge kernel reconstructs the gradients itself (k_edge_flux_b<.., GS = 1>) from tr_xy
+                // and the node means; the one-sweep non-FCT kernel reads a materialised edge_up_dn_grad
+                char lbuf[16]; int k = 0;
+                for (const char* q = tr[i].tra_adv_lim; q && *q && *q != ' ' && k < 15; ++q) lbuf[k++] = *q;
+                lbuf[k] = 0;
+                const bool fuse = c->fuse_grad && c->bulk && strcmp(lbuf, "FCT") == 0 && c->gm.n_nie >= m.Nh;
+                if (fuse) fused.push_back(i);
+                else {
+                    if (s.grad.n != 4 * nLE) CU(s.grad.alloc(4 * nLE));
+                    cxy.push_back(s.tr_xy.p); gr.push_back(s.grad.p);
+                    p.grad[i] = s.grad.p;
+                }
             }
             if (int rc = adv_tracer_gradient_elements(c, (int)need.size(), ttfs.data(), xy.data())) return rc;
             if (c->npes > 1) if (int rc = adv_exchange_elem(c, (int)need.size(), xy.data(), 2 * m.L)) return rc;
-            if (int rc = adv_fill_up_dn_grad(c, (int)need.size(), cxy.data(), gr.data())) return rc;
+            if (!cxy.empty()) if (int rc = adv_fill_up_dn_grad(c, (int)cxy.size(), cxy.data(), gr.data())) return rc;
+            for (int i : fused) {
+                Slot& s = c->slots[i];
+                if (s.gmean.n != nmean) CU(s.gmean.alloc(nmean));
+                k_node_mean_grad<<<nblocks(m.Nh, cpb), cpb * m.L, 0, c->s_comp>>>(m, c->gm, cpb, s.tr_xy.p, s.gmean.p);
+                ++c->launches;
+                p.txy[i] = s.tr_xy.p; p.gmean[i] = s.gmean.p;
+            }
+            CU(cudaGetLastError());
         }
     }
     CU(cudaEventRecord(c->ev_t0, c->s_comp));
@@ -1281,6 +1308,21 @@ int adv_ctx_set_gradient_mesh(adv_ctx_t* c, const adv_gradient_mesh_desc_t* g)
     gm.nie = c->g_nie.p; gm.nie_num = c->g_nie_num.p; gm.nlevels = c->g_nlevels.p; gm.ulevels = c->g_ulevels.p;
     gm.up_dn_tri = c->g_tri.p; gm.nmin = c->g_nmin.p; gm.umax = c->g_umax.p; gm.elem_nodes = c->g_elem_nodes.p;
     gm.gsca = c->g_sca.p; gm.earea = c->g_earea.p;
+    {   // per edge: the two triangles and the layers on which fill_up_dn_grad takes their gradients (:431-440)
+        std::vector<int4> em(m.E), eg(m.E);
+        CU(cudaMemcpy(em.data(), m.edge_meta, sizeof(int4) * m.E, cudaMemcpyDeviceToHost));
+        for (int e = 0; e < m.E; ++e) {
+            const int t1 = g->edge_up_dn_tri[2 * e] - 1, t2 = g->edge_up_dn_tri[2 * e + 1] - 1;
+            int lo = 1, hi = 0;
+            if (t1 >= 0 && t2 >= 0) {
+                lo = std::max(g->ulevels_nod2D_max[em[e].x], g->ulevels_nod2D_max[em[e].y]);
+                hi = std::min(g->nlevels_nod2D_min[em[e].x], g->nlevels_nod2D_min[em[e].y]) - 1;
+            }
+            eg[e] = make_int4(t1, t2, lo, hi);
+        }
+        CU(c->edge_g.upload(eg));
+        c->m.edge_g = c->edge_g.p;
+    }
     // com_elem2D_full: halo of tr_xy (exchange_elem, src/oce_tracer_mod.F90:140)
     c->elem_halo_set = false;
     if (c->npes > 1 && (g->rPEnum > 0 || g->sPEnum > 0)) {

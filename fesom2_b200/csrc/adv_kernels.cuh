@@ -109,6 +109,8 @@ struct MeshDev {
     const uchar4* edge_lev;  // (E) {nu1, nl1, nu2, nl2}  (nl = nlevels-1; 0,0 for a missing el2)
     const double4* edge_cross; // (E) edge_cross_dxdy
     const double2* edge_c;   // (E) {edge_dxdy(1)*a, edge_dxdy(2)*r_earth}
+    const int4*   edge_g;    // (E) fused gradients (adv_ctx_set_gradient_mesh): {up triangle, down triangle (0-based, -1 none),
+                             //     first, last layer on which the triangles' gradients are used (first > last: none)}
     const int*    nboundary_lay; // (Nh)
     const double* area;      // (nl,Nh)
     const double* areasvol;  // (nl,Nh)
@@ -129,6 +131,8 @@ struct Chunk {
     const double* ttf[TB];
     const double* ttfAB[TB];
     const double* grad[TB];
+    const double* txy[TB];    // fused gradients (grad[t] == nullptr): tr_xy (2,L,n_elem) and the node-mean gradients (2,L,Nh)
+    const double* gmean[TB];
     double* dttf_h[TB];
     double* dttf_v[TB];
     double ph[TB], pv[TB];
@@ -1628,6 +1632,23 @@ __global__ void __launch_bounds__(kBlock) k_fill_up_dn_grad(MeshDev m, GradMeshD
     const bool w2 = both ? ((nz >= u2 && nz <= nzmin - 1) || (nz >= nzmax && nz <= n2)) : (nz >= u2 && nz <= n2);
     if (w1) { const double2 v = node_mean_gradient(m, g, em.x, nz, tr_xy); out[0] = v.x; out[2] = v.y; }
     if (w2) { const double2 v = node_mean_gradient(m, g, em.y, nz, tr_xy); out[1] = v.x; out[3] = v.y; }
+}
+
+// The node part of fill_up_dn_grad (src/oce_muscl_adv.F90:391-406,:414-429 and the below-bottom / boundary-edge
+// twins): the area-weighted mean of the element gradients around a node depends on (node, layer) only, so it is
+// evaluated ONCE per node instead of once per incident edge; the fused edge kernel (k_edge_flux_b<.., GS = 1>)
+// picks it up on the layers where the reference uses it.  One thread per (node, layer) of all local nodes.
+__global__ void __launch_bounds__(kBlock) k_node_mean_grad(MeshDev m, GradMeshDev g, int cpb, const double* __restrict__ tr_xy,
+                                                           double* __restrict__ gmean)
+{
+    const ColThread c = col_thread(m);
+    const int n = blockIdx.x * cpb + c.g;
+    if (c.g >= cpb || n >= g.n_nie) return;
+    const int nz = c.nz0 + 1;
+    const uchar4 lv = __ldg(&m.node_lev[n]);
+    double2 v = make_double2(0.0, 0.0);
+    if (nz >= (int)lv.x && nz <= (int)lv.y - 1) v = node_mean_gradient(m, g, n, nz, tr_xy);
+    reinterpret_cast<double2*>(gmean)[(size_t)n * m.L + c.nz0] = v;
 }
 
 // self-test of div_rcp against the IEEE division: returns the number of mismatching results over

@@ -47,8 +47,8 @@ template <int TB> __device__ __forceinline__ void cpa_vec(unsigned dst, const do
 
 __host__ __device__ constexpr size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-// per-CTA edge metadata block: int4 em[nge], double2 cr[2 nge], double2 ec[nge], int2 nb[nge], unsigned lv[nge]
-__host__ __device__ inline size_t e1p_meta_bytes(int nge) { return align16((size_t)nge * (16 + 32 + 16 + 8 + 4)); }
+// per-CTA edge metadata block: int4 em[nge], double2 cr[2 nge], double2 ec[nge], int4 eg[nge], int2 nb[nge], unsigned lv[nge]
+__host__ __device__ inline size_t e1p_meta_bytes(int nge) { return align16((size_t)nge * (16 + 32 + 16 + 16 + 8 + 4)); }
 
 // ----------------------------------------------------------------------------------------------
 // E1 (bulk): edge_up_dn_grad of the group's epb consecutive edges (up to epb * L * 32 bytes per tracer)
@@ -96,17 +96,22 @@ struct E1bCells {
     static constexpr int c_t1 = 0, c_t2 = TB, c_a1 = 2 * TB, c_a2 = 3 * TB, c_he = (ADV_E1B_DIRECT ? 0 : 4 * TB);
 };
 __host__ __device__ constexpr size_t align128(size_t x) { return (x + 127) & ~(size_t)127; }
-template <int TB, int QMODE>
-__host__ __device__ inline size_t e1b_bulk_bytes(int nthr) { return align128((size_t)nthr * 32 * TB); }
-template <int TB, int QMODE>
-__host__ __device__ inline size_t e1b_stage_bytes(int nthr) { return e1b_bulk_bytes<TB, QMODE>(nthr) + align128((size_t)E1bCells<TB, QMODE>::bytes * nthr); }
-template <int TB, int QMODE>
+// GS = 0: the stage holds the edge's edge_up_dn_grad column (32 bytes per level and tracer);
+// GS = 1: the gradients are reconstructed on the fly (fill_up_dn_grad fused, src/oce_muscl_adv.F90:378-522): the stage
+//         holds four 16-byte-per-level columns per edge and tracer -- tr_xy of the up- and of the down-wind triangle,
+//         the node-mean gradients of the two end nodes -- and every (edge, layer) picks the pair the reference
+//         would have stored: the triangles' on the layers both end nodes share, the node means elsewhere.
+template <int TB, int QMODE, int GS>
+__host__ __device__ inline size_t e1b_bulk_bytes(int nthr) { return align128((size_t)nthr * (GS ? 64 : 32) * TB); }
+template <int TB, int QMODE, int GS>
+__host__ __device__ inline size_t e1b_stage_bytes(int nthr) { return e1b_bulk_bytes<TB, QMODE, GS>(nthr) + align128((size_t)E1bCells<TB, QMODE>::bytes * nthr); }
+template <int TB, int QMODE, int GS>
 __host__ __device__ inline size_t e1b_smem_bytes(int nge, int nthr, int D)
 {
-    return align128(e1p_meta_bytes(nge)) + (size_t)D * e1b_stage_bytes<TB, QMODE>(nthr) + 16 * D;
+    return align128(e1p_meta_bytes(nge)) + (size_t)D * e1b_stage_bytes<TB, QMODE, GS>(nthr) + 16 * D;
 }
 
-template <int HOR, int TB, int QMODE, int D>
+template <int HOR, int TB, int QMODE, int D, int GS>
 __global__ void __launch_bounds__(kBlock, ADV_E1P_MINB) k_edge_flux_b(MeshDev m, Chunk<TB> b, int epb, int ng, int il, int pf)
 {
     static_assert(HOR != HOR_UPW1, "the bulk variant stages edge_up_dn_grad");
@@ -121,11 +126,12 @@ __global__ void __launch_bounds__(kBlock, ADV_E1P_MINB) k_edge_flux_b(MeshDev m,
     int4* s_em = reinterpret_cast<int4*>(smem_raw);
     double2* s_cr = reinterpret_cast<double2*>(s_em + nge);
     double2* s_ec = s_cr + 2 * nge;
-    int2* s_nb = reinterpret_cast<int2*>(s_ec + nge);
+    int4* s_eg = reinterpret_cast<int4*>(s_ec + nge);
+    int2* s_nb = reinterpret_cast<int2*>(s_eg + nge);
     unsigned* s_lv = reinterpret_cast<unsigned*>(s_nb + nge);
     unsigned char* s_stage = smem_raw + align128(e1p_meta_bytes(nge));
-    const unsigned stage_bytes = (unsigned)e1b_stage_bytes<TB, QMODE>(nthr);
-    const unsigned bulk_bytes = (unsigned)e1b_bulk_bytes<TB, QMODE>(nthr);
+    const unsigned stage_bytes = (unsigned)e1b_stage_bytes<TB, QMODE, GS>(nthr);
+    const unsigned bulk_bytes = (unsigned)e1b_bulk_bytes<TB, QMODE, GS>(nthr);
     unsigned long long* full = reinterpret_cast<unsigned long long*>(s_stage + (size_t)D * stage_bytes);
     if (tid == 0) {
 #pragma unroll
@@ -156,6 +162,7 @@ __global__ void __launch_bounds__(kBlock, ADV_E1P_MINB) k_edge_flux_b(MeshDev m,
             const double2* cr = reinterpret_cast<const double2*>(&m.edge_cross[e]);
             s_cr[2 * i] = __ldg(cr); s_cr[2 * i + 1] = __ldg(cr + 1);
             s_ec[i] = __ldg(&m.edge_c[e]);
+            if (GS) s_eg[i] = __ldg(&m.edge_g[e]);
             if (HOR == HOR_MUSCL) s_nb[i] = make_int2(__ldg(&m.nboundary_lay[em.x]), __ldg(&m.nboundary_lay[em.y]));
         }
     }
@@ -178,15 +185,32 @@ __global__ void __launch_bounds__(kBlock, ADV_E1P_MINB) k_edge_flux_b(MeshDev m,
                 unsigned total = 0;
                 for (int k = 0; k < ne; ++k) {
                     const unsigned lvw = s_lv[i * epb + k];
-                    total += max((lvw >> 8) & 0xff, lvw >> 24) * 32u;
+                    const unsigned hi = max((lvw >> 8) & 0xff, lvw >> 24);
+                    if (GS) { const int4 g4 = s_eg[i * epb + k]; total += hi * 16u * (2u + (g4.x >= 0 ? 1u : 0u) + (g4.y >= 0 ? 1u : 0u)); }
+                    else total += hi * 32u;
                 }
                 mbar_expect(&full[i % D], total * TB);
                 for (int k = 0; k < ne; ++k) {
                     const unsigned lvw = s_lv[i * epb + k];
-                    const unsigned nb = max((lvw >> 8) & 0xff, lvw >> 24) * 32u;
-                    const size_t ecol = (size_t)(eg + k) * L;
+                    const unsigned hi = max((lvw >> 8) & 0xff, lvw >> 24);
+                    if (GS) {
+                        const int4 g4 = s_eg[i * epb + k];
+                        const int4 em = s_em[i * epb + k];
+                        const unsigned cw = (unsigned)L * 16u, nb = hi * 16u;
 #pragma unroll
-                    for (int t = 0; t < TB; ++t) bulk_g2s(sb + (unsigned)(t * epb + k) * colw, b.grad[t] + ecol * 4, nb, &full[i % D]);
+                        for (int t = 0; t < TB; ++t) {
+                            const unsigned st = sb + (unsigned)(t * 4 * epb + k) * cw;
+                            if (g4.x >= 0) bulk_g2s(st, b.txy[t] + (size_t)g4.x * L * 2, nb, &full[i % D]);
+                            if (g4.y >= 0) bulk_g2s(st + (unsigned)epb * cw, b.txy[t] + (size_t)g4.y * L * 2, nb, &full[i % D]);
+                            bulk_g2s(st + 2u * epb * cw, b.gmean[t] + (size_t)em.x * L * 2, nb, &full[i % D]);
+                            bulk_g2s(st + 3u * epb * cw, b.gmean[t] + (size_t)em.y * L * 2, nb, &full[i % D]);
+                        }
+                    } else {
+                        const unsigned nb = hi * 32u;
+                        const size_t ecol = (size_t)(eg + k) * L;
+#pragma unroll
+                        for (int t = 0; t < TB; ++t) bulk_g2s(sb + (unsigned)(t * epb + k) * colw, b.grad[t] + ecol * 4, nb, &full[i % D]);
+                    }
                 }
             }
             const int li = i * epb + c.g;
@@ -319,8 +343,18 @@ __global__ void __launch_bounds__(kBlock, ADV_E1P_MINB) k_edge_flux_b(MeshDev m,
             const double aq = fabs(q), qp = q + aq, qm = q - aq;
 #pragma unroll
             for (int t = 0; t < TB; ++t) {
-                const double2* gp = reinterpret_cast<const double2*>(sp + (size_t)t * epb * colw) + (size_t)tid * 2;
-                const double2 g12 = gp[0], g34 = gp[1];
+                double2 g12, g34;
+                if (GS) {                                  // fill_up_dn_grad :435-440 (shared layers) / :391-406 (node means)
+                    const int4 g4 = s_eg[li];
+                    const bool sh = nz >= g4.z && nz <= g4.w;
+                    const double2* base = reinterpret_cast<const double2*>(sp + (size_t)t * 4 * epb * L * 16);
+                    const double2 up = base[(size_t)((sh ? 0 : 2) * epb + c.g) * L + nz0];
+                    const double2 dn = base[(size_t)((sh ? 1 : 3) * epb + c.g) * L + nz0];
+                    g12 = make_double2(up.x, dn.x); g34 = make_double2(up.y, dn.y);
+                } else {
+                    const double2* gp = reinterpret_cast<const double2*>(sp + (size_t)t * epb * colw) + (size_t)tid * 2;
+                    g12 = gp[0]; g34 = gp[1];
+                }
                 const double flo = hor_lo(t1[t], t2[t], qp, qm);
                 out[t] = hor_ho<HOR>(a1[t], a2[t], q, qp, qm, ec, g12, g34, b.ph[t], clo1, clo2, flo);
             }

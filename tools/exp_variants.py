@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--nl", type=int, default=71)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--tracers", type=int, default=2)
+    ap.add_argument("--null-grad", action="store_true", help="edge_up_dn_grad = NULL: the library computes the gradients inside the step")
     ap.add_argument("variants", nargs="*")
     a = ap.parse_args()
     import torch
@@ -55,6 +56,10 @@ def main():
             os.environ[k] = val
         try:
             ctx = AdvB200(g, nb, device=0, max_tracers=a.tracers)
+            if a.null_grad:
+                ctx.set_gradient_mesh(tri)
+                for t in trs:
+                    t.edge_up_dn_grad = None
             for x in dh + dv:
                 x.zero_()
             ctx.set_state(st)
