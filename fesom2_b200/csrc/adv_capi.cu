@@ -783,7 +783,7 @@ int launch_phase(adv_ctx* c, Phase ph, int hor, int ver, bool q_stored, const Ch
             N1(VER_UPW1) N1(VER_QR4C) N1(VER_PPM) N1(VER_CDIFF)
 #undef N1
         } else if (ph == PH_K2) {
-            const size_t sm2 = hdr + (size_t)2 * TB * nthr * sizeof(double);
+            const size_t sm2 = hdr + (size_t)(6 * TB + 1) * nthr * sizeof(double);   // tvert exchange area + parked own-column operands
             if (c->g_k2 == 6) NODE_LAUNCH((k_fct_bounds<TB, 6>), sm2);
             else if (c->g_k2 == 3) NODE_LAUNCH((k_fct_bounds<TB, 3>), sm2);
             else if (c->g_k2 == 1) NODE_LAUNCH((k_fct_bounds<TB, 1>), sm2);

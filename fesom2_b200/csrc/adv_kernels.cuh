@@ -63,7 +63,7 @@ constexpr int kBlock = 256;
 #define ADV_K2_REGS 72
 #endif
 #ifndef ADV_K3_REGS
-#define ADV_K3_REGS 72
+#define ADV_K3_REGS 56   // since the vertical part of the update moved into k_fct_bounds: no spills at 56, 5 CTAs per SM (0.84 -> 0.77 ms)
 #endif
 #if ADV_N1_REGS > 0
 #define ADV_N1_BOUNDS __maxnreg__(ADV_N1_REGS)
@@ -183,30 +183,32 @@ template <> __device__ __forceinline__ void stv<2>(double* __restrict__ p, const
 template <int TB> __device__ __forceinline__ void ldpm(const double* __restrict__ p, double (&pl)[TB], double (&mi)[TB])
 {
 #ifndef ADV_NO_LDG256
-    if (TB == 2) {   // the {R+,R-} pairs of both tracers are one 32-byte record: a single 256-bit load (sm_100: LDG.E.256)
+    if constexpr (TB == 2) {   // the {R+,R-} pairs of both tracers are one 32-byte record: a single 256-bit load (sm_100: LDG.E.256)
         double a, b, c, d;
         asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
         pl[0] = a; mi[0] = b; pl[TB - 1] = c; mi[TB - 1] = d;
-        return;
-    }
+    } else
 #endif
+    {
 #pragma unroll
-    for (int t = 0; t < TB; ++t) {
-        const double2 v = __ldg(reinterpret_cast<const double2*>(p) + t);
-        pl[t] = v.x; mi[t] = v.y;
+        for (int t = 0; t < TB; ++t) {
+            const double2 v = __ldg(reinterpret_cast<const double2*>(p) + t);
+            pl[t] = v.x; mi[t] = v.y;
+        }
     }
 }
 // store TB {a, b} pairs at p (32-byte aligned for TB = 2: one 256-bit store)
 template <int TB> __device__ __forceinline__ void stpm(double* __restrict__ p, const double (&a)[TB], const double (&b)[TB])
 {
 #ifndef ADV_NO_LDG256
-    if (TB == 2) {
+    if constexpr (TB == 2) {
         asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a[0]), "d"(b[0]), "d"(a[TB - 1]), "d"(b[TB - 1]) : "memory");
-        return;
-    }
+    } else
 #endif
+    {
 #pragma unroll
-    for (int t = 0; t < TB; ++t) reinterpret_cast<double2*>(p)[t] = make_double2(a[t], b[t]);
+        for (int t = 0; t < TB; ++t) reinterpret_cast<double2*>(p)[t] = make_double2(a[t], b[t]);
+    }
 }
 
 // Correctly rounded x / b from y = RN(1/b): q0 = x*y is refined twice with exact FMA residuals
@@ -1130,6 +1132,20 @@ __global__ void __launch_bounds__(256) k_cflz_wsplit(MeshDev m, double dt, int u
     We[idx] = we; Wi[idx] = wi;
 }
 
+// limited vertical antidiffusive flux at interface k of a column (oce_adv_tra_fct.F90:425-455):
+// f = adf_v(k); (pa, ma) = R+/R- of layer k-1, (pk, mk) of layer k
+__device__ __forceinline__ double limit_v(double f, int k, int nzmin, int nzmax, double pa, double ma, double pk, double mk)
+{
+    double ae = 1.0;
+    if (k == nzmin) {                                                 // :430-438
+        ae = (f >= 0.0) ? dmin(ae, pk) : dmin(ae, mk);
+    } else if (k <= nzmax - 1) {                                      // :442-453
+        if (f >= 0.0) { ae = dmin(ae, ma); ae = dmin(ae, pk); }
+        else { ae = dmin(ae, pa); ae = dmin(ae, mk); }
+    }                                                                 // bottom interface untouched
+    return ae * f;
+}
+
 // ----------------------------------------------------------------------------------------------
 // K2: FCT bounds, P+/P- sums and limiter factors (owned nodes); needs lo on the halo.
 //   reference: oce_adv_tra_fct.F90:124-248 (a1-a3), :265-377 (b1), :394-405 (b2)
@@ -1144,12 +1160,13 @@ __global__ void ADV_K2_BOUNDS k_fct_bounds(MeshDev m, Chunk<TB> b, NodePart r, d
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw + node_smem_header(m.ell_w));   // [2*TB][blockDim]: tvert_max, tvert_min
     const int L = m.L, nl = m.nl;
-    node_cta_prefetch<TB + 4>(m, r, [&](int q) {
-        if (q < TB) return PfArr{b.ttf[q], (unsigned)L * 8u, 8u, 0};
-        switch (q - TB) {
+    node_cta_prefetch<2 * TB + 5>(m, r, [&](int q) {
+        if (q < 2 * TB) return PfArr{(q & 1) ? (const void*)b.dttf_v[q >> 1] : (const void*)b.ttf[q >> 1], (unsigned)L * 8u, 8u, 0};
+        switch (q - 2 * TB) {
         case 0: return PfArr{b.lo, (unsigned)L * TB * 8u, TB * 8u, 0};
         case 1: return PfArr{b.adf_v, (unsigned)nl * TB * 8u, TB * 8u, 1};
         case 2: return PfArr{m.areasvol, (unsigned)nl * 8u, 8u, 1};
+        case 3: return PfArr{m.hnode, (unsigned)L * 8u, 8u, 0};
         default: return PfArr{m.hnode_new, (unsigned)L * 8u, 8u, 0};
         }
     }, (ADV_PF_OWN & 2) != 0);
@@ -1159,6 +1176,10 @@ __global__ void ADV_K2_BOUNDS k_fct_bounds(MeshDev m, Chunk<TB> b, NodePart r, d
     const unsigned oL = (unsigned)n * L + nz0;
     double tmax[TB], tmin[TB], pp[TB], pn[TB], lo_n[TB];
     double av = 1.0, hnn = 1.0;
+    // own-column operands that are needed again only after the gather (vertical update at the end) are parked in
+    // shared memory instead of being held in registers across it: [4*TB + 1][blockDim] after the tvert area
+    double* park = sm + (size_t)2 * TB * blockDim.x + threadIdx.x;
+    const unsigned pst = blockDim.x;
     if (valid) {
         // ---- all global loads of the first batch + the own column ------------------------------
         int4 ent[G];
@@ -1167,13 +1188,14 @@ __global__ void ADV_K2_BOUNDS k_fct_bounds(MeshDev m, Chunk<TB> b, NodePart r, d
 #pragma unroll
         for (int j = 0; j < G; ++j) ent[j] = (j < th.deg) ? th.ell[j] : ADV_EMPTY_SLOT;
         const size_t cN = (size_t)n * nl + nz0;
-        double tn[TB], vt[TB], vb[TB];
+        double tn[TB], vt[TB], vb[TB], dvv[TB];
         ldv<TB>(b.lo + (size_t)oL * TB, lo_n);
 #pragma unroll
-        for (int t = 0; t < TB; ++t) tn[t] = __ldg(&b.ttf[t][oL]);
+        for (int t = 0; t < TB; ++t) { tn[t] = __ldg(&b.ttf[t][oL]); dvv[t] = n < m.N ? b.dttf_v[t][oL] : 0.0; }
         ldv<TB>(b.adf_v + cN * TB, vt);
         ldv<TB>(b.adf_v + (cN + 1) * TB, vb);
         av = __ldg(&m.areasvol[cN]); hnn = __ldg(&m.hnode_new[oL]);
+        const double hn = __ldg(&m.hnode[oL]);
 #pragma unroll
         for (int j = 0; j < G; ++j) {
             const int lo = ent[j].z & 0xff, hi = (ent[j].z >> 8) & 0xff;
@@ -1199,7 +1221,9 @@ __global__ void ADV_K2_BOUNDS k_fct_bounds(MeshDev m, Chunk<TB> b, NodePart r, d
             tmin[t] = (self_in && lo2 < tmin[t]) ? lo2 : tmin[t];
             pp[t] = 0.0 + (dmax(0.0, vt[t]) + dmax(0.0, -vb[t]));                          // fct :291
             pn[t] = 0.0 + (dmin(0.0, vt[t]) + dmin(0.0, -vb[t]));                          // fct :292
+            park[(4 * t) * pst] = tn[t]; park[(4 * t + 1) * pst] = vt[t]; park[(4 * t + 2) * pst] = vb[t]; park[(4 * t + 3) * pst] = dvv[t];
         }
+        park[(4 * TB) * pst] = hn;
         for (int j0 = 0;;) {
 #pragma unroll
             for (int j = 0; j < G; ++j) {
@@ -1239,12 +1263,14 @@ __global__ void ADV_K2_BOUNDS k_fct_bounds(MeshDev m, Chunk<TB> b, NodePart r, d
         }
     }
     __syncthreads();
-    if (!valid) return;
     const double r_av = 1.0 / av, r_hnn = 1.0 / hnn;
     const bool edge_layer = (nz == th.nzmin) || (nz == th.nzmax - 1);   // :233-234, :245-247
     double rp[TB], rm[TB];
 #pragma unroll
+    for (int t = 0; t < TB; ++t) { rp[t] = 1.0; rm[t] = 1.0; }
+#pragma unroll
     for (int t = 0; t < TB; ++t) {
+        if (!valid) break;
         double vmax = tmax[t], vmin = tmin[t];
         if (!edge_layer) {                                               // :238-241 (layers nz-1, nz+1 = the threads before / after)
             const double* smax = sm + (2 * t) * blockDim.x + threadIdx.x;
@@ -1257,26 +1283,41 @@ __global__ void ADV_K2_BOUNDS k_fct_bounds(MeshDev m, Chunk<TB> b, NodePart r, d
         const double fm = div_rcp(div_rcp(pn[t] * dt, av, r_av), hnn, r_hnn) - 1e-16;   // :401
         rp[t] = dmin(1.0, inc_max / fp); rm[t] = dmin(1.0, inc_min / fm);
     }
-    stpm<TB>(b.pm + (size_t)oL * TB * 2, rp, rm);
-}
-
-// limited vertical antidiffusive flux at interface k of a column (oce_adv_tra_fct.F90:425-455):
-// f = adf_v(k); (pa, ma) = R+/R- of layer k-1, (pk, mk) of layer k
-__device__ __forceinline__ double limit_v(double f, int k, int nzmin, int nzmax, double pa, double ma, double pk, double mk)
-{
-    double ae = 1.0;
-    if (k == nzmin) {                                                 // :430-438
-        ae = (f >= 0.0) ? dmin(ae, pk) : dmin(ae, mk);
-    } else if (k <= nzmax - 1) {                                      // :442-453
-        if (f >= 0.0) { ae = dmin(ae, ma); ae = dmin(ae, pk); }
-        else { ae = dmin(ae, pa); ae = dmin(ae, mk); }
-    }                                                                 // bottom interface untouched
-    return ae * f;
+    if (valid) stpm<TB>(b.pm + (size_t)oL * TB * 2, rp, rm);
+    // ---- vertical part of the update (oce_adv_tra_fct.F90:425-455 b3 vertical, driver :529-556 U1-U2): the limited
+    // vertical fluxes of a column need R+/R- of THIS column only, which this CTA has just computed, so the update of
+    // del_ttf_advvert happens here and k_fct_update no longer re-reads adf_v, fct_LO, ttf, hnode, hnode_new.
+    __syncthreads();                                  // everybody is done with the tvert exchange area
+#pragma unroll
+    for (int t = 0; t < TB; ++t) {
+        sm[(2 * t) * blockDim.x + threadIdx.x] = rp[t];
+        sm[(2 * t + 1) * blockDim.x + threadIdx.x] = rm[t];
+    }
+    __syncthreads();
+    if (!valid || n >= m.N) return;
+    const bool above = nz > th.nzmin, below = nz + 1 <= th.nzmax - 1;
+    const bool has_below = nz0 + 1 < L;
+    const double hn = park[(4 * TB) * pst];
+#pragma unroll
+    for (int t = 0; t < TB; ++t) {
+        const double tn_t = park[(4 * t) * pst], vt_t = park[(4 * t + 1) * pst], vb_t = park[(4 * t + 2) * pst], dv_t = park[(4 * t + 3) * pst];
+        const double* sp = sm + (2 * t) * blockDim.x + threadIdx.x;
+        const double* sn = sm + (2 * t + 1) * blockDim.x + threadIdx.x;
+        const double pa = above ? sp[-1] : 1.0, ma = above ? sn[-1] : 1.0;
+        const double pb = below ? sp[1] : 1.0, mb = below ? sn[1] : 1.0;
+        const double fv_top = limit_v(vt_t, nz, th.nzmin, th.nzmax, pa, ma, rp[t], rm[t]);
+        const double fv_bot = has_below ? limit_v(vb_t, nz + 1, th.nzmin, th.nzmax, rp[t], rm[t], pb, mb) : 0.0;
+        double d = dv_t;
+        d = d - tn_t * hn + lo_n[t] * hnn;                            // driver :535
+        d = d + div_rcp((fv_top - fv_bot) * dt, av, r_av);            // driver :556
+        b.dttf_v[t][oL] = d;
+    }
 }
 
 // ----------------------------------------------------------------------------------------------
-// K3: limit the antidiffusive fluxes and accumulate the tendencies.  Owned nodes: vertical +
-// horizontal; halo nodes: the partial horizontal sums the reference's edge scatter leaves there.
+// K3: limit the horizontal antidiffusive fluxes and accumulate del_ttf_advhoriz (the vertical part of the update
+// needs R+/R- of the own column only and runs at the end of k_fct_bounds).  Owned nodes and, on more than one rank,
+// halo nodes: the partial horizontal sums the reference's edge scatter leaves there.
 //   reference: oce_adv_tra_fct.F90:425-500 (b3), oce_adv_tra_driver.F90:529-633 (U1-U3)
 // ----------------------------------------------------------------------------------------------
 template <int TB, int G>
@@ -1284,25 +1325,14 @@ __global__ void ADV_K3_BOUNDS k_fct_update(MeshDev m, Chunk<TB> b, NodePart r, d
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int L = m.L, nl = m.nl;
-    node_cta_prefetch<3 * TB + 6>(m, r, [&](int q) {
-        const unsigned cl = (unsigned)L * 8u;
-        if (q < 3 * TB) {
-            const int t = q / 3, w = q - 3 * t;
-            return PfArr{w == 0 ? (const void*)b.dttf_h[t] : w == 1 ? (const void*)b.dttf_v[t] : (const void*)b.ttf[t], cl, 8u, 0};
-        }
-        switch (q - 3 * TB) {
-        case 0: return PfArr{b.pm, (unsigned)L * TB * 16u, TB * 16u, 0};
-        case 1: return PfArr{b.adf_v, (unsigned)nl * TB * 8u, TB * 8u, 1};
-        case 2: return PfArr{b.lo, (unsigned)L * TB * 8u, TB * 8u, 0};
-        case 3: return PfArr{m.areasvol, (unsigned)nl * 8u, 8u, 1};
-        case 4: return PfArr{m.hnode, cl, 8u, 0};
-        default: return PfArr{m.hnode_new, cl, 8u, 0};
-        }
+    node_cta_prefetch<TB + 2>(m, r, [&](int q) {
+        if (q < TB) return PfArr{(const void*)b.dttf_h[q], (unsigned)L * 8u, 8u, 0};
+        if (q == TB) return PfArr{b.pm, (unsigned)L * TB * 16u, TB * 16u, 0};
+        return PfArr{m.areasvol, (unsigned)nl * 8u, 8u, 1};
     }, (ADV_PF_OWN & 4) != 0);
     const NodeCta th = node_cta(m, r, smem_raw);
     const int n = th.n, nz = th.nz, nz0 = nz - 1;
     if (!th.valid) return;
-    const bool owned = n < m.N;
     const unsigned oL = (unsigned)n * L + nz0;
     const size_t cN = (size_t)n * nl + nz0;
     // ---- gather metadata first (its latency hides behind the vertical part) ----------------------
@@ -1317,30 +1347,6 @@ __global__ void ADV_K3_BOUNDS k_fct_update(MeshDev m, Chunk<TB> b, NodePart r, d
 #pragma unroll
     for (int t = 0; t < TB; ++t) dh[t] = b.dttf_h[t][oL];
     const double r_av = 1.0 / av;
-    // ---- vertical part (own column only), finished before the gather operands are loaded so that
-    //      the two register sets are never live together
-    if (owned) {
-        double vt[TB], vb[TB], pa[TB], ma[TB], pb[TB], mb[TB], lo_n[TB], tn[TB], dv[TB];
-        const bool above = nz > th.nzmin, below = nz + 1 <= th.nzmax - 1;
-        ldv<TB>(b.adf_v + cN * TB, vt);
-        ldv<TB>(b.adf_v + (cN + 1) * TB, vb);
-        ldv<TB>(b.lo + (size_t)oL * TB, lo_n);
-#pragma unroll
-        for (int t = 0; t < TB; ++t) { pa[t] = ma[t] = pb[t] = mb[t] = 1.0; tn[t] = __ldg(&b.ttf[t][oL]); dv[t] = b.dttf_v[t][oL]; }
-        if (above) ldpm<TB>(b.pm + (size_t)(oL - 1) * TB * 2, pa, ma);
-        if (below) ldpm<TB>(b.pm + (size_t)(oL + 1) * TB * 2, pb, mb);
-        const double hn = __ldg(&m.hnode[oL]), hnn = __ldg(&m.hnode_new[oL]);
-        const bool has_below = nz0 + 1 < L;
-#pragma unroll
-        for (int t = 0; t < TB; ++t) {
-            const double fv_top = limit_v(vt[t], nz, th.nzmin, th.nzmax, pa[t], ma[t], pk[t], mk[t]);
-            const double fv_bot = has_below ? limit_v(vb[t], nz + 1, th.nzmin, th.nzmax, pk[t], mk[t], pb[t], mb[t]) : 0.0;
-            double d = dv[t];
-            d = d - tn[t] * hn + lo_n[t] * hnn;                           // driver :535
-            d = d + div_rcp((fv_top - fv_bot) * dt, av, r_av);            // driver :556
-            b.dttf_v[t][oL] = d;
-        }
-    }
 #pragma unroll
     for (int j = 0; j < G; ++j) {
         const int lo = ent[j].z & 0xff, hi = (ent[j].z >> 8) & 0xff;
