@@ -288,9 +288,8 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
             // scatter range of oce_adv_tra_driver.F90:154-156: [min(nu1, nu2>0), max(nl1, nl2)]
             const int lo = lv.z > 0 ? std::min<int>(lv.x, lv.z) : lv.x;
             const int hi = std::max<int>(lv.y, lv.w);
-            const bool w1 = n1 < N;   // designated writer of adf_h(:,e) in k_nofct: edges(1,e) if owned, else edges(2,e)
-            ne_ent[fill[n1]++] = make_int4(e, n2, lo | (hi << 8) | (0 << 16) | ((w1 ? 1 : 0) << 17), 0);
-            ne_ent[fill[n2]++] = make_int4(e, n1, lo | (hi << 8) | (1 << 16) | ((w1 ? 0 : 1) << 17), 0);
+            ne_ent[fill[n1]++] = make_int4(e, n2, lo | (hi << 8) | (0 << 16), 0);
+            ne_ent[fill[n2]++] = make_int4(e, n1, lo | (hi << 8) | (1 << 16), 0);
         }
     }
     // FCT clusters (oce_adv_tra_fct.F90:148-215 collapsed): for owned node n the distinct nodes of
@@ -667,6 +666,7 @@ Chunk<TB> make_chunk(adv_ctx* c, const TrPtrs& p, const adv_tracer_desc_t* tr, c
         b.ph[t] = tr[i].tra_adv_ph; b.pv[t] = tr[i].tra_adv_pv;
     }
     b.lo = cb.lo.p; b.adf_h = cb.adf_h.p; b.adf_v = cb.adf_v.p; b.pm = cb.pm.p;
+    b.nolo = ch.fct ? 0 : 1;
     return b;
 }
 
@@ -760,11 +760,9 @@ int launch_phase(adv_ctx* c, Phase ph, int hor, int ver, bool q_stored, const Ch
         nthr = r.cpb * m.L;
         const size_t sm1 = (size_t)TB * nthr * sizeof(double);
         grid = nblocks(r.count, r.cpb);
-#define HV(H, V) if (hor == H && ver == V) k_nofct<H, V, TB><<<grid, nthr, sm1, s>>>(m, b, r, dt);
-        HV(HOR_UPW1, VER_UPW1) HV(HOR_UPW1, VER_QR4C) HV(HOR_UPW1, VER_PPM) HV(HOR_UPW1, VER_CDIFF)
-        HV(HOR_MUSCL, VER_UPW1) HV(HOR_MUSCL, VER_QR4C) HV(HOR_MUSCL, VER_PPM) HV(HOR_MUSCL, VER_CDIFF)
-        HV(HOR_MFCT, VER_UPW1) HV(HOR_MFCT, VER_QR4C) HV(HOR_MFCT, VER_PPM) HV(HOR_MFCT, VER_CDIFF)
-#undef HV
+#define NV(V) if (ver == V) k_nofct_update<V, TB><<<grid, nthr, sm1, s>>>(m, b, r, dt);
+        NV(VER_UPW1) NV(VER_QR4C) NV(VER_PPM) NV(VER_CDIFF)
+#undef NV
     } else {
         // FCT node kernels: wet-level compaction, CTA partition of the range built in adv_ctx_create
         const NodePart r = node_part(c, rid);
@@ -797,7 +795,7 @@ int launch_phase(adv_ctx* c, Phase ph, int hor, int ver, bool q_stored, const Ch
 #undef NODE_LAUNCH
     }
     ++c->launches;
-    static const char* names[] = {"k_edge_flux", "k_node_lo", "k_fct_bounds", "k_fct_update", "k_nofct"};
+    static const char* names[] = {"k_edge_flux", "k_node_lo", "k_fct_bounds", "k_fct_update", "k_nofct_update"};
     if (se != cudaSuccess) return fail(ADV_ECUDA, std::string(names[ph]) + " attributes: " + cudaGetErrorString(se));
     if (cudaError_t e = cudaGetLastError()) {
         return fail(ADV_ECUDA, std::string("launch ") + names[ph] + (piped ? "_b" : "") + " (grid " + std::to_string(grid) + ", block " + std::to_string(nthr) +
@@ -942,24 +940,20 @@ static int run_batch(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr
     };
     std::vector<double*> f1, s1, f2, s2;   // exchange field / send buffer lists over all FCT chunks
     std::vector<int> n1, n2;
-    bool any_fct = false, any_nofct = false;
+    bool any_fct = false;
     for (auto& ch : chunks) {
         if (ch.fct) {
             any_fct = true;
             ChunkBuf& cb = *c->cbufs[ch.buf];
             f1.push_back(cb.lo.p); s1.push_back(cb.sendbuf.p); n1.push_back(m.L * ch.tb);
             f2.push_back(cb.pm.p); s2.push_back(cb.sendbuf.p); n2.push_back(m.L * ch.tb * 2);
-        } else any_nofct = true;
+        }
     }
     mark(0);
-    // ---- phase 0: antidiffusive edge fluxes (the first launch of a step also produces Q)
-    for (auto& ch : chunks) if (ch.fct) run(PH_E1, ch, rAll);
-    if (any_nofct && !c->q_valid) {
-        k_edge_volflux<<<nblocks(m.E, cpb), cpb * m.L, 0, sc>>>(m, cpb);
-        ++c->launches;
-        c->q_valid = true;
-    }
-    // non-FCT tracers: one sweep, no exchange inside the path
+    // ---- phase 0: edge fluxes, every chunk (FCT: antidiffusive HO - LO; otherwise the HO flux itself); the first
+    //      launch of a step also produces Q
+    for (auto& ch : chunks) run(PH_E1, ch, rAll);
+    // non-FCT tracers: one more sweep, no exchange inside the path
     for (auto& ch : chunks)
         if (!ch.fct) run(PH_NOFCT, ch, multi ? rAllH : rAll);
     mark(1);

@@ -15,7 +15,7 @@
 //   k_fct_bounds   F1-F8: cluster bounds, P+/P- sums and the limiter factors R+/R-
 //   ------------------------------------------------------------ exchange_nod(fct_plus, fct_minus)
 //   k_fct_update   F10-F11 + U1-U3: limit and accumulate del_ttf_advhoriz / del_ttf_advvert
-//   k_nofct        D7/D8 + U2-U3 when tra_adv_lim /= 'FCT'
+//   k_nofct_update D8 + U2-U3 when tra_adv_lim /= 'FCT' (D7 by the edge kernel with Chunk::nolo)
 //   k_vert_impl    adv_tra_vert_impl (use_wsplit only)
 //   k_tracer_gradient_elements, k_fill_up_dn_grad   the producer of edge_up_dn_grad
 //   k_init_tracers_AB, k_update_values              prologue / epilogue of the dwarf iteration (row 2)
@@ -137,6 +137,8 @@ struct Chunk {
     double* dttf_v[TB];
     double ph[TB], pv[TB];
     double *lo, *adf_h, *adf_v, *pm;
+    int nolo;                 // 1: tra_adv_lim /= 'FCT' -- the edge kernel stores the high-order flux itself (o_init_zero = .true.,
+                              //    oce_adv_tra_driver.F90:339-346), not HO - LO
 };
 
 struct NodeRange {
@@ -251,39 +253,6 @@ __device__ __forceinline__ void edge_use(uchar4 lv, int nz, bool& use1, bool& us
     const bool inE = nz >= nl12 + 1 && nz <= nl2;
     use1 = inA || inC || inD;
     use2 = inB || inC || inE;
-}
-
-// Q(nz,e): vflux of oce_adv_tra_hor.F90:170,190,211-212,226,242
-__device__ __forceinline__ double edge_volflux(const MeshDev& m, int2 el, double4 cr, bool use1, bool use2, int nz0)
-{
-    double v1 = 0.0, v2 = 0.0;
-    if (use1) {
-        const unsigned o = (unsigned)el.x * m.L + nz0;
-        const double2 uv = __ldg(reinterpret_cast<const double2*>(m.uv) + o);
-        v1 = (-uv.y * cr.x + uv.x * cr.y) * __ldg(&m.helem[o]);
-    }
-    if (use2) {
-        const unsigned o = (unsigned)el.y * m.L + nz0;
-        const double2 uv = __ldg(reinterpret_cast<const double2*>(m.uv) + o);
-        v2 = (uv.y * cr.z - uv.x * cr.w) * __ldg(&m.helem[o]);
-    }
-    double q = 0.0;
-    if (use1 && use2) q = v1 + v2;
-    else if (use1) q = v1;
-    else if (use2) q = v2;
-    return q;
-}
-
-// stand-alone Q kernel (only the non-FCT path needs it; the FCT path fuses Q into k_edge_flux)
-__global__ void __launch_bounds__(kBlock) k_edge_volflux(MeshDev m, int epb)
-{
-    const ColThread c = col_thread(m);
-    const int e = blockIdx.x * epb + c.g;
-    if (e >= m.E) return;
-    const int nz = c.nz0 + 1;
-    bool use1, use2;
-    edge_use(m.edge_lev[e], nz, use1, use2);
-    m.Q[(size_t)e * m.L + c.nz0] = edge_volflux(m, m.edge_el[e], m.edge_cross[e], use1, use2, c.nz0);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -766,7 +735,7 @@ __global__ void __launch_bounds__(kBlock, ADV_E1_MINB) k_edge_flux(MeshDev m, Ch
         const double aq = fabs(q), qp = q + aq, qm = q - aq;
 #pragma unroll
         for (int t = 0; t < TB; ++t) {
-            const double flo = hor_lo(t1[t], t2[t], qp, qm);
+            const double flo = b.nolo ? 0.0 : hor_lo(t1[t], t2[t], qp, qm);
             out[t] = hor_ho<HOR>(a1[t], a2[t], q, qp, qm, ec, g12[t], g34[t], b.ph[t], clo1, clo2, flo);
         }
     }
@@ -1403,11 +1372,14 @@ __global__ void ADV_K3_BOUNDS k_fct_update(MeshDev m, Chunk<TB> b, NodePart r, d
 }
 
 // ----------------------------------------------------------------------------------------------
-// tra_adv_lim /= 'FCT': HO fluxes with o_init_zero=.true. and the plain tendency update
+// tra_adv_lim /= 'FCT': the edge kernel has stored the high-order horizontal flux (Chunk::nolo, o_init_zero=.true.);
+// this pass computes the high-order vertical flux and accumulates both tendencies -- an ordered gather of the edge
+// slots like k_fct_update, without limiter.  Round 1 recomputed every edge flux at both end nodes from a CSR walk and
+// read edge_up_dn_grad twice; now every flux is evaluated once, by the streaming edge kernel.
 //   reference: oce_adv_tra_driver.F90:339-379, :387, :551-633 (vertical velocity is `we`, :358)
 // ----------------------------------------------------------------------------------------------
-template <int HOR, int VER, int TB>
-__global__ void __launch_bounds__(kBlock) k_nofct(MeshDev m, Chunk<TB> b, NodeRange r, double dt)
+template <int VER, int TB>
+__global__ void __launch_bounds__(kBlock) k_nofct_update(MeshDev m, Chunk<TB> b, NodeRange r, double dt)
 {
     extern __shared__ double sm[];  // [TB][blockDim]
     const int L = m.L, nl = m.nl;
@@ -1446,9 +1418,9 @@ __global__ void __launch_bounds__(kBlock) k_nofct(MeshDev m, Chunk<TB> b, NodeRa
     const double av = m.areasvol[cN + nz0];
     const double r_av = 1.0 / av;
     const bool has_below = nz0 + 1 < L;
-    double dh[TB], tabn[TB];
+    double dh[TB];
 #pragma unroll
-    for (int t = 0; t < TB; ++t) { dh[t] = b.dttf_h[t][oL]; tabn[t] = b.ttfAB[t][oL]; }
+    for (int t = 0; t < TB; ++t) dh[t] = b.dttf_h[t][oL];
     if (owned) {
 #pragma unroll
         for (int t = 0; t < TB; ++t) {
@@ -1456,38 +1428,18 @@ __global__ void __launch_bounds__(kBlock) k_nofct(MeshDev m, Chunk<TB> b, NodeRa
             b.dttf_v[t][oL] = b.dttf_v[t][oL] + div_rcp((fv_top[t] - fv_bot) * dt, av, r_av);   // driver :556
         }
     }
-    const int nb_n = (HOR == HOR_MUSCL) ? m.nboundary_lay[n] : 0;
-    const int k1 = m.ne_ptr[n + 1];
-    for (int k = m.ne_ptr[n]; k < k1; ++k) {
-        const int4 ent = m.ne_ent[k];
+    const int4* ell = m.ne_ell + (size_t)n * m.ell_w;
+    for (int j = 0; j < tc.deg; ++j) {
+        const int4 ent = __ldg(&ell[j]);
         const int lo = ent.z & 0xff, hi = (ent.z >> 8) & 0xff;
         if (nz < lo || nz > hi) continue;
-        const int e = ent.x, mo = ent.y;
-        const bool second = (ent.z >> 16) & 1, writer = (ent.z >> 17) & 1;
-        const size_t oe = (size_t)e * L + nz0, om = (size_t)mo * L + nz0;
-        const double q = m.Q[oe];
-        const double aq = fabs(q), qp = q + aq, qm = q - aq;
-        double2 ec = make_double2(0.0, 0.0);
-        double clo_n = 1.0, clo_m = 1.0;
-        if (HOR != HOR_UPW1) ec = m.edge_c[e];
-        if (HOR == HOR_MUSCL) {
-            clo_n = (nb_n - nz >= 0) ? 1.0 : 0.0;
-            clo_m = (m.nboundary_lay[mo] - nz >= 0) ? 1.0 : 0.0;
-        }
+        double f[TB];
+        ldv<TB>(b.adf_h + ((size_t)(unsigned)ent.x * L + nz0) * TB, f);
+        const bool second = (ent.z >> 16) & 1;
 #pragma unroll
         for (int t = 0; t < TB; ++t) {
-            const double tabm = b.ttfAB[t][om];
-            const double a1 = second ? tabm : tabn[t], a2 = second ? tabn[t] : tabm;
-            double2 g12 = make_double2(0.0, 0.0), g34 = g12;
-            if (HOR != HOR_UPW1) {
-                const double2* gp = reinterpret_cast<const double2*>(b.grad[t]) + oe * 2;
-                g12 = __ldg(gp); g34 = __ldg(gp + 1);
-            }
-            const double f = hor_ho<HOR>(a1, a2, q, qp, qm, ec, g12, g34, b.ph[t], second ? clo_m : clo_n,
-                                         second ? clo_n : clo_m, 0.0);
-            const double term = div_rcp(f * dt, av, r_av);                          // driver :607,:620
+            const double term = div_rcp(f[t] * dt, av, r_av);                       // driver :607,:620
             dh[t] = second ? dh[t] - term : dh[t] + term;
-            if (writer && owned) b.adf_h[oe * TB + t] = f;
         }
     }
 #pragma unroll

@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(kBlock, ADV_E1P_MINB) k_edge_flux_b(MeshDev m,
                     const double2* gp = reinterpret_cast<const double2*>(sp + (size_t)t * epb * colw) + (size_t)tid * 2;
                     g12 = gp[0]; g34 = gp[1];
                 }
-                const double flo = hor_lo(t1[t], t2[t], qp, qm);
+                const double flo = b.nolo ? 0.0 : hor_lo(t1[t], t2[t], qp, qm);
                 out[t] = hor_ho<HOR>(a1[t], a2[t], q, qp, qm, ec, g12, g34, b.ph[t], clo1, clo2, flo);
             }
         }
