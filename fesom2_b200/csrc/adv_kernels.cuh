@@ -1204,8 +1204,9 @@ __global__ void ADV_K2_BOUNDS k_fct_bounds(MeshDev m, Chunk<TB> b, NodePart r, d
                     tmax[t] = hi2 > tmax[t] ? hi2 : tmax[t];                  // a2 :166, a3 :209
                     tmin[t] = lo2 < tmin[t] ? lo2 : tmin[t];
                     const double a = second ? -f[j][t] : f[j][t];             // fct :342,:346 / :360,:364
-                    pp[t] = pp[t] + dmax(0.0, a);
-                    pn[t] = pn[t] + dmin(0.0, a);
+                    // pp += max(0,a); pn += min(0,a): exactly one addend is non-zero, and adding +0.0 changes nothing
+                    // (pp >= +0, pn <= +0 and never -0.0: both start as 0.0 + x), so one compare and two predicated adds
+                    if (a > 0.0) pp[t] = pp[t] + a; else pn[t] = pn[t] + a;
                 }
             }
             j0 += G;
