@@ -1200,9 +1200,12 @@ int adv_exchange_elem(adv_ctx_t* c, int nfields, double* const* fields, int nwor
     return exchange_fields(c, HALO_ELEM, nfields, fields, nwords);
 }
 
-int adv_vert_vel_ale(adv_ctx_t* c, double dt, int use_wsplit, double wsplit_maxcfl, double* w, double* w_e, double* w_i, double* cfl_z)
+static int vert_vel_ale_impl(adv_ctx_t* c, double dt, int use_wsplit, double wsplit_maxcfl, const adv_zstar_desc_t* z,
+                             double* w, double* w_e, double* w_i, double* cfl_z)
 {
     if (!c || !w || !w_e || !w_i) return fail(ADV_EINVAL, "adv_vert_vel_ale: null argument");
+    if (z && (!z->hbar || !z->hbar_old || !z->water_flux || !z->nlevels_nod2D_min || !z->hnode_new))
+        return fail(ADV_EINVAL, "adv_vert_vel_ale_zstar: null field in the zstar descriptor");
     if (!c->state_set) return fail(ADV_ESTATE, "adv_ctx_set_state has not been called");
     if (c->npes > 1 && !c->comm && !c->lc) return fail(ADV_ESTATE, "adv_ctx_comm_init was not called");
     CU(cudaSetDevice(c->device));
@@ -1211,16 +1214,35 @@ int adv_vert_vel_ale(adv_ctx_t* c, double dt, int use_wsplit, double wsplit_maxc
     const NodeRange rAll{nullptr, 0, m.N, cpb, 0, 0};
     k_vert_vel_ale<<<nblocks(m.N, cpb), cpb * m.L, (size_t)cpb * m.L * sizeof(double), c->s_comp>>>(m, rAll, w);
     ++c->launches;
+    if (z) {                                                      // which_ALE = 'zstar', src/oce_ale.F90:2539-2603
+        k_vert_vel_zstar<<<nblocks(m.N, cpb), cpb * m.L, 0, c->s_comp>>>(m, rAll, dt, z->nlevels_nod2D_min, z->hbar, z->hbar_old,
+                                                                         z->water_flux, w, z->hnode_new);
+        ++c->launches;
+    }
     CU(cudaGetLastError());
-    if (c->npes > 1) {                                            // exchange_nod(Wvel), src/oce_ale.F90:2654
+    if (c->npes > 1) {                                            // exchange_nod(Wvel), exchange_nod(hnode_new): :2654-2655
         double* f[1] = {w};
         if (int rc = exchange_fields(c, HALO_NOD, 1, f, m.nl)) return rc;
+        if (z) { double* h[1] = {z->hnode_new}; if (int rc = exchange_fields(c, HALO_NOD, 1, h, m.L)) return rc; }
     }
     const size_t n = (size_t)m.Nh * m.nl;
-    k_cflz_wsplit<<<(unsigned)((n + 255) / 256), 256, 0, c->s_comp>>>(m, dt, use_wsplit ? 1 : 0, wsplit_maxcfl, w, w_e, w_i, cfl_z);
+    k_cflz_wsplit<<<(unsigned)((n + 255) / 256), 256, 0, c->s_comp>>>(m, z ? z->hnode_new : m.hnode_new, dt, use_wsplit ? 1 : 0, wsplit_maxcfl,
+                                                                     w, w_e, w_i, cfl_z);
     ++c->launches;
     CU(cudaGetLastError());
     return ADV_OK;
+}
+
+int adv_vert_vel_ale(adv_ctx_t* c, double dt, int use_wsplit, double wsplit_maxcfl, double* w, double* w_e, double* w_i, double* cfl_z)
+{
+    return vert_vel_ale_impl(c, dt, use_wsplit, wsplit_maxcfl, nullptr, w, w_e, w_i, cfl_z);
+}
+
+int adv_vert_vel_ale_zstar(adv_ctx_t* c, double dt, int use_wsplit, double wsplit_maxcfl, const adv_zstar_desc_t* z,
+                           double* w, double* w_e, double* w_i, double* cfl_z)
+{
+    if (!z) return fail(ADV_EINVAL, "adv_vert_vel_ale_zstar: null descriptor");
+    return vert_vel_ale_impl(c, dt, use_wsplit, wsplit_maxcfl, z, w, w_e, w_i, cfl_z);
 }
 
 int adv_update_values(adv_ctx_t* c, int ntr, double* const* values, const double* const* dh, const double* const* dv)

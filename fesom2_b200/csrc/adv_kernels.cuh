@@ -1075,11 +1075,38 @@ __global__ void __launch_bounds__(kBlock) k_vert_vel_ale(MeshDev m, NodeRange r,
     if (nz0 == L - 1) W[cN + 1] = 0.0;                          // interface nl
 }
 
+// vert_vel_ale, 'zstar' correction (src/oce_ale.F90:2539-2603): the elevation change hbar - hbar_old is distributed over
+// the layers above the shallowest bottom around the node (Wvel and hnode_new), the surface fresh-water flux closes
+// the continuity at the top.  Owned, cavity-free columns; one thread per (column, layer), no dependence between layers.
+__global__ void __launch_bounds__(kBlock) k_vert_vel_zstar(MeshDev m, NodeRange r, double dt, const int* __restrict__ nmin,
+                                                           const double* __restrict__ hbar, const double* __restrict__ hbar_old,
+                                                           const double* __restrict__ wflux, double* __restrict__ W, double* __restrict__ hnode_new)
+{
+    const NodeThread th = node_thread(m, r);
+    if (!th.active || th.nzmin != 1) return;                                        // :2550
+    const int n = th.n, nz = th.nz0 + 1, nzmin = th.nzmin, nzmax = __ldg(&nmin[n]) - 1;
+    const double* zb = m.zbar3d + (size_t)n * m.nl;
+    const double dd1 = __ldg(&zb[nzmax - 1]);
+    double dd = __ldg(&zb[nzmin - 1]) - dd1;
+    dd = (__ldg(&hbar[n]) - __ldg(&hbar_old[n])) / dd;
+    const double dddt = dd / dt;
+    const size_t cN = (size_t)n * m.nl + th.nz0, oL = (size_t)n * m.L + th.nz0;
+    if (nz >= nzmin && nz <= nzmax - 1) {                                           // :2574-2589
+        double w = W[cN];
+        w = w - (__ldg(&zb[nz - 1]) - dd1) * dddt;
+        if (nz == nzmin) w = w - __ldg(&wflux[n]);                                  // :2595
+        W[cN] = w;
+        hnode_new[oL] = __ldg(&m.hnode[oL]) + (__ldg(&zb[nz - 1]) - __ldg(&zb[nz])) * dd;
+    } else if (nz == nzmin) {
+        W[cN] = W[cN] - __ldg(&wflux[n]);                                           // empty stretch range: only the flux
+    }
+}
+
 // compute_CFLz (src/oce_ale.F90:2933-2952, without the diagnostic print) and compute_Wvel_split (:3033-3047):
 // one thread per (interface, node) over all myDim+eDim columns.  CFL_z(nz) = c2 of the layer above, then + c1 of
 // the layer below, in that order; W_e / W_i are written for nzmin..nlevels_nod2D only, like the reference.
-__global__ void __launch_bounds__(256) k_cflz_wsplit(MeshDev m, double dt, int use_wsplit, double maxcfl, const double* __restrict__ W,
-                                                     double* __restrict__ We, double* __restrict__ Wi, double* __restrict__ cflz)
+__global__ void __launch_bounds__(256) k_cflz_wsplit(MeshDev m, const double* __restrict__ hnode_new, double dt, int use_wsplit, double maxcfl,
+                                                     const double* __restrict__ W, double* __restrict__ We, double* __restrict__ Wi, double* __restrict__ cflz)
 {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)m.Nh * m.nl) return;
@@ -1088,8 +1115,8 @@ __global__ void __launch_bounds__(256) k_cflz_wsplit(MeshDev m, double dt, int u
     const int nzmin = lv.x, nlev = lv.y, nzmax = nlev - 1;
     const double w = W[idx];
     double cfl = 0.0;
-    if (nz - 1 >= nzmin && nz - 1 <= nzmax) cfl = fabs(w * dt / __ldg(&m.hnode_new[(size_t)n * m.L + nz - 2]));            // c2 of layer nz-1
-    if (nz >= nzmin && nz <= nzmax) cfl = cfl + fabs(w * dt / __ldg(&m.hnode_new[(size_t)n * m.L + nz - 1]));              // + c1 of layer nz
+    if (nz - 1 >= nzmin && nz - 1 <= nzmax) cfl = fabs(w * dt / __ldg(&hnode_new[(size_t)n * m.L + nz - 2]));            // c2 of layer nz-1
+    if (nz >= nzmin && nz <= nzmax) cfl = cfl + fabs(w * dt / __ldg(&hnode_new[(size_t)n * m.L + nz - 1]));              // + c1 of layer nz
     if (cflz) cflz[idx] = cfl;
     if (nz < nzmin || nz > nlev) return;
     double we = w, wi = 0.0;

@@ -96,6 +96,14 @@ module oce_adv_tra_b200
      type(c_ptr) :: sPE, sptr, slist
   end type adv_gradient_mesh_desc_t
 
+  ! adv_zstar_desc_t
+  type, bind(C) :: adv_zstar_desc_t
+     type(c_ptr) :: hbar, hbar_old
+     type(c_ptr) :: water_flux
+     type(c_ptr) :: nlevels_nod2D_min
+     type(c_ptr) :: hnode_new
+  end type adv_zstar_desc_t
+
   interface
      integer(c_int) function adv_ctx_create(ctx, mesh, device, max_tracers) bind(C, name='adv_ctx_create')
        import :: c_int, c_ptr, adv_mesh_desc_t
@@ -186,6 +194,25 @@ module oce_adv_tra_b200
        integer(c_int), value :: nfields
        type(c_ptr), intent(in) :: fields(*)
        integer(c_int), value :: nlev
+     end function
+     ! vert_vel_ale (continuity part, exchange, compute_CFLz, compute_Wvel_split) for linfs / zstar, src/oce_ale.F90:2107-2668
+     integer(c_int) function adv_vert_vel_ale(ctx, dt, use_wsplit, wsplit_maxcfl, w, w_e, w_i, cfl_z) bind(C, name='adv_vert_vel_ale')
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value    :: ctx
+       real(c_double), value :: dt
+       integer(c_int), value :: use_wsplit
+       real(c_double), value :: wsplit_maxcfl
+       type(c_ptr), value    :: w, w_e, w_i, cfl_z
+     end function
+     integer(c_int) function adv_vert_vel_ale_zstar(ctx, dt, use_wsplit, wsplit_maxcfl, z, w, w_e, w_i, cfl_z) &
+                                                    bind(C, name='adv_vert_vel_ale_zstar')
+       import :: c_ptr, c_int, c_double, adv_zstar_desc_t
+       type(c_ptr), value    :: ctx
+       real(c_double), value :: dt
+       integer(c_int), value :: use_wsplit
+       real(c_double), value :: wsplit_maxcfl
+       type(adv_zstar_desc_t), intent(in) :: z
+       type(c_ptr), value    :: w, w_e, w_i, cfl_z
      end function
      integer(c_int) function adv_ctx_wait_for(ctx, stream) bind(C, name='adv_ctx_wait_for')
        import :: c_ptr, c_int

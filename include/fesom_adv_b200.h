@@ -184,6 +184,19 @@ int adv_update_values(adv_ctx_t *ctx, int ntr, double *const *values,
  * The result becomes the path's input with the next adv_ctx_set_state. */
 int adv_vert_vel_ale(adv_ctx_t *ctx, double dt, int use_wsplit, double wsplit_maxcfl,
                      double *w, double *w_e, double *w_i, double *cfl_z);
+/* The same for which_ALE = 'zstar' (the reference's default, config/namelist.config:71): after the continuity part the
+ * elevation change hbar - hbar_old is distributed over the layers above the shallowest bottom around each owned,
+ * cavity-free node -- Wvel and hnode_new, src/oce_ale.F90:2539-2603 --, the surface fresh-water flux closes the
+ * continuity at the top, then exchange_nod(Wvel) and exchange_nod(hnode_new) (:2654-2655); compute_CFLz uses the new
+ * hnode_new.  All arrays are DEVICE arrays.  The 'zlevel' variant (:2336-2538) is not built. */
+typedef struct {
+    const double  *hbar, *hbar_old;      /* (Nh) mesh%hbar, mesh%hbar_old                              */
+    const double  *water_flux;           /* (Nh) o_ARRAYS water_flux                                   */
+    const int32_t *nlevels_nod2D_min;    /* (Nh) mesh%nlevels_nod2D_min                                */
+    double        *hnode_new;            /* (nl-1, Nh) inout: the stretched layers of the owned nodes are rewritten from hnode */
+} adv_zstar_desc_t;
+int adv_vert_vel_ale_zstar(adv_ctx_t *ctx, double dt, int use_wsplit, double wsplit_maxcfl, const adv_zstar_desc_t *z,
+                           double *w, double *w_e, double *w_i, double *cfl_z);
 
 /* The prologue of the tracer step, `init_tracers_AB(tr_num, tracers, partit, mesh)`
  * (src/oce_tracer_mod.F90:13-123) without its gradient calls, for ntr tracers: zeroes del_ttf /

@@ -982,3 +982,33 @@ void ora_compute_wvel_split(const ora_mesh_t *m, int use_wsplit, double wsplit_m
 #undef C_W
 #undef C_C
 }
+
+/* ====================================================================================================
+ * vert_vel_ale, the 'zstar' correction for the free surface (src/oce_ale.F90:2539-2603): the change of the
+ * elevation hbar - hbar_old is distributed over the layers above the shallowest bottom around the node, the
+ * surface fresh-water flux closes the continuity at the top.  Owned nodes without a cavity (ulevels_nod2D = 1).
+ * Wvel (nl, Nh) in/out, hnode_new (nl-1, Nh) in/out (only the stretched layers are written).
+ * ==================================================================================================== */
+void ora_vert_vel_ale_zstar(const ora_mesh_t *m, double dt, const int *nlevels_nod2D_min, const double *hbar,
+                            const double *hbar_old, const double *water_flux, double *Wvel, double *hnode_new)
+{
+    const int nl = m->nl, L = nl - 1;
+#define Z_W(nz, n) Wvel[(size_t)((n) - 1) * nl + ((nz) - 1)]
+#define Z_ZB(nz, n) m->zbar_3d_n[(size_t)((n) - 1) * nl + ((nz) - 1)]
+    for (int n = 1; n <= m->myDim_nod2D; ++n) {
+        const int nzmin = m->ulevels_nod2D[n - 1];
+        const int nzmax = nlevels_nod2D_min[n - 1] - 1;
+        if (nzmin != 1) continue;                                                   /* :2550 */
+        const double dd1 = Z_ZB(nzmax, n);                                          /* :2558 */
+        double dd = Z_ZB(nzmin, n) - dd1;                                           /* :2562 */
+        dd = (hbar[n - 1] - hbar_old[n - 1]) / dd;                                  /* :2566 */
+        const double dddt = dd / dt;                                                /* :2570 */
+        for (int nz = nzmin; nz <= nzmax - 1; ++nz) {                               /* :2574-2589 */
+            Z_W(nz, n) = Z_W(nz, n) - (Z_ZB(nz, n) - dd1) * dddt;
+            hnode_new[(size_t)(n - 1) * L + (nz - 1)] = m->hnode[(size_t)(n - 1) * L + (nz - 1)] + (Z_ZB(nz, n) - Z_ZB(nz + 1, n)) * dd;
+        }
+        Z_W(nzmin, n) = Z_W(nzmin, n) - water_flux[n - 1];                          /* :2595 */
+    }
+#undef Z_W
+#undef Z_ZB
+}

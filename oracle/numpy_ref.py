@@ -500,3 +500,27 @@ def compute_cflz_and_split(mesh, hnode_new, dt, W, use_wsplit, wsplit_maxcfl):
         we = np.where(big, (1.0 / (1.0 + dd)) * W, we)
         wi = np.where(big, (dd / (1.0 + dd)) * W, wi)
     return cfl, we, wi
+
+
+def vert_vel_ale_zstar(mesh, zbar_3d_n, hnode, hnode_new, dt, W, hbar, hbar_old, water_flux):
+    """src/oce_ale.F90:2539-2603, whole-array: returns (W, hnode_new) with the zstar correction applied to the owned,
+    cavity-free columns."""
+    N, L, nl = mesh.N, mesh.L, mesh.nl
+    W, hn = np.array(W, dtype=np.float64), np.array(hnode_new, dtype=np.float64)
+    zb = np.asarray(zbar_3d_n, dtype=np.float64)[:N]
+    uln = np.asarray(mesh.ulevels_nod2D)[:N]
+    nzmax = np.asarray(mesh.nlevels_nod2D_min)[:N] - 1
+    rows = np.arange(N)
+    dd1 = zb[rows, nzmax - 1]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dd = (np.asarray(hbar)[:N] - np.asarray(hbar_old)[:N]) / (zb[rows, uln - 1] - dd1)
+        dddt = dd / dt
+    k = np.arange(1, nl + 1)[None, :]
+    sel = (uln == 1)[:, None] & (k >= uln[:, None]) & (k <= (nzmax - 1)[:, None])          # layers nzmin .. nzmax-1
+    Wn = W[:N]
+    Wn[sel] = (Wn - (zb - dd1[:, None]) * dddt[:, None])[sel]
+    hsel = sel[:, :L]
+    hn[:N][hsel] = (np.asarray(hnode)[:N] + (zb[:, :L] - zb[:, 1:]) * dd[:, None])[hsel]
+    top = uln == 1
+    Wn[top, 0] = Wn[top, 0] - np.asarray(water_flux)[:N][top]
+    return W, hn

@@ -341,3 +341,17 @@ def compute_cflz_and_split(rank: "OracleRank", dt: float, Wvel: np.ndarray, use_
     L_.ora_compute_cflz(C.byref(rank.cmesh), float(dt), _dp(W), _dp(cfl))
     L_.ora_compute_wvel_split(C.byref(rank.cmesh), int(bool(use_wsplit)), float(wsplit_maxcfl), _dp(W), _dp(cfl), _dp(we), _dp(wi))
     return cfl, we, wi
+
+
+def vert_vel_ale_zstar(rank: "OracleRank", dt: float, Wvel: np.ndarray, hbar, hbar_old, water_flux):
+    """ora_vert_vel_ale_zstar: returns (Wvel, hnode_new) after the zstar correction; the rank's hnode_new is the start."""
+    L_ = lib()
+    L_.ora_vert_vel_ale_zstar.argtypes = [C.POINTER(OraMesh), C.c_double, c_ip, c_dp, c_dp, c_dp, c_dp, c_dp]
+    L_.ora_vert_vel_ale_zstar.restype = None
+    m = rank.mesh_py
+    W = np.ascontiguousarray(Wvel, dtype=np.float64).copy()
+    hn = rank.keep["hnode_new"].copy()
+    nmin = np.ascontiguousarray(m.nlevels_nod2D_min, dtype=np.int32)
+    a = [np.ascontiguousarray(x, dtype=np.float64) for x in (hbar, hbar_old, water_flux)]
+    L_.ora_vert_vel_ale_zstar(C.byref(rank.cmesh), float(dt), _ip(nmin), _dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(W), _dp(hn))
+    return W, hn

@@ -57,7 +57,7 @@ def f_types():
 
 def test_bind_c_types_match_the_header_structs():
     cs, fs = c_structs(), f_types()
-    assert set(fs) == {"adv_mesh_desc_t", "adv_state_desc_t", "adv_tracer_desc_t", "adv_gradient_mesh_desc_t"}
+    assert set(fs) == {"adv_mesh_desc_t", "adv_state_desc_t", "adv_tracer_desc_t", "adv_gradient_mesh_desc_t", "adv_zstar_desc_t"}
     for name, ff in fs.items():
         assert name in cs, name
         assert ff == cs[name], (name, [x for x in zip(ff, cs[name]) if x[0] != x[1]][:3], len(ff), len(cs[name]))
@@ -75,7 +75,7 @@ def c_prototypes():
                 continue
             if re.match(r"adv_ctx_t \*\*\w+$", a):
                 kinds.append("ptr&")                                  # pointer returned through the argument
-            elif re.match(r"(const )?adv_ctx_t \*\w+$", a) or re.match(r"void \*\w+$", a):
+            elif re.match(r"(const )?adv_ctx_t \*\w+$", a) or re.match(r"void \*\w+$", a) or re.match(r"(const )?double \*\w+$", a):
                 kinds.append("ptr")
             elif re.match(r"const (adv_\w+_desc_t) \*\w+$", a):
                 kinds.append("ref:" + re.match(r"const (adv_\w+_desc_t)", a).group(1))
@@ -141,7 +141,7 @@ def test_interface_blocks_match_the_c_prototypes():
     must = {"adv_ctx_create", "adv_ctx_destroy", "adv_last_error", "adv_comm_unique_id", "adv_ctx_comm_init", "adv_ctx_set_state",
             "adv_ctx_set_state_step", "adv_do_oce_adv_tra", "adv_ctx_set_gradient_mesh", "adv_tracer_gradient_elements",
             "adv_fill_up_dn_grad", "adv_exchange_elem", "adv_init_tracers_AB", "adv_update_values", "adv_exchange_nod",
-            "adv_ctx_wait_for", "adv_ctx_signal", "adv_ctx_synchronize"}
+            "adv_ctx_wait_for", "adv_ctx_signal", "adv_ctx_synchronize", "adv_vert_vel_ale", "adv_vert_vel_ale_zstar"}
     assert must <= set(fi), must - set(fi)
     for name, fk in fi.items():
         assert name in cp, name

@@ -128,3 +128,63 @@ def test_local_ranks_wsplit_and_vert_vel(world, pi_mesh):
             assert np.array_equal(rk["dh"][k][:loc.N].cpu().numpy(), ora.dttf_h[k][own])
             assert np.array_equal(rk["dv"][k][:loc.N].cpu().numpy(), ora.dttf_v[k][own])
         rk["ctx"].close()
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_vert_vel_ale_zstar(world, pi_mesh):
+    """which_ALE = 'zstar' (the reference's default): continuity part + elevation change distributed over the layers
+    (Wvel, hnode_new) + fresh-water flux + both exchanges + CFLz/split with the NEW hnode_new, against the oracle chain"""
+    import threading
+    from oracle import oracle_py as O
+    from fesom2_b200.driver import AdvB200, comm_init_local
+    g = pi_mesh
+    st, trs, nb_g, dt = make_case(g, 1)
+    dtc = 40.0 * dt
+    ids = np.arange(g.Nh, dtype=np.float64)
+    hbar_old = 0.05 * np.sin(0.37 * ids)
+    hbar = hbar_old + 0.01 * np.cos(0.11 * ids)
+    wflux = 1.0e-6 * np.sin(0.05 * ids)
+    rk = O.OracleRank(g, st, trs, nb_g)
+    W0 = O.vert_vel_ale_core(rk)
+    W, hn = O.vert_vel_ale_zstar(rk, dtc, W0, hbar, hbar_old, wflux)
+    rk.keep["hnode_new"][...] = hn                     # compute_CFLz sees the new thickness
+    cfl, we, wi = O.compute_cflz_and_split(rk, dtc, W, True, 0.5)
+    ndev = torch.cuda.device_count()
+    part = g.parts[world] if world > 1 else np.zeros(g.Nh, np.int32)
+    ranks = []
+    for r in range(world):
+        loc = M.localize(g, part, r) if world > 1 else g
+        lst = F.scatter_to_local(g, loc, st, trs)[0] if world > 1 else st
+        alln = (loc.myList_nod2D.astype(np.int64) - 1) if world > 1 else np.arange(g.Nh)
+        dev = torch.device(f"cuda:{r % ndev}")
+        st_d, _ = to_device(lst, [], dev)
+        ctx = AdvB200(loc, nb_g[alln], device=r % ndev, max_tracers=1)
+        t = lambda a, dt_=torch.float64: torch.as_tensor(np.ascontiguousarray(a[alln]), dtype=dt_, device=dev)   # noqa: E731
+        ranks.append(dict(loc=loc, ctx=ctx, st=st_d, alln=alln, err=None, hbar=t(hbar), hbar_old=t(hbar_old), wflux=t(wflux),
+                          nmin=torch.as_tensor(np.ascontiguousarray(g.nlevels_nod2D_min[alln]), dtype=torch.int32, device=dev),
+                          out=[torch.zeros((loc.Nh, loc.nl), dtype=torch.float64, device=dev) for _ in range(4)]))
+    if world > 1:
+        comm_init_local([rk_["ctx"] for rk_ in ranks])
+    torch.cuda.synchronize()
+
+    def work(q):
+        try:
+            ctx, s = q["ctx"], q["st"]
+            torch.cuda.set_device(ctx.device)
+            ctx.set_state(s)
+            ctx.vert_vel_ale_zstar(dtc, True, 0.5, q["hbar"], q["hbar_old"], q["wflux"], q["nmin"], s.hnode_new, *q["out"])
+            ctx.synchronize()
+        except Exception as ex:
+            q["err"] = ex
+    th = [threading.Thread(target=work, args=(q,)) for q in ranks]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    for q in ranks:
+        if q["err"] is not None:
+            raise q["err"]
+        a = q["alln"]
+        for got, ref, name in zip(q["out"], (W, we, wi, cfl), ("w", "w_e", "w_i", "cfl_z")):
+            assert np.array_equal(got.cpu().numpy(), ref[a]), (name, world)
+        assert np.array_equal(q["st"].hnode_new.cpu().numpy(), hn[a])
+        q["ctx"].close()
+    assert (wi != 0).any() and not np.array_equal(hn, st.hnode_new.numpy())

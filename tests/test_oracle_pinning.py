@@ -228,3 +228,21 @@ def test_cflz_and_wvel_split_two_restatements(pi_mesh, use_wsplit):
     if use_wsplit:
         assert (a[2] != 0.0).any(), "nothing went implicit: the test does not exercise the split"
         assert np.abs(a[1] + a[2] - np.where(a[1] != 0, W, 0.0)).max() <= 1e-15 * np.abs(W).max()
+
+
+def test_vert_vel_ale_zstar_two_restatements(pi_mesh):
+    """the zstar free-surface correction of vert_vel_ale (src/oce_ale.F90:2539-2603): C loop vs whole-array NumPy"""
+    from oracle import numpy_ref as R, oracle_py as O
+    g = pi_mesh
+    st, trs, nb, dt = make_case(g, 1)
+    rk = O.OracleRank(g, st, trs, nb)
+    W = O.vert_vel_ale_core(rk)
+    ids = np.arange(g.Nh, dtype=np.float64)
+    hbar_old = 0.05 * np.sin(0.37 * ids)
+    hbar = hbar_old + 0.01 * np.cos(0.11 * ids)
+    wflux = 1.0e-6 * np.sin(0.05 * ids)
+    a = O.vert_vel_ale_zstar(rk, 1800.0, W, hbar, hbar_old, wflux)
+    b = R.vert_vel_ale_zstar(g, st.zbar_3d_n.numpy(), st.hnode.numpy(), st.hnode_new.numpy(), 1800.0, W, hbar, hbar_old, wflux)
+    for x, y in zip(a, b):
+        assert np.isfinite(x).all() and np.array_equal(x, y)
+    assert not np.array_equal(a[0], W) and not np.array_equal(a[1], st.hnode_new.numpy())
