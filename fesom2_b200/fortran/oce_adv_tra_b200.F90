@@ -229,6 +229,9 @@ module oce_adv_tra_b200
   end interface
 
   type(c_ptr), save :: adv_b200_ctx = c_null_ptr   ! one context per MPI rank (one rank <-> one GPU)
+  ! .true.: the library computes edge_up_dn_grad itself (tracer_gradient_elements, exchange_elem, fill_up_dn_grad on
+  ! the device; the wrapper then passes a NULL gradient pointer and the 4 E (nl-1) words per tracer never cross PCIe)
+  logical, save :: adv_b200_device_gradients = .false.
 
 contains
 
@@ -237,7 +240,7 @@ contains
   ! static mesh slice, builds the gather lists and the NCCL communicator.  The descriptor's arrays are
   ! always HOST arrays (the library copies them).
   !-----------------------------------------------------------------------------
-  subroutine adv_b200_init(tracers, partit, mesh, device)
+  subroutine adv_b200_init(tracers, partit, mesh, device, device_gradients)
     use MOD_MESH
     use MOD_TRACER
     use MOD_PARTIT
@@ -247,7 +250,9 @@ contains
     type(t_partit), intent(inout), target :: partit
     type(t_mesh),   intent(in),    target :: mesh
     integer,        intent(in)            :: device
+    logical,        intent(in), optional  :: device_gradients
     type(adv_mesh_desc_t) :: d
+    type(adv_gradient_mesh_desc_t) :: gd
     character(kind=c_char) :: id(128)
     integer :: rc, ierr
 
@@ -277,6 +282,27 @@ contains
        if (partit%mype == 0) call check(adv_comm_unique_id(id), partit)
        call MPI_Bcast(id, 128, MPI_BYTE, 0, partit%MPI_COMM_FESOM, ierr)   ! replaces init_mpi_types for this path
        call check(adv_ctx_comm_init(adv_b200_ctx, id), partit)
+    end if
+
+    if (present(device_gradients)) adv_b200_device_gradients = device_gradients
+    if (adv_b200_device_gradients) then
+       ! static inputs of tracer_gradient_elements / fill_up_dn_grad (src/oce_tracer_mod.F90:146-188,
+       ! src/oce_muscl_adv.F90:356-525) and the element halo of tr_xy (com_elem2D_full); call after muscl_adv_init
+       gd%n_elem = partit%myDim_elem2D + partit%eDim_elem2D + partit%eXDim_elem2D
+       gd%n_nod_in_elem = size(mesh%nod_in_elem2D, 2)
+       gd%nod_in_elem2D_ld = size(mesh%nod_in_elem2D, 1)
+       gd%nod_in_elem2D = c_loc(mesh%nod_in_elem2D); gd%nod_in_elem2D_num = c_loc(mesh%nod_in_elem2D_num)
+       gd%nlevels = c_loc(mesh%nlevels);             gd%ulevels = c_loc(mesh%ulevels)
+       gd%edge_up_dn_tri = c_loc(tracers%work%edge_up_dn_tri)
+       gd%nlevels_nod2D_min = c_loc(mesh%nlevels_nod2D_min); gd%ulevels_nod2D_max = c_loc(mesh%ulevels_nod2D_max)
+       gd%gradient_sca = c_loc(mesh%gradient_sca);   gd%elem_area = c_loc(mesh%elem_area)
+       gd%rPEnum = partit%com_elem2D_full%rPEnum
+       gd%rPE = c_loc(partit%com_elem2D_full%rPE); gd%rptr = c_loc(partit%com_elem2D_full%rptr)
+       gd%rlist = c_loc(partit%com_elem2D_full%rlist)
+       gd%sPEnum = partit%com_elem2D_full%sPEnum
+       gd%sPE = c_loc(partit%com_elem2D_full%sPE); gd%sptr = c_loc(partit%com_elem2D_full%sptr)
+       gd%slist = c_loc(partit%com_elem2D_full%slist)
+       call check(adv_ctx_set_gradient_mesh(adv_b200_ctx, gd), partit)
     end if
   end subroutine adv_b200_init
 
@@ -355,6 +381,7 @@ contains
           dh1 => dh_b(:,:,k); dv1 => dv_b(:,:,k)
        end if
        td(k)%edge_up_dn_grad  = ADV_ADDR(grad1)
+       if (adv_b200_device_gradients) td(k)%edge_up_dn_grad = c_null_ptr   ! computed by the library from `values`
        td(k)%del_ttf_advhoriz = ADV_ADDR(dh1)
        td(k)%del_ttf_advvert  = ADV_ADDR(dv1)
        td(k)%tra_adv_hor = c_loc(hs(k)); td(k)%tra_adv_ver = c_loc(vs(k)); td(k)%tra_adv_lim = c_loc(ls(k))

@@ -159,5 +159,8 @@ def test_wrapper_keeps_the_reference_signature_and_guards_the_batch():
     # device addresses are taken with acc_deviceptr (scope-independent), never via HOST_DATA in a caller
     assert "HOST_DATA" not in src.upper().replace("`!$ACC HOST_DATA USE_DEVICE`", "")
     assert "#define ADV_ADDR(x) acc_deviceptr(x)" in src and "#define ADV_ADDR(x) c_loc(x)" in src
+    # optional: gradients computed by the library (NULL pointer in the descriptor), element halo handed over at init
+    assert "if (adv_b200_device_gradients) td(k)%edge_up_dn_grad = c_null_ptr" in src
+    assert "gd%n_elem = partit%myDim_elem2D + partit%eDim_elem2D + partit%eXDim_elem2D" in src and "partit%com_elem2D_full%slist" in src
     # state handed over once per model step
     assert "adv_ctx_set_state_step(adv_b200_ctx, st, ADV_WHERE, int(mstep, c_int64_t))" in src
