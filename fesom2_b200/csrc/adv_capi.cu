@@ -1106,12 +1106,24 @@ static int do_adv(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr, i
             if (int rc = adv_tracer_gradient_elements(c, (int)need.size(), ttfs.data(), xy.data())) return rc;
             if (c->npes > 1) if (int rc = adv_exchange_elem(c, (int)need.size(), xy.data(), 2 * m.L)) return rc;
             if (!cxy.empty()) if (int rc = adv_fill_up_dn_grad(c, (int)cxy.size(), cxy.data(), gr.data())) return rc;
-            for (int i : fused) {
-                Slot& s = c->slots[i];
-                if (s.gmean.n != nmean) CU(s.gmean.alloc(nmean));
-                k_node_mean_grad<<<nblocks(m.Nh, cpb), cpb * m.L, 0, c->s_comp>>>(m, c->gm, cpb, s.tr_xy.p, s.gmean.p);
+            for (size_t k = 0; k < fused.size();) {           // node means: two tracers per launch share the element walk
+                const int i0 = fused[k], i1 = k + 1 < fused.size() ? fused[k + 1] : -1;
+                for (int i : {i0, i1}) {
+                    if (i < 0) continue;
+                    Slot& s = c->slots[i];
+                    if (s.gmean.n != nmean) CU(s.gmean.alloc(nmean));
+                    p.txy[i] = s.tr_xy.p; p.gmean[i] = s.gmean.p;
+                }
+                if (i1 >= 0) {
+                    PtrPack<2> pk{{c->slots[i0].tr_xy.p, c->slots[i1].tr_xy.p}, {c->slots[i0].gmean.p, c->slots[i1].gmean.p}};
+                    k_node_mean_grad<2><<<nblocks(m.Nh, cpb), cpb * m.L, 0, c->s_comp>>>(m, c->gm, cpb, pk);
+                    k += 2;
+                } else {
+                    PtrPack<1> pk{{c->slots[i0].tr_xy.p}, {c->slots[i0].gmean.p}};
+                    k_node_mean_grad<1><<<nblocks(m.Nh, cpb), cpb * m.L, 0, c->s_comp>>>(m, c->gm, cpb, pk);
+                    k += 1;
+                }
                 ++c->launches;
-                p.txy[i] = s.tr_xy.p; p.gmean[i] = s.gmean.p;
             }
             CU(cudaGetLastError());
         }
@@ -1383,7 +1395,17 @@ int adv_tracer_gradient_elements(adv_ctx_t* c, int ntr, const double* const* ttf
     for (int i = 0; i < ntr; ++i) {
         if (!ttf[i] || !tr_xy[i]) return fail(ADV_EINVAL, "tracer " + std::to_string(i + 1) + ": null field");
         if ((uintptr_t)tr_xy[i] & 15u) return fail(ADV_EINVAL, "tr_xy must be 16-byte aligned");
-        k_tracer_gradient_elements<<<nblocks(m.T, cpb), cpb * m.L, 0, c->s_comp>>>(m, c->gm, cpb, ttf[i], tr_xy[i]);
+    }
+    for (int i = 0; i < ntr;) {                               // two tracers per launch share the element's metadata
+        if (i + 1 < ntr) {
+            PtrPack<2> pk{{ttf[i], ttf[i + 1]}, {tr_xy[i], tr_xy[i + 1]}};
+            k_tracer_gradient_elements<2><<<nblocks(m.T, cpb), cpb * m.L, 0, c->s_comp>>>(m, c->gm, cpb, pk);
+            i += 2;
+        } else {
+            PtrPack<1> pk{{ttf[i]}, {tr_xy[i]}};
+            k_tracer_gradient_elements<1><<<nblocks(m.T, cpb), cpb * m.L, 0, c->s_comp>>>(m, c->gm, cpb, pk);
+            i += 1;
+        }
         ++c->launches;
     }
     CU(cudaGetLastError());

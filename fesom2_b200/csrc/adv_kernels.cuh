@@ -1549,9 +1549,11 @@ struct GradMeshDev {
     const double* earea;     // (n_elem)
 };
 
-// tracer_gradient_elements, src/oce_tracer_mod.F90:171-180: one thread per (element, layer)
-__global__ void __launch_bounds__(kBlock) k_tracer_gradient_elements(MeshDev m, GradMeshDev g, int cpb,
-                                                                     const double* __restrict__ ttf, double* __restrict__ tr_xy)
+// tracer_gradient_elements, src/oce_tracer_mod.F90:171-180: one thread per (element, layer), NT tracers per launch
+// (the element's node ids, level range and gradient_sca row are loaded once for all of them)
+template <int NT> struct PtrPack { const double* in[NT]; double* out[NT]; };
+template <int NT>
+__global__ void __launch_bounds__(kBlock) k_tracer_gradient_elements(MeshDev m, GradMeshDev g, int cpb, PtrPack<NT> p)
 {
     const ColThread c = col_thread(m);
     const int el = blockIdx.x * cpb + c.g;
@@ -1559,31 +1561,54 @@ __global__ void __launch_bounds__(kBlock) k_tracer_gradient_elements(MeshDev m, 
     const int nz = c.nz0 + 1;
     if (nz < __ldg(&g.ulevels[el]) || nz > __ldg(&g.nlevels[el]) - 1) return;
     const int n1 = __ldg(&g.elem_nodes[3 * el]) - 1, n2 = __ldg(&g.elem_nodes[3 * el + 1]) - 1, n3 = __ldg(&g.elem_nodes[3 * el + 2]) - 1;
-    const double t1 = __ldg(&ttf[(size_t)n1 * m.L + c.nz0]), t2 = __ldg(&ttf[(size_t)n2 * m.L + c.nz0]), t3 = __ldg(&ttf[(size_t)n3 * m.L + c.nz0]);
     const double* gs = g.gsca + (size_t)el * 6;
-    const double tx = __ldg(&gs[0]) * t1 + __ldg(&gs[1]) * t2 + __ldg(&gs[2]) * t3;      // sum() left to right
-    const double ty = __ldg(&gs[3]) * t1 + __ldg(&gs[4]) * t2 + __ldg(&gs[5]) * t3;
-    reinterpret_cast<double2*>(tr_xy)[(size_t)el * m.L + c.nz0] = make_double2(tx, ty);
+    const double g0 = __ldg(&gs[0]), g1 = __ldg(&gs[1]), g2 = __ldg(&gs[2]), g3 = __ldg(&gs[3]), g4 = __ldg(&gs[4]), g5 = __ldg(&gs[5]);
+    double t1[NT], t2[NT], t3[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        t1[t] = __ldg(&p.in[t][(size_t)n1 * m.L + c.nz0]); t2[t] = __ldg(&p.in[t][(size_t)n2 * m.L + c.nz0]); t3[t] = __ldg(&p.in[t][(size_t)n3 * m.L + c.nz0]);
+    }
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        const double tx = g0 * t1[t] + g1 * t2[t] + g2 * t3[t];      // sum() left to right
+        const double ty = g3 * t1[t] + g4 * t2[t] + g5 * t3[t];
+        reinterpret_cast<double2*>(p.out[t])[(size_t)el * m.L + c.nz0] = make_double2(tx, ty);
+    }
 }
 
 // area-weighted mean of the element gradients around `node` at layer nz, slots in their order
-// (src/oce_muscl_adv.F90:391-406)
-__device__ __forceinline__ double2 node_mean_gradient(const MeshDev& m, const GradMeshDev& g, int node, int nz,
-                                                       const double* __restrict__ tr_xy)
+// (src/oce_muscl_adv.F90:391-406), for NT tracers at once (the element walk is shared)
+template <int NT>
+__device__ __forceinline__ void node_mean_gradient(const MeshDev& m, const GradMeshDev& g, int node, int nz,
+                                                   const double* const (&tr_xy)[NT], double2 (&out)[NT])
 {
-    double tvol = 0.0, tx = 0.0, ty = 0.0;
+    double tvol = 0.0, tx[NT], ty[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) { tx[t] = 0.0; ty[t] = 0.0; }
     const int num = __ldg(&g.nie_num[node]);
     const int* row = g.nie + (size_t)node * g.ld;
     for (int k = 0; k < num; ++k) {
         const int el = __ldg(&row[k]) - 1;
         if (__ldg(&g.nlevels[el]) - 1 < nz || nz < __ldg(&g.ulevels[el])) continue;
         const double a = __ldg(&g.earea[el]);
-        const double2 t = __ldg(reinterpret_cast<const double2*>(tr_xy) + (size_t)el * m.L + (nz - 1));
         tvol = tvol + a;
-        tx = tx + t.x * a;
-        ty = ty + t.y * a;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const double2 v = __ldg(reinterpret_cast<const double2*>(tr_xy[t]) + (size_t)el * m.L + (nz - 1));
+            tx[t] = tx[t] + v.x * a;
+            ty[t] = ty[t] + v.y * a;
+        }
     }
-    return make_double2(tx / tvol, ty / tvol);
+#pragma unroll
+    for (int t = 0; t < NT; ++t) out[t] = make_double2(tx[t] / tvol, ty[t] / tvol);
+}
+__device__ __forceinline__ double2 node_mean_gradient(const MeshDev& m, const GradMeshDev& g, int node, int nz,
+                                                       const double* __restrict__ tr_xy)
+{
+    const double* const p[1] = {tr_xy};
+    double2 o[1];
+    node_mean_gradient<1>(m, g, node, nz, p, o);
+    return o[0];
 }
 
 // fill_up_dn_grad, src/oce_muscl_adv.F90:378-522: one thread per (edge, layer); writes exactly the entries
@@ -1624,17 +1649,20 @@ __global__ void __launch_bounds__(kBlock) k_fill_up_dn_grad(MeshDev m, GradMeshD
 // twins): the area-weighted mean of the element gradients around a node depends on (node, layer) only, so it is
 // evaluated ONCE per node instead of once per incident edge; the fused edge kernel (k_edge_flux_b<.., GS = 1>)
 // picks it up on the layers where the reference uses it.  One thread per (node, layer) of all local nodes.
-__global__ void __launch_bounds__(kBlock) k_node_mean_grad(MeshDev m, GradMeshDev g, int cpb, const double* __restrict__ tr_xy,
-                                                           double* __restrict__ gmean)
+template <int NT>
+__global__ void __launch_bounds__(kBlock) k_node_mean_grad(MeshDev m, GradMeshDev g, int cpb, PtrPack<NT> p)
 {
     const ColThread c = col_thread(m);
     const int n = blockIdx.x * cpb + c.g;
     if (c.g >= cpb || n >= g.n_nie) return;
     const int nz = c.nz0 + 1;
     const uchar4 lv = __ldg(&m.node_lev[n]);
-    double2 v = make_double2(0.0, 0.0);
-    if (nz >= (int)lv.x && nz <= (int)lv.y - 1) v = node_mean_gradient(m, g, n, nz, tr_xy);
-    reinterpret_cast<double2*>(gmean)[(size_t)n * m.L + c.nz0] = v;
+    double2 v[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) v[t] = make_double2(0.0, 0.0);
+    if (nz >= (int)lv.x && nz <= (int)lv.y - 1) node_mean_gradient<NT>(m, g, n, nz, p.in, v);
+#pragma unroll
+    for (int t = 0; t < NT; ++t) reinterpret_cast<double2*>(p.out[t])[(size_t)n * m.L + c.nz0] = v[t];
 }
 
 // self-test of div_rcp against the IEEE division: returns the number of mismatching results over
