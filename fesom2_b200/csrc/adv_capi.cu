@@ -758,7 +758,7 @@ int launch_phase(adv_ctx* c, Phase ph, int hor, int ver, bool q_stored, const Ch
         const NodeRange r = node_range(c, rid, cols_per_block(m.L));
         if (r.count <= 0) return ADV_OK;
         nthr = r.cpb * m.L;
-        const size_t sm1 = (size_t)TB * nthr * sizeof(double);
+        const size_t sm1 = (size_t)(2 * TB + 6) * nthr * sizeof(double);
         grid = nblocks(r.count, r.cpb);
 #define NV(V) if (ver == V) k_nofct_update<V, TB><<<grid, nthr, sm1, s>>>(m, b, r, dt);
         NV(VER_UPW1) NV(VER_QR4C) NV(VER_PPM) NV(VER_CDIFF)

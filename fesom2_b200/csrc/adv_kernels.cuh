@@ -1409,24 +1409,35 @@ __global__ void ADV_K3_BOUNDS k_fct_update(MeshDev m, Chunk<TB> b, NodePart r, d
 template <int VER, int TB>
 __global__ void __launch_bounds__(kBlock) k_nofct_update(MeshDev m, Chunk<TB> b, NodeRange r, double dt)
 {
-    extern __shared__ double sm[];  // [TB][blockDim]
-    const int L = m.L, nl = m.nl;
+    extern __shared__ double sm[];  // [TB][blockDim] vertical flux, then [6 + TB][blockDim] own-column operands
+    const int L = m.L, nl = m.nl, nthr = blockDim.x, tid = threadIdx.x;
     const NodeThread tc = node_thread(m, r);
     const int n = tc.n, nz0 = tc.nz0, nz = nz0 + 1;
     const bool owned = n < m.N;
     const bool valid = tc.active && nz >= tc.nzmin && nz <= tc.nzmax - 1;
-    const size_t oL = (size_t)n * L + nz0, cL = (size_t)n * L, cN = (size_t)n * nl;
+    const size_t oL = (size_t)n * L + nz0, cN = (size_t)n * nl;
+    // own-column operands of the vertical stencils: one coalesced load per thread, parked in shared memory (as k_node_lo)
+    double* s_we = sm + (size_t)TB * nthr; double* s_area = s_we + nthr; double* s_Z = s_area + nthr; double* s_zbar = s_Z + nthr;
+    double* s_hn = s_zbar + nthr; double* s_hnn = s_hn + nthr; double* s_tab = s_hnn + nthr;   // [TB][nthr]
+    if (tc.active && owned && nz >= tc.nzmin && nz <= tc.nzmax - 1) {
+        s_we[tid] = __ldg(&m.we[cN + nz0]); s_area[tid] = __ldg(&m.area[cN + nz0]); s_Z[tid] = __ldg(&m.Z3d[oL]);
+        s_zbar[tid] = __ldg(&m.zbar3d[cN + nz0]); s_hn[tid] = __ldg(&m.hnode[oL]); s_hnn[tid] = __ldg(&m.hnode_new[oL]);
+#pragma unroll
+        for (int t = 0; t < TB; ++t) s_tab[t * nthr + tid] = __ldg(&b.ttfAB[t][oL]);
+    }
+    __syncthreads();
     double fv_top[TB];
 #pragma unroll
     for (int t = 0; t < TB; ++t) fv_top[t] = 0.0;
     if (tc.active && owned && nz >= tc.nzmin && nz <= tc.nzmax) {
+        const int c0 = tid - nz0;                     // first element of this thread's column
         ColV c;
-        c.area = m.area + cN; c.Z = m.Z3d + cL; c.zbar = m.zbar3d + cN;
-        c.hnode = m.hnode + cL; c.hnode_new = m.hnode_new + cL;
-        c.nzmin = tc.nzmin; c.nzmax = tc.nzmax; c.dt = dt; c.w = m.we + cN;
+        c.area = s_area + c0; c.Z = s_Z + c0; c.zbar = s_zbar + c0;
+        c.hnode = s_hn + c0; c.hnode_new = s_hnn + c0;
+        c.nzmin = tc.nzmin; c.nzmax = tc.nzmax; c.dt = dt; c.w = s_we + c0;
 #pragma unroll
         for (int t = 0; t < TB; ++t) {
-            c.ttf = b.ttfAB[t] + cL; c.num_ord = b.pv[t];
+            c.ttf = s_tab + t * nthr + c0; c.num_ord = b.pv[t];
             fv_top[t] = ver_flux<VER>(c, nz, 0.0);
         }
     }
