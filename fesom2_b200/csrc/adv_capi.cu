@@ -89,14 +89,21 @@ struct DevBuf {
         if (count == 0) return cudaSuccess;
         cudaError_t e = cudaMalloc(&p, count * sizeof(T));
         if (e != cudaSuccess) { p = nullptr; return e; }
-        if (zero) e = cudaMemset(p, 0, count * sizeof(T));
+        // cudaMemset on device memory is asynchronous on the LEGACY default stream, which the context's non-blocking
+        // streams do not synchronise with: without the wait a kernel could write the buffer before the zeroing lands
+        // (seen under compute-sanitizer's timing: work arrays allocated inside the first call came back zeroed)
+        if (zero) { e = cudaMemset(p, 0, count * sizeof(T)); if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy); }
         return e;
     }
     cudaError_t upload(const std::vector<T>& h)
     {
         cudaError_t e = alloc(h.size(), false);
         if (e != cudaSuccess || h.empty()) return e;
-        return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+        // a pageable-source cudaMemcpy may return while the DMA from its staging buffer is still in flight on the
+        // legacy stream: wait, for the same reason as above
+        e = cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
+        return e;
     }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
     ~DevBuf() { release(); }
