@@ -1220,9 +1220,16 @@ int adv_exchange_elem(adv_ctx_t* c, int nfields, double* const* fields, int nwor
 }
 
 static int vert_vel_ale_impl(adv_ctx_t* c, double dt, int use_wsplit, double wsplit_maxcfl, const adv_zstar_desc_t* z,
-                             double* w, double* w_e, double* w_i, double* cfl_z)
+                             double* w, double* w_e, double* w_i, double* cfl_z, const adv_zlevel_desc_t* zl = nullptr)
 {
     if (!c || !w || !w_e || !w_i) return fail(ADV_EINVAL, "adv_vert_vel_ale: null argument");
+    if (zl) {
+        if (!zl->hbar || !zl->hbar_old || !zl->water_flux || !zl->nlevels_nod2D_min || !zl->hnode_new || !zl->zbar)
+            return fail(ADV_EINVAL, "adv_vert_vel_ale_zlevel: null field in the zlevel descriptor");
+        if (!cfl_z) return fail(ADV_EINVAL, "adv_vert_vel_ale_zlevel: cfl_z must hold the previous step's CFL_z (it is read before it is recomputed)");
+        if (zl->lzstar_lev < 1 || zl->lzstar_lev > kMaxLzstar || zl->lzstar_lev > c->m.L)
+            return fail(ADV_EINVAL, "adv_vert_vel_ale_zlevel: lzstar_lev out of range (1 .. min(16, nl-1))");
+    }
     if (z && (!z->hbar || !z->hbar_old || !z->water_flux || !z->nlevels_nod2D_min || !z->hnode_new))
         return fail(ADV_EINVAL, "adv_vert_vel_ale_zstar: null field in the zstar descriptor");
     if (!c->state_set) return fail(ADV_ESTATE, "adv_ctx_set_state has not been called");
@@ -1238,14 +1245,20 @@ static int vert_vel_ale_impl(adv_ctx_t* c, double dt, int use_wsplit, double wsp
                                                                          z->water_flux, w, z->hnode_new);
         ++c->launches;
     }
+    if (zl) {                                                     // which_ALE = 'zlevel', src/oce_ale.F90:2336-2538
+        k_vert_vel_zlevel<<<nblocks(m.N, 256), 256, 0, c->s_comp>>>(m, dt, zl->nlevels_nod2D_min, zl->hbar, zl->hbar_old, zl->water_flux,
+                                                                    zl->zbar, cfl_z, zl->min_hnode, zl->lzstar_lev, w, zl->hnode_new);
+        ++c->launches;
+    }
     CU(cudaGetLastError());
+    double* hnew = z ? z->hnode_new : zl ? zl->hnode_new : nullptr;
     if (c->npes > 1) {                                            // exchange_nod(Wvel), exchange_nod(hnode_new): :2654-2655
         double* f[1] = {w};
         if (int rc = exchange_fields(c, HALO_NOD, 1, f, m.nl)) return rc;
-        if (z) { double* h[1] = {z->hnode_new}; if (int rc = exchange_fields(c, HALO_NOD, 1, h, m.L)) return rc; }
+        if (hnew) { double* h[1] = {hnew}; if (int rc = exchange_fields(c, HALO_NOD, 1, h, m.L)) return rc; }
     }
     const size_t n = (size_t)m.Nh * m.nl;
-    k_cflz_wsplit<<<(unsigned)((n + 255) / 256), 256, 0, c->s_comp>>>(m, z ? z->hnode_new : m.hnode_new, dt, use_wsplit ? 1 : 0, wsplit_maxcfl,
+    k_cflz_wsplit<<<(unsigned)((n + 255) / 256), 256, 0, c->s_comp>>>(m, hnew ? hnew : m.hnode_new, dt, use_wsplit ? 1 : 0, wsplit_maxcfl,
                                                                      w, w_e, w_i, cfl_z);
     ++c->launches;
     CU(cudaGetLastError());
@@ -1262,6 +1275,13 @@ int adv_vert_vel_ale_zstar(adv_ctx_t* c, double dt, int use_wsplit, double wspli
 {
     if (!z) return fail(ADV_EINVAL, "adv_vert_vel_ale_zstar: null descriptor");
     return vert_vel_ale_impl(c, dt, use_wsplit, wsplit_maxcfl, z, w, w_e, w_i, cfl_z);
+}
+
+int adv_vert_vel_ale_zlevel(adv_ctx_t* c, double dt, int use_wsplit, double wsplit_maxcfl, const adv_zlevel_desc_t* z,
+                            double* w, double* w_e, double* w_i, double* cfl_z)
+{
+    if (!z) return fail(ADV_EINVAL, "adv_vert_vel_ale_zlevel: null descriptor");
+    return vert_vel_ale_impl(c, dt, use_wsplit, wsplit_maxcfl, nullptr, w, w_e, w_i, cfl_z, z);
 }
 
 int adv_update_values(adv_ctx_t* c, int ntr, double* const* values, const double* const* dh, const double* const* dv)

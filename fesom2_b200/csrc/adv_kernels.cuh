@@ -152,6 +152,12 @@ struct NodeRange {
 __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
 __device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
 
+// x or -x (mask = 0 / 0x80000000): the IEEE negation is a flip of the sign bit, one integer instruction on the high
+// word instead of DADD + two selects
+__device__ __forceinline__ double flip_sign(double x, int mask)
+{
+    return __hiloint2double(__double2hiint(x) ^ mask, __double2loint(x));
+}
 // L2 software prefetch of [p, p+bytes), widened to the 16-byte granularity of the bulk-prefetch
 // instruction (sm_90+: one instruction per column instead of one per 128-byte line).  CTAs
 // prefetch the operands of the CTA `pf` launches ahead so that the dependent metadata -> data
@@ -1102,6 +1108,79 @@ __global__ void __launch_bounds__(kBlock) k_vert_vel_zstar(MeshDev m, NodeRange 
     }
 }
 
+// which_ALE = 'zlevel' (src/oce_ale.F90:2336-2538): one thread per owned, cavity-free column -- the correction touches at
+// most the first lzstar_lev (namelist default 4) layers of a column and is a short serial recurrence over them.  The
+// elevation change goes into the surface layer (:2519-2520) unless that layer would shrink below min_hnode times its
+// rest thickness: then it is spread downwards over the layers that still have room ("local zstar", :2367-2449; the
+// reference's pairwise "cumsum" at :2397-2398 decides how many layers take part), and a later rise refills the squeezed
+// subsurface layers before the surface layer (:2461-2510).  zbar = mesh%zbar (nl); cfl_old = CFL_z of the previous step.
+constexpr int kMaxLzstar = 16;
+__global__ void __launch_bounds__(256) k_vert_vel_zlevel(MeshDev m, double dt, const int* __restrict__ nmin, const double* __restrict__ hbar,
+                                                         const double* __restrict__ hbar_old, const double* __restrict__ wflux,
+                                                         const double* __restrict__ zbar, const double* __restrict__ cfl_old, double min_hnode,
+                                                         int lz, double* __restrict__ W, double* __restrict__ hnode_new)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= m.N) return;
+    if (m.node_lev[n].x != 1) return;                                               // :2354: a cavity is treated like linfs
+    double* w = W + (size_t)n * m.nl;
+    double* hn = hnode_new + (size_t)n * m.L;
+    const double* h = m.hnode + (size_t)n * m.L;
+    int nzmax = __ldg(&nmin[n]) - 1;
+    const double dh = __ldg(&hbar[n]) - __ldg(&hbar_old[n]);                        // :2357
+    double mx[kMaxLzstar];
+    if (dh < 0.0 && h[0] + dh <= (zbar[0] - zbar[1]) * min_hnode) {                 // :2367 local zstar
+#pragma unroll 1
+        for (int k = 0; k < lz; ++k) {                                              // :2374-2383
+            double v = (zbar[k] - zbar[k + 1]) * min_hnode - h[k];
+            if (v >= 0.0) v = 0.0;
+            if (__ldg(&cfl_old[(size_t)n * m.nl + k]) >= 0.95) v = 0.0;
+            mx[k] = v;
+        }
+        int nz = lz;                                                                // :2397-2400
+        for (int k = lz - 1; k >= 0; --k) {
+            const double cs = k == 0 ? mx[0] : mx[k] + mx[k - 1];
+            if (cs < dh) nz = k + 1;
+        }
+        nzmax = min(nz, nzmax - 1);                                                 // :2411
+        double rest = dh, distrib[kMaxLzstar];
+        for (int k = 0; k < nzmax; ++k) {                                           // :2412-2416
+            distrib[k] = dmax(rest, mx[k]);
+            rest = rest - distrib[k];
+            rest = dmin(0.0, rest);
+        }
+        double integ = 0.0;
+        for (int k = nzmax - 1; k >= 0; --k) {                                      // :2438-2449
+            integ = integ + distrib[k];
+            w[k] = w[k] - integ / dt;
+            hn[k] = h[k] + distrib[k];
+        }
+    } else {
+        int last_ne = -1;
+        bool any_ne = false;
+        if (dh > 0.0)
+            for (int k = 0; k < lz; ++k)
+                if (h[k] != zbar[k] - zbar[k + 1]) { last_ne = k + 1; any_ne = any_ne || k >= 1; }   // :2462-2463, :2482
+        if (dh > 0.0 && any_ne) {                                                   // refill, :2461-2510
+            nzmax = min(last_ne, nzmax - 1);                                        // :2488
+            double rest = dh, integ = 0.0;
+            for (int k = nzmax - 1; k >= 0; --k) {
+                const double cap = k == 0 ? 1000.0 : (zbar[k] - zbar[k + 1]) - h[k];     // :2471-2475
+                const double d = dmin(rest, cap);
+                rest = rest - d;
+                rest = dmax(0.0, rest);
+                integ = integ + d;
+                w[k] = w[k] - integ / dt;
+                hn[k] = h[k] + d;
+            }
+        } else {                                                                    // :2519-2520
+            w[0] = w[0] - dh / dt;
+            hn[0] = h[0] + dh;
+        }
+    }
+    w[0] = w[0] - __ldg(&wflux[n]);                                                 // :2527
+}
+
 // compute_CFLz (src/oce_ale.F90:2933-2952, without the diagnostic print) and compute_Wvel_split (:3033-3047):
 // one thread per (interface, node) over all myDim+eDim columns.  CFL_z(nz) = c2 of the layer above, then + c1 of
 // the layer below, in that order; W_e / W_i are written for nzmin..nlevels_nod2D only, like the reference.
@@ -1224,13 +1303,13 @@ __global__ void ADV_K2_BOUNDS k_fct_bounds(MeshDev m, Chunk<TB> b, NodePart r, d
 #pragma unroll
             for (int j = 0; j < G; ++j) {
                 if (!in[j]) continue;
-                const bool second = (ent[j].z >> 16) & 1;
+                const int smask = (ent[j].z & 0x10000) << 15;                 // bit 31 set: this node is edges(2,e)
 #pragma unroll
                 for (int t = 0; t < TB; ++t) {
                     const double hi2 = dmax(lo_o[j][t], t_o[j][t]), lo2 = dmin(lo_o[j][t], t_o[j][t]);
                     tmax[t] = hi2 > tmax[t] ? hi2 : tmax[t];                  // a2 :166, a3 :209
                     tmin[t] = lo2 < tmin[t] ? lo2 : tmin[t];
-                    const double a = second ? -f[j][t] : f[j][t];             // fct :342,:346 / :360,:364
+                    const double a = flip_sign(f[j][t], smask);               // fct :342,:346 / :360,:364: -f for edges(2,e)
                     // pp += max(0,a); pn += min(0,a): exactly one addend is non-zero, and adding +0.0 changes nothing
                     // (pp >= +0, pn <= +0 and never -0.0: both start as 0.0 + x), so one compare and two predicated adds
                     if (a > 0.0) pp[t] = pp[t] + a; else pn[t] = pn[t] + a;
@@ -1359,15 +1438,16 @@ __global__ void ADV_K3_BOUNDS k_fct_update(MeshDev m, Chunk<TB> b, NodePart r, d
 #pragma unroll
         for (int j = 0; j < G; ++j) {
             if (!in[j]) continue;
-            // fct :489-494: ae = min(1, R+/R- of edges(1,e), R-/R+ of edges(2,e)) by the sign of the flux;
-            // one (nearly warp-uniform) branch on which end this node is replaces four double selects
+            // fct :489-494: ae = min(1, R+/R- of edges(1,e), R-/R+ of edges(2,e)) by the sign of the flux; R+/R- are
+            // themselves min(1, .) (k_fct_bounds), so min(1, A, B) == min(A, B) bit for bit (also for NaN operands).
+            // One (nearly warp-uniform) branch on which end this node is replaces four double selects
             if (!((ent[j].z >> 16) & 1)) {                 // this node is edges(1,e)
 #pragma unroll
                 for (int t = 0; t < TB; ++t) {
                     const double ff = f[j][t];
                     const bool pos = ff >= 0.0;
                     const double A = pos ? pk[t] : mk[t], B = pos ? mo[j][t] : po[j][t];
-                    const double ae = dmin(dmin(1.0, A), B);
+                    const double ae = dmin(A, B);
                     dh[t] = dh[t] + div_rcp(ae * ff * dt, av, r_av);          // fct :497, driver :607
                 }
             } else {                                       // this node is edges(2,e)
@@ -1376,7 +1456,7 @@ __global__ void ADV_K3_BOUNDS k_fct_update(MeshDev m, Chunk<TB> b, NodePart r, d
                     const double ff = f[j][t];
                     const bool pos = ff >= 0.0;
                     const double A = pos ? po[j][t] : mo[j][t], B = pos ? mk[t] : pk[t];
-                    const double ae = dmin(dmin(1.0, A), B);
+                    const double ae = dmin(A, B);
                     dh[t] = dh[t] - div_rcp(ae * ff * dt, av, r_av);          // driver :620
                 }
             }

@@ -64,6 +64,11 @@ class ZstarDesc(C.Structure):
     _fields_ = [("hbar", c_dp), ("hbar_old", c_dp), ("water_flux", c_dp), ("nlevels_nod2D_min", c_ip), ("hnode_new", c_dp)]
 
 
+class ZlevelDesc(C.Structure):
+    _fields_ = [("hbar", c_dp), ("hbar_old", c_dp), ("water_flux", c_dp), ("nlevels_nod2D_min", c_ip), ("hnode_new", c_dp),
+                ("zbar", c_dp), ("min_hnode", C.c_double), ("lzstar_lev", C.c_int32)]
+
+
 class GradientMeshDesc(C.Structure):
     _fields_ = [("n_elem", C.c_int32), ("n_nod_in_elem", C.c_int32), ("nod_in_elem2D_ld", C.c_int32),
                 ("nod_in_elem2D", c_ip), ("nod_in_elem2D_num", c_ip), ("nlevels", c_ip), ("ulevels", c_ip),
@@ -75,7 +80,7 @@ class GradientMeshDesc(C.Structure):
 
 EXPORTS = ["adv_ctx_create", "adv_ctx_destroy", "adv_last_error", "adv_comm_unique_id",
            "adv_ctx_comm_init", "adv_ctx_comm_init_local", "adv_exchange_elem", "adv_ctx_halo_stats",
-           "adv_ctx_wait_for", "adv_ctx_signal", "adv_vert_vel_ale", "adv_vert_vel_ale_zstar", "adv_ctx_set_state_step", "adv_ctx_set_host_register", "adv_ctx_set_state", "adv_do_oce_adv_tra", "adv_do_oce_adv_tra_async",
+           "adv_ctx_wait_for", "adv_ctx_signal", "adv_vert_vel_ale", "adv_vert_vel_ale_zstar", "adv_vert_vel_ale_zlevel", "adv_ctx_set_state_step", "adv_ctx_set_host_register", "adv_ctx_set_state", "adv_do_oce_adv_tra", "adv_do_oce_adv_tra_async",
            "adv_ctx_synchronize", "adv_exchange_nod", "adv_update_values", "adv_init_tracers_AB",
            "adv_ctx_set_gradient_mesh", "adv_tracer_gradient_elements", "adv_fill_up_dn_grad", "adv_ctx_get_work",
            "adv_ctx_launch_count", "adv_ctx_stream", "adv_ctx_last_elapsed_ms",
@@ -104,6 +109,7 @@ def load_library():
         L.adv_ctx_set_state.argtypes = [C.c_void_p, C.POINTER(StateDesc), C.c_int]
         L.adv_vert_vel_ale.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double, c_dp, c_dp, c_dp, c_dp]
         L.adv_vert_vel_ale_zstar.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double, C.POINTER(ZstarDesc), c_dp, c_dp, c_dp, c_dp]
+        L.adv_vert_vel_ale_zlevel.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double, C.POINTER(ZlevelDesc), c_dp, c_dp, c_dp, c_dp]
         L.adv_ctx_set_state_step.argtypes = [C.c_void_p, C.POINTER(StateDesc), C.c_int, C.c_int64]
         L.adv_ctx_set_host_register.argtypes = [C.c_void_p, C.c_int]
         L.adv_do_oce_adv_tra.argtypes = [C.c_void_p, C.c_double, C.c_int, C.POINTER(TracerDesc), C.c_int]
@@ -308,6 +314,18 @@ class AdvB200:
                       nlevels_nod2D_min=C.cast(nlevels_nod2D_min.data_ptr(), c_ip), hnode_new=_ptr(hnode_new))
         _check(self.lib.adv_vert_vel_ale_zstar(self.h, float(dt), int(bool(use_wsplit)), float(wsplit_maxcfl), C.byref(z),
                                                _ptr(w), _ptr(w_e), _ptr(w_i), _ptr(cfl_z)))
+        self._before_torch()
+
+    def vert_vel_ale_zlevel(self, dt: float, use_wsplit: bool, wsplit_maxcfl: float, hbar, hbar_old, water_flux, nlevels_nod2D_min,
+                            hnode_new, zbar, min_hnode: float, lzstar_lev: int, w, w_e, w_i, cfl_z):
+        """``vert_vel_ale`` for which_ALE = 'zlevel' (src/oce_ale.F90:2164-2310, :2336-2538, :2654-2666): device tensors;
+        ``zbar`` the (nl) rest interfaces, ``cfl_z`` in/out (the previous step's CFL_z on entry), ``hnode_new`` updated in place."""
+        self._after_torch()
+        z = ZlevelDesc(hbar=_ptr(hbar), hbar_old=_ptr(hbar_old), water_flux=_ptr(water_flux),
+                       nlevels_nod2D_min=C.cast(nlevels_nod2D_min.data_ptr(), c_ip), hnode_new=_ptr(hnode_new),
+                       zbar=_ptr(zbar), min_hnode=float(min_hnode), lzstar_lev=int(lzstar_lev))
+        _check(self.lib.adv_vert_vel_ale_zlevel(self.h, float(dt), int(bool(use_wsplit)), float(wsplit_maxcfl), C.byref(z),
+                                                _ptr(w), _ptr(w_e), _ptr(w_i), _ptr(cfl_z)))
         self._before_torch()
 
     def update_values(self, values: Sequence, dttf_h: Sequence, dttf_v: Sequence):

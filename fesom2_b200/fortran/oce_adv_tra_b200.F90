@@ -104,6 +104,17 @@ module oce_adv_tra_b200
      type(c_ptr) :: hnode_new
   end type adv_zstar_desc_t
 
+  ! adv_zlevel_desc_t
+  type, bind(C) :: adv_zlevel_desc_t
+     type(c_ptr) :: hbar, hbar_old
+     type(c_ptr) :: water_flux
+     type(c_ptr) :: nlevels_nod2D_min
+     type(c_ptr) :: hnode_new
+     type(c_ptr) :: zbar
+     real(c_double) :: min_hnode
+     integer(c_int32_t) :: lzstar_lev
+  end type adv_zlevel_desc_t
+
   interface
      integer(c_int) function adv_ctx_create(ctx, mesh, device, max_tracers) bind(C, name='adv_ctx_create')
        import :: c_int, c_ptr, adv_mesh_desc_t
@@ -212,6 +223,17 @@ module oce_adv_tra_b200
        integer(c_int), value :: use_wsplit
        real(c_double), value :: wsplit_maxcfl
        type(adv_zstar_desc_t), intent(in) :: z
+       type(c_ptr), value    :: w, w_e, w_i, cfl_z
+     end function
+     ! which_ALE = 'zlevel' (src/oce_ale.F90:2336-2538); cfl_z is in/out (the previous step's CFL_z on entry)
+     integer(c_int) function adv_vert_vel_ale_zlevel(ctx, dt, use_wsplit, wsplit_maxcfl, z, w, w_e, w_i, cfl_z) &
+                                                     bind(C, name='adv_vert_vel_ale_zlevel')
+       import :: c_ptr, c_int, c_double, adv_zlevel_desc_t
+       type(c_ptr), value    :: ctx
+       real(c_double), value :: dt
+       integer(c_int), value :: use_wsplit
+       real(c_double), value :: wsplit_maxcfl
+       type(adv_zlevel_desc_t), intent(in) :: z
        type(c_ptr), value    :: w, w_e, w_i, cfl_z
      end function
      integer(c_int) function adv_ctx_wait_for(ctx, stream) bind(C, name='adv_ctx_wait_for')

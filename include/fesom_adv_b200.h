@@ -188,7 +188,7 @@ int adv_vert_vel_ale(adv_ctx_t *ctx, double dt, int use_wsplit, double wsplit_ma
  * elevation change hbar - hbar_old is distributed over the layers above the shallowest bottom around each owned,
  * cavity-free node -- Wvel and hnode_new, src/oce_ale.F90:2539-2603 --, the surface fresh-water flux closes the
  * continuity at the top, then exchange_nod(Wvel) and exchange_nod(hnode_new) (:2654-2655); compute_CFLz uses the new
- * hnode_new.  All arrays are DEVICE arrays.  The 'zlevel' variant (:2336-2538) is not built. */
+ * hnode_new.  All arrays are DEVICE arrays. */
 typedef struct {
     const double  *hbar, *hbar_old;      /* (Nh) mesh%hbar, mesh%hbar_old                              */
     const double  *water_flux;           /* (Nh) o_ARRAYS water_flux                                   */
@@ -197,6 +197,24 @@ typedef struct {
 } adv_zstar_desc_t;
 int adv_vert_vel_ale_zstar(adv_ctx_t *ctx, double dt, int use_wsplit, double wsplit_maxcfl, const adv_zstar_desc_t *z,
                            double *w, double *w_e, double *w_i, double *cfl_z);
+/* The same for which_ALE = 'zlevel' (src/oce_ale.F90:2336-2538): the elevation change goes into the surface layer of every
+ * owned, cavity-free node; where that layer would become thinner than min_hnode times its rest thickness the change is
+ * spread over the first lzstar_lev layers (local zstar, :2367-2449, with the previous step's CFL_z as a brake), and a
+ * later rise refills the squeezed subsurface layers first (:2461-2510); then the fresh-water flux, both exchanges,
+ * compute_CFLz with the new thickness and compute_Wvel_split as above.  `cfl_z` is IN/OUT here and must not be NULL: on
+ * entry the previous step's CFL_z (the reference reads its module array before compute_CFLz rewrites it).  min_hnode and
+ * lzstar_lev are the namelist values (src/gen_modules_config.F90:71,:75: 0.5 and 4).  All arrays are DEVICE arrays. */
+typedef struct {
+    const double  *hbar, *hbar_old;      /* (Nh) mesh%hbar, mesh%hbar_old                              */
+    const double  *water_flux;           /* (Nh) o_ARRAYS water_flux                                   */
+    const int32_t *nlevels_nod2D_min;    /* (Nh) mesh%nlevels_nod2D_min                                */
+    double        *hnode_new;            /* (nl-1, Nh) inout: the layers that take part are rewritten from hnode */
+    const double  *zbar;                 /* (nl) mesh%zbar: the rest interfaces                        */
+    double         min_hnode;            /* g_config min_hnode                                         */
+    int32_t        lzstar_lev;           /* g_config lzstar_lev (1 .. 16)                              */
+} adv_zlevel_desc_t;
+int adv_vert_vel_ale_zlevel(adv_ctx_t *ctx, double dt, int use_wsplit, double wsplit_maxcfl, const adv_zlevel_desc_t *z,
+                            double *w, double *w_e, double *w_i, double *cfl_z);
 
 /* The prologue of the tracer step, `init_tracers_AB(tr_num, tracers, partit, mesh)`
  * (src/oce_tracer_mod.F90:13-123) without its gradient calls, for ntr tracers: zeroes del_ttf /

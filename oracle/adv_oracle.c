@@ -1012,3 +1012,88 @@ void ora_vert_vel_ale_zstar(const ora_mesh_t *m, double dt, const int *nlevels_n
 #undef Z_W
 #undef Z_ZB
 }
+
+/* ====================================================================================================
+ * vert_vel_ale, the free-surface correction for which_ALE = 'zlevel' (src/oce_ale.F90:2336-2538): the elevation
+ * change goes into the surface layer; when that layer would get thinner than min_hnode times its rest thickness the
+ * change is spread over the first lzstar_lev layers ("local zstar", :2371-2454), and a later rise refills the
+ * subsurface layers first (:2455-2510).  zbar = mesh%zbar (nl), CFL_z = the previous step's (nl, Nh) array.
+ * Loop for loop, including the reference's pairwise (not cumulative) "cumsum" at :2397-2398.
+ * ==================================================================================================== */
+void ora_vert_vel_ale_zlevel(const ora_mesh_t *m, double dt, const int *nlevels_nod2D_min, const double *hbar,
+                             const double *hbar_old, const double *water_flux, const double *zbar, const double *CFL_z,
+                             double min_hnode, int lzstar_lev, double *Wvel, double *hnode_new)
+{
+    const int nl = m->nl, L = nl - 1, lz = lzstar_lev;
+    double max_dhbar2distr[256], distrib_dhbar[256], cumsum_maxdhbar[256];
+#define Z_W(nz, n) Wvel[(size_t)((n) - 1) * nl + ((nz) - 1)]
+#define Z_H(nz, n) m->hnode[(size_t)((n) - 1) * L + ((nz) - 1)]
+#define Z_HN(nz, n) hnode_new[(size_t)((n) - 1) * L + ((nz) - 1)]
+#define Z_C(nz, n) CFL_z[(size_t)((n) - 1) * nl + ((nz) - 1)]
+#define ZB(nz) zbar[(nz) - 1]
+    for (int n = 1; n <= m->myDim_nod2D; ++n) {
+        const int nzmin = m->ulevels_nod2D[n - 1];
+        int nzmax = nlevels_nod2D_min[n - 1] - 1;
+        if (nzmin != 1) continue;                                                   /* :2354 cavity: like linfs */
+        const double dhbar_total = hbar[n - 1] - hbar_old[n - 1];                   /* :2357 */
+        if (dhbar_total < 0.0 && Z_H(nzmin, n) + dhbar_total <= (ZB(nzmin) - ZB(nzmin + 1)) * min_hnode) {   /* :2367 */
+            for (int k = 1; k <= lz; ++k) {                                         /* :2374-2383 */
+                double v = (ZB(nzmin + k - 1) - ZB(nzmin + k)) * min_hnode - Z_H(nzmin + k - 1, n);
+                if (v >= 0.0) v = 0.0;
+                if (Z_C(nzmin + k - 1, n) >= 0.95) v = 0.0;
+                max_dhbar2distr[k - 1] = v;
+            }
+            cumsum_maxdhbar[0] = max_dhbar2distr[0];                                /* :2397 */
+            for (int k = 2; k <= lz; ++k) cumsum_maxdhbar[k - 1] = max_dhbar2distr[k - 1] + max_dhbar2distr[k - 2];   /* :2398 */
+            int nz = 2147483647;                                                    /* minval of an empty pack = huge */
+            for (int k = lz; k >= 1; --k) if (cumsum_maxdhbar[k - 1] < dhbar_total) nz = k;                           /* :2399 */
+            if (nz > lz) nz = lz;                                                   /* :2400 */
+            for (int k = 0; k < lz; ++k) distrib_dhbar[k] = 0.0;
+            double dhbar_rest = dhbar_total;
+            nzmax = nz < nzmax - 1 ? nz : nzmax - 1;                                /* :2411 */
+            for (nz = 1; nz <= nzmax; ++nz) {                                       /* :2412-2416 */
+                distrib_dhbar[nz - 1] = dhbar_rest > max_dhbar2distr[nz - 1] ? dhbar_rest : max_dhbar2distr[nz - 1];
+                dhbar_rest = dhbar_rest - distrib_dhbar[nz - 1];
+                dhbar_rest = 0.0 < dhbar_rest ? 0.0 : dhbar_rest;
+            }
+            double distrib_dhbar_int = 0.0;
+            for (nz = nzmax; nz >= 1; --nz) {                                       /* :2438-2449 */
+                distrib_dhbar_int = distrib_dhbar_int + distrib_dhbar[nz - 1];
+                Z_W(nzmin + nz - 1, n) = Z_W(nzmin + nz - 1, n) - distrib_dhbar_int / dt;
+                Z_HN(nzmin + nz - 1, n) = Z_H(nzmin + nz - 1, n) + distrib_dhbar[nz - 1];
+            }
+        } else {
+            int any_ne = 0, last_ne = -2147483647;                                  /* maxval of an empty pack = -huge */
+            if (dhbar_total > 0.0)
+                for (int k = 2; k <= lz; ++k)                                       /* :2462-2463 */
+                    if (Z_H(nzmin + k - 1, n) != ZB(nzmin + k - 1) - ZB(nzmin + k)) any_ne = 1;
+            if (dhbar_total > 0.0 && any_ne) {
+                for (int k = 1; k <= lz; ++k)                                       /* :2471 */
+                    max_dhbar2distr[k - 1] = (ZB(nzmin + k - 1) - ZB(nzmin + k)) - Z_H(nzmin + k - 1, n);
+                max_dhbar2distr[0] = 1000.0;                                        /* :2475 */
+                for (int k = 1; k <= lz; ++k)                                       /* :2482 */
+                    if (Z_H(nzmin + k - 1, n) != ZB(nzmin + k - 1) - ZB(nzmin + k)) last_ne = k;
+                int nz = last_ne;
+                nzmax = nz < nzmax - 1 ? nz : nzmax - 1;                            /* :2488 */
+                double dhbar_rest = dhbar_total, distrib_dhbar_int = 0.0;
+                for (nz = nzmax; nz >= 1; --nz) {                                   /* :2496-2510 */
+                    const double d = dhbar_rest < max_dhbar2distr[nz - 1] ? dhbar_rest : max_dhbar2distr[nz - 1];
+                    dhbar_rest = dhbar_rest - d;
+                    dhbar_rest = 0.0 > dhbar_rest ? 0.0 : dhbar_rest;
+                    distrib_dhbar_int = distrib_dhbar_int + d;
+                    Z_W(nzmin + nz - 1, n) = Z_W(nzmin + nz - 1, n) - distrib_dhbar_int / dt;
+                    Z_HN(nzmin + nz - 1, n) = Z_H(nzmin + nz - 1, n) + d;
+                }
+            } else {                                                                /* :2519-2520 the normal zlevel case */
+                Z_W(nzmin, n) = Z_W(nzmin, n) - dhbar_total / dt;
+                Z_HN(nzmin, n) = Z_H(nzmin, n) + dhbar_total;
+            }
+        }
+        Z_W(nzmin, n) = Z_W(nzmin, n) - water_flux[n - 1];                          /* :2527 */
+    }
+#undef Z_W
+#undef Z_H
+#undef Z_HN
+#undef Z_C
+#undef ZB
+}

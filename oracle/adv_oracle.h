@@ -165,6 +165,10 @@ double ora_run_ranks(int nranks, ora_rank_t *ranks, double dt, int nsteps, int m
 /* vert_vel_ale, zstar correction (src/oce_ale.F90:2539-2603): Wvel (nl,Nh) and hnode_new (nl-1,Nh) updated in place */
 void ora_vert_vel_ale_zstar(const ora_mesh_t *m, double dt, const int *nlevels_nod2D_min, const double *hbar,
                             const double *hbar_old, const double *water_flux, double *Wvel, double *hnode_new);
+/* vert_vel_ale, zlevel correction (src/oce_ale.F90:2336-2538): zbar = mesh%zbar (nl), CFL_z = the previous step's (nl,Nh) */
+void ora_vert_vel_ale_zlevel(const ora_mesh_t *m, double dt, const int *nlevels_nod2D_min, const double *hbar,
+                             const double *hbar_old, const double *water_flux, const double *zbar, const double *CFL_z,
+                             double min_hnode, int lzstar_lev, double *Wvel, double *hnode_new);
 void ora_compute_cflz(const ora_mesh_t *m, double dt, const double *Wvel, double *CFL_z);
 void ora_compute_wvel_split(const ora_mesh_t *m, int use_wsplit, double wsplit_maxcfl, const double *Wvel,
                             const double *CFL_z, double *Wvel_e, double *Wvel_i);

@@ -524,3 +524,65 @@ def vert_vel_ale_zstar(mesh, zbar_3d_n, hnode, hnode_new, dt, W, hbar, hbar_old,
     top = uln == 1
     Wn[top, 0] = Wn[top, 0] - np.asarray(water_flux)[:N][top]
     return W, hn
+
+
+def vert_vel_ale_zlevel(mesh, zbar, hnode, hnode_new, cfl_z, dt, W, hbar, hbar_old, water_flux, min_hnode, lzstar_lev):
+    """src/oce_ale.F90:2336-2538 (which_ALE = 'zlevel'), vectorised over the columns: returns (W, hnode_new).  The three
+    cases of a cavity-free column -- local zstar over the first lzstar_lev layers (:2367-2454), refill of the subsurface
+    layers (:2461-2510), plain zlevel (:2519-2520) -- are masks; the two short recurrences over the layers run as loops
+    over k with whole-array operands.  `zbar` is mesh%zbar (nl), `cfl_z` the previous step's CFL_z (nl, Nh)."""
+    N, lz = mesh.N, int(lzstar_lev)
+    fmax = lambda a, b: np.where(a > b, a, b)            # Fortran MAX / MIN on reals   # noqa: E731
+    fmin = lambda a, b: np.where(a < b, a, b)            # noqa: E731
+    W, hn = np.array(W, dtype=np.float64), np.array(hnode_new, dtype=np.float64)
+    zbar = np.asarray(zbar, dtype=np.float64)
+    h = np.asarray(hnode, dtype=np.float64)[:N, :lz]
+    cfl = np.asarray(cfl_z, dtype=np.float64)[:N, :lz]
+    top = np.asarray(mesh.ulevels_nod2D)[:N] == 1                                  # :2354 (nzmin == 1: layer k sits at index k-1)
+    nzmax0 = np.asarray(mesh.nlevels_nod2D_min)[:N] - 1
+    dh = np.asarray(hbar, dtype=np.float64)[:N] - np.asarray(hbar_old, dtype=np.float64)[:N]
+    rest = (zbar[:lz] - zbar[1:lz + 1])[None, :]
+    zero = np.zeros(N)
+    # ---- local zstar (:2367-2449)
+    A = top & (dh < 0.0) & (h[:, 0] + dh <= rest[0, 0] * min_hnode)
+    mx = rest * min_hnode - h
+    mx = np.where(mx >= 0.0, 0.0, mx)
+    mx = np.where(cfl >= 0.95, 0.0, mx)
+    cs = mx.copy()
+    cs[:, 1:] = mx[:, 1:] + mx[:, :-1]                                             # the reference's pairwise "cumsum", :2398
+    lt = cs < dh[:, None]
+    nzA = np.minimum(np.where(lt.any(axis=1), lt.argmax(axis=1) + 1, lz), nzmax0 - 1)      # :2399-2400, :2411
+    distrib = np.zeros((N, lz))
+    rest_d = dh.copy()
+    for k in range(lz):                                                            # :2412-2416
+        act = A & (k + 1 <= nzA)
+        d = fmax(rest_d, mx[:, k])
+        distrib[:, k] = np.where(act, d, 0.0)
+        rest_d = np.where(act, fmin(zero, rest_d - d), rest_d)
+    integ = np.zeros(N)
+    for k in range(lz - 1, -1, -1):                                                # :2438-2449
+        act = A & (k + 1 <= nzA)
+        integ = np.where(act, integ + distrib[:, k], integ)
+        W[:N, k] = np.where(act, W[:N, k] - integ / dt, W[:N, k])
+        hn[:N, k] = np.where(act, h[:, k] + distrib[:, k], hn[:N, k])
+    # ---- return to zlevel: refill the subsurface layers first (:2461-2510)
+    ne = h != rest
+    B = top & ~A & (dh > 0.0) & ne[:, 1:].any(axis=1)
+    mxB = rest - h
+    mxB[:, 0] = 1000.0
+    nzB = np.minimum(lz - ne[:, ::-1].argmax(axis=1), nzmax0 - 1)                  # :2482, :2488 (only used where B)
+    rest_d = dh.copy()
+    integ = np.zeros(N)
+    for k in range(lz - 1, -1, -1):
+        act = B & (k + 1 <= nzB)
+        d = fmin(rest_d, mxB[:, k])
+        rest_d = np.where(act, fmax(zero, rest_d - d), rest_d)
+        integ = np.where(act, integ + d, integ)
+        W[:N, k] = np.where(act, W[:N, k] - integ / dt, W[:N, k])
+        hn[:N, k] = np.where(act, h[:, k] + d, hn[:N, k])
+    # ---- the normal zlevel case (:2519-2520) and the fresh-water flux (:2527)
+    Cn = top & ~A & ~B
+    W[:N, 0] = np.where(Cn, W[:N, 0] - dh / dt, W[:N, 0])
+    hn[:N, 0] = np.where(Cn, h[:, 0] + dh, hn[:N, 0])
+    W[:N, 0] = np.where(top, W[:N, 0] - np.asarray(water_flux, dtype=np.float64)[:N], W[:N, 0])
+    return W, hn

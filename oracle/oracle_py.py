@@ -355,3 +355,18 @@ def vert_vel_ale_zstar(rank: "OracleRank", dt: float, Wvel: np.ndarray, hbar, hb
     a = [np.ascontiguousarray(x, dtype=np.float64) for x in (hbar, hbar_old, water_flux)]
     L_.ora_vert_vel_ale_zstar(C.byref(rank.cmesh), float(dt), _ip(nmin), _dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(W), _dp(hn))
     return W, hn
+
+
+def vert_vel_ale_zlevel(rank: "OracleRank", dt: float, Wvel: np.ndarray, hbar, hbar_old, water_flux, zbar, cfl_z, min_hnode: float, lzstar_lev: int):
+    """ora_vert_vel_ale_zlevel: returns (Wvel, hnode_new) after the zlevel correction; the rank's hnode_new is the start."""
+    L_ = lib()
+    L_.ora_vert_vel_ale_zlevel.argtypes = [C.POINTER(OraMesh), C.c_double, c_ip, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_double, C.c_int, c_dp, c_dp]
+    L_.ora_vert_vel_ale_zlevel.restype = None
+    m = rank.mesh_py
+    W = np.ascontiguousarray(Wvel, dtype=np.float64).copy()
+    hn = rank.keep["hnode_new"].copy()
+    nmin = np.ascontiguousarray(m.nlevels_nod2D_min, dtype=np.int32)
+    a = [np.ascontiguousarray(x, dtype=np.float64) for x in (hbar, hbar_old, water_flux, zbar, cfl_z)]
+    L_.ora_vert_vel_ale_zlevel(C.byref(rank.cmesh), float(dt), _ip(nmin), _dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(a[3]), _dp(a[4]),
+                               float(min_hnode), int(lzstar_lev), _dp(W), _dp(hn))
+    return W, hn

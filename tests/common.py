@@ -59,3 +59,29 @@ def run_cuda(mesh, st, trs, nb, dt, device=0, host_ptrs=False):
     ctx.set_state(st_d)
     ctx.do_oce_adv_tra(dt, trs_d, dh, dv)
     return ctx, [x.cpu().numpy() for x in dh], [x.cpu().numpy() for x in dv]
+
+
+def zlevel_case(mesh, st, lz=4, min_hnode=0.5):
+    """Inputs that drive every branch of the reference's which_ALE = 'zlevel' correction (src/oce_ale.F90:2336-2538):
+    modifies st.hnode in place (squeezed subsurface layers in a quarter of the columns) and returns
+    (hbar, hbar_old, water_flux, cfl_z_old).  Column classes by node id mod 4: 0 small change (plain zlevel),
+    1 a drop that empties the surface layer (local zstar over several layers, some of them already at their
+    minimum or CFL-limited), 2 a rise over squeezed subsurface layers (refill), 3 a rise / small drop over rest layers."""
+    Nh = mesh.Nh
+    ids = np.arange(Nh, dtype=np.float64)
+    cls = np.arange(Nh) % 4
+    zb = np.asarray(mesh.zbar, dtype=np.float64)
+    rest = zb[:lz] - zb[1:lz + 1]
+    h = st.hnode.numpy()
+    sq = 0.55 + 0.4 * np.abs(np.sin(0.3 * ids))                   # 0.55 .. 0.95 of the rest thickness
+    for k in range(1, lz):
+        col = (cls == 2) | ((cls == 1) & (np.arange(Nh) % 3 == k % 3))
+        h[col, k] = (rest[k] * sq * (1.0 - 0.05 * k))[col]
+    hbar_old = 0.05 * np.sin(0.37 * ids)
+    dh = 0.01 * np.cos(0.11 * ids)
+    dh = np.where(cls == 1, -rest[0] * (0.55 + 1.2 * np.abs(np.sin(0.23 * ids))), dh)
+    dh = np.where(cls == 2, rest[0] * (0.02 + 0.5 * np.abs(np.sin(0.19 * ids))), dh)
+    dh = np.where(cls == 3, 0.3 * np.sin(0.41 * ids), dh)
+    wflux = 1.0e-6 * np.sin(0.05 * ids)
+    cfl_old = 1.1 * np.abs(np.sin(0.7 * ids[:, None] + np.arange(mesh.nl)[None, :]))
+    return hbar_old + dh, hbar_old, wflux, cfl_old

@@ -57,7 +57,7 @@ def f_types():
 
 def test_bind_c_types_match_the_header_structs():
     cs, fs = c_structs(), f_types()
-    assert set(fs) == {"adv_mesh_desc_t", "adv_state_desc_t", "adv_tracer_desc_t", "adv_gradient_mesh_desc_t", "adv_zstar_desc_t"}
+    assert set(fs) == {"adv_mesh_desc_t", "adv_state_desc_t", "adv_tracer_desc_t", "adv_gradient_mesh_desc_t", "adv_zstar_desc_t", "adv_zlevel_desc_t"}
     for name, ff in fs.items():
         assert name in cs, name
         assert ff == cs[name], (name, [x for x in zip(ff, cs[name]) if x[0] != x[1]][:3], len(ff), len(cs[name]))

@@ -188,3 +188,83 @@ def test_vert_vel_ale_zstar(world, pi_mesh):
         assert np.array_equal(q["st"].hnode_new.cpu().numpy(), hn[a])
         q["ctx"].close()
     assert (wi != 0).any() and not np.array_equal(hn, st.hnode_new.numpy())
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_vert_vel_ale_zlevel(world, pi_mesh):
+    """which_ALE = 'zlevel' (src/oce_ale.F90:2336-2538): continuity part + the surface-layer / local-zstar / refill
+    correction of Wvel and hnode_new (all three branches occur in the inputs) + fresh-water flux + both exchanges +
+    CFLz/split with the NEW hnode_new, against the oracle chain; cfl_z carries the previous step's CFL_z in"""
+    import threading
+    from common import zlevel_case
+    from oracle import oracle_py as O
+    from fesom2_b200.driver import AdvB200, comm_init_local
+    g = pi_mesh
+    st, trs, nb_g, dt = make_case(g, 1)
+    dtc = 40.0 * dt
+    lz, mh = 4, 0.5
+    hbar, hbar_old, wflux, cfl_old = zlevel_case(g, st, lz, mh)
+    rk = O.OracleRank(g, st, trs, nb_g)
+    W0 = O.vert_vel_ale_core(rk)
+    W, hn = O.vert_vel_ale_zlevel(rk, dtc, W0, hbar, hbar_old, wflux, g.zbar, cfl_old, mh, lz)
+    assert (hn[:g.N, 1:lz] != st.hnode_new.numpy()[:g.N, 1:lz]).any()
+    rk.keep["hnode_new"][...] = hn                     # compute_CFLz sees the new thickness
+    cfl, we, wi = O.compute_cflz_and_split(rk, dtc, W, True, 0.5)
+    ndev = torch.cuda.device_count()
+    part = g.parts[world] if world > 1 else np.zeros(g.Nh, np.int32)
+    ranks = []
+    for r in range(world):
+        loc = M.localize(g, part, r) if world > 1 else g
+        lst = F.scatter_to_local(g, loc, st, trs)[0] if world > 1 else st
+        alln = (loc.myList_nod2D.astype(np.int64) - 1) if world > 1 else np.arange(g.Nh)
+        dev = torch.device(f"cuda:{r % ndev}")
+        st_d, _ = to_device(lst, [], dev)
+        ctx = AdvB200(loc, nb_g[alln], device=r % ndev, max_tracers=1)
+        t = lambda a, dt_=torch.float64: torch.as_tensor(np.ascontiguousarray(a[alln]), dtype=dt_, device=dev)   # noqa: E731
+        out = [torch.zeros((loc.Nh, loc.nl), dtype=torch.float64, device=dev) for _ in range(3)] + [t(cfl_old)]
+        ranks.append(dict(loc=loc, ctx=ctx, st=st_d, alln=alln, err=None, hbar=t(hbar), hbar_old=t(hbar_old), wflux=t(wflux),
+                          zbar=torch.as_tensor(np.ascontiguousarray(g.zbar), dtype=torch.float64, device=dev),
+                          nmin=torch.as_tensor(np.ascontiguousarray(g.nlevels_nod2D_min[alln]), dtype=torch.int32, device=dev), out=out))
+    if world > 1:
+        comm_init_local([rk_["ctx"] for rk_ in ranks])
+    torch.cuda.synchronize()
+
+    def work(q):
+        try:
+            ctx, s = q["ctx"], q["st"]
+            torch.cuda.set_device(ctx.device)
+            ctx.set_state(s)
+            ctx.vert_vel_ale_zlevel(dtc, True, 0.5, q["hbar"], q["hbar_old"], q["wflux"], q["nmin"], s.hnode_new, q["zbar"], mh, lz, *q["out"])
+            ctx.synchronize()
+        except Exception as ex:
+            q["err"] = ex
+    th = [threading.Thread(target=work, args=(q,)) for q in ranks]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    for q in ranks:
+        if q["err"] is not None:
+            raise q["err"]
+        a = q["alln"]
+        for got, ref, name in zip(q["out"], (W, we, wi, cfl), ("w", "w_e", "w_i", "cfl_z")):
+            assert np.array_equal(got.cpu().numpy(), ref[a]), (name, world)
+        assert np.array_equal(q["st"].hnode_new.cpu().numpy(), hn[a])
+        q["ctx"].close()
+
+
+def test_vert_vel_ale_zlevel_rejects_bad_arguments(pi_mesh):
+    """cfl_z = NULL (nothing to read the previous CFL_z from) and lzstar_lev outside 1..16 are refused"""
+    from fesom2_b200.driver import AdvB200, AdvError
+    g = pi_mesh
+    st, trs, nb_g, dt = make_case(g, 1)
+    dev = torch.device("cuda:0")
+    st_d, _ = to_device(st, [], dev)
+    ctx = AdvB200(g, nb_g, device=0, max_tracers=1)
+    ctx.set_state(st_d)
+    z = lambda n, dt_=torch.float64: torch.zeros(n, dtype=dt_, device=dev)   # noqa: E731
+    out = [z((g.Nh, g.nl)) for _ in range(4)]
+    args = (z(g.Nh), z(g.Nh), z(g.Nh), torch.ones(g.Nh, dtype=torch.int32, device=dev), st_d.hnode_new, z(g.nl))
+    with pytest.raises(AdvError):
+        ctx.vert_vel_ale_zlevel(1.0, False, 1.0, *args, 0.5, 4, out[0], out[1], out[2], None)
+    with pytest.raises(AdvError):
+        ctx.vert_vel_ale_zlevel(1.0, False, 1.0, *args, 0.5, 17, *out)
+    ctx.close()

@@ -246,3 +246,29 @@ def test_vert_vel_ale_zstar_two_restatements(pi_mesh):
     for x, y in zip(a, b):
         assert np.isfinite(x).all() and np.array_equal(x, y)
     assert not np.array_equal(a[0], W) and not np.array_equal(a[1], st.hnode_new.numpy())
+
+
+def test_vert_vel_ale_zlevel_two_restatements(pi_mesh):
+    """the zlevel free-surface correction of vert_vel_ale (src/oce_ale.F90:2336-2538: plain zlevel, local zstar over the
+    first lzstar_lev layers, refill on the way back): C loop vs masked whole-array NumPy, every branch exercised"""
+    from common import zlevel_case
+    from oracle import numpy_ref as R, oracle_py as O
+    g = pi_mesh
+    st, trs, nb, dt = make_case(g, 1)
+    for lz, mh in ((4, 0.5), (3, 0.7)):
+        hbar, hbar_old, wflux, cfl_old = zlevel_case(g, st, lz, mh)
+        rk = O.OracleRank(g, st, trs, nb)
+        W = O.vert_vel_ale_core(rk)
+        a = O.vert_vel_ale_zlevel(rk, 1800.0, W, hbar, hbar_old, wflux, g.zbar, cfl_old, mh, lz)
+        b = R.vert_vel_ale_zlevel(g, g.zbar, st.hnode.numpy(), st.hnode_new.numpy(), cfl_old, 1800.0, W, hbar, hbar_old, wflux, mh, lz)
+        for x, y in zip(a, b):
+            assert np.isfinite(x).all() and np.array_equal(x, y)
+        # every branch is taken: layers below the surface change in some columns (local zstar / refill), only the
+        # surface layer in others, and the elevation change is conserved by the distribution wherever it fits
+        ch = a[1][:g.N] != st.hnode_new.numpy()[:g.N]
+        deep = ch[:, 1:lz].any(axis=1)
+        assert deep.any() and (ch[:, 0] & ~deep).any() and not ch[:, lz:].any()
+        top = np.asarray(g.ulevels_nod2D)[:g.N] == 1
+        dsum = (a[1][:g.N, :lz] - st.hnode.numpy()[:g.N, :lz]).sum(axis=1)
+        ok = top & (np.abs(dsum - (hbar - hbar_old)[:g.N]) < 1e-10)
+        assert ok.sum() > 0.5 * top.sum()
