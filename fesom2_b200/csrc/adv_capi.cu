@@ -110,7 +110,7 @@ struct DevBuf {
 };
 
 struct Slot {  // per-tracer staging: host pointers, unaligned device pointers, library-computed gradients
-    DevBuf<double> ttf, ttfAB, grad, dh, dv, tr_xy, gmean;
+    DevBuf<double> ttf, ttfAB, grad, dh, dv, tr_xy, gmean, dgh, dgv;
 };
 
 // work arrays of one chunk of <= 2 tracers (t_tracer_work, allocated by oce_adv_tra_fct_init in the
@@ -659,6 +659,7 @@ inline int nblocks(int count, int cpb) { return (count + cpb - 1) / cpb; }
 struct TrPtrs {   // device pointers of the call's tracers
     std::vector<const double*> ttf, ttfAB, grad, txy, gmean;   // grad == nullptr && txy != nullptr: fused gradients
     std::vector<double*> dh, dv;
+    std::vector<double*> dgh, dgv;                             // ltra_diag outputs (nullptr = off)
 };
 
 template <int TB>
@@ -670,6 +671,7 @@ Chunk<TB> make_chunk(adv_ctx* c, const TrPtrs& p, const adv_tracer_desc_t* tr, c
         const int i = ch.idx[t];
         b.ttf[t] = p.ttf[i]; b.ttfAB[t] = p.ttfAB[i]; b.grad[t] = p.grad[i]; b.txy[t] = p.txy[i]; b.gmean[t] = p.gmean[i];
         b.dttf_h[t] = p.dh[i]; b.dttf_v[t] = p.dv[i];
+        b.dgh[t] = p.dgh[i]; b.dgv[t] = p.dgv[i];
         b.ph[t] = tr[i].tra_adv_ph; b.pv[t] = tr[i].tra_adv_pv;
     }
     b.lo = cb.lo.p; b.adf_h = cb.adf_h.p; b.adf_v = cb.adf_v.p; b.pm = cb.pm.p;
@@ -1041,12 +1043,14 @@ static int do_adv(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr, i
     const size_t nLN = (size_t)m.L * m.Nh, nLE = (size_t)m.L * m.E;
     TrPtrs p;
     p.ttf.resize(ntr); p.ttfAB.resize(ntr); p.grad.resize(ntr); p.txy.assign(ntr, nullptr); p.gmean.assign(ntr, nullptr); p.dh.resize(ntr); p.dv.resize(ntr);
+    p.dgh.assign(ntr, nullptr); p.dgv.assign(ntr, nullptr);
     for (int i = 0; i < ntr; ++i) {
         if (!tr[i].values || !tr[i].valuesAB || !tr[i].del_ttf_advhoriz || !tr[i].del_ttf_advvert)
             return fail(ADV_EINVAL, "tracer " + std::to_string(i + 1) + ": null field");
         if (where == ADV_DEVICE) {
             p.ttf[i] = tr[i].values; p.ttfAB[i] = tr[i].valuesAB; p.grad[i] = tr[i].edge_up_dn_grad;
             p.dh[i] = tr[i].del_ttf_advhoriz; p.dv[i] = tr[i].del_ttf_advvert;
+            p.dgh[i] = tr[i].tra_advhoriz; p.dgv[i] = tr[i].tra_advvert;
             if (tr[i].edge_up_dn_grad && ((uintptr_t)tr[i].edge_up_dn_grad & 15u)) {
                 // edge_up_dn_grad(1:4,nz,e) is read as 16-byte words / bulk copies: stage an aligned copy
                 Slot& s = c->slots[i];
@@ -1071,6 +1075,16 @@ static int do_adv(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr, i
                 p.grad[i] = s.grad.p;
             }
             p.ttf[i] = s.ttf.p; p.ttfAB[i] = s.ttfAB.p; p.dh[i] = s.dh.p; p.dv[i] = s.dv.p;
+            // ltra_diag arrays: staged both ways (the entries the path does not write keep the caller's values)
+            double* const hd[2] = {tr[i].tra_advhoriz, tr[i].tra_advvert};
+            DevBuf<double>* const sd[2] = {&s.dgh, &s.dgv};
+            for (int k = 0; k < 2; ++k) {
+                if (!hd[k]) continue;
+                host_register(c, hd[k], nLN * 8);
+                if (sd[k]->n != nLN) CU(sd[k]->alloc(nLN, false));
+                CU(cudaMemcpyAsync(sd[k]->p, hd[k], nLN * 8, cudaMemcpyHostToDevice, c->s_comp));
+                (k == 0 ? p.dgh[i] : p.dgv[i]) = sd[k]->p;
+            }
         }
     }
     // edge_up_dn_grad == NULL for a gradient-based scheme: the library runs the caller's tracer_gradient_elements,
@@ -1143,6 +1157,8 @@ static int do_adv(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr, i
         for (int i = 0; i < ntr; ++i) {
             CU(cudaMemcpyAsync(tr[i].del_ttf_advhoriz, p.dh[i], nLN * 8, cudaMemcpyDeviceToHost, c->s_comp));
             CU(cudaMemcpyAsync(tr[i].del_ttf_advvert, p.dv[i], nLN * 8, cudaMemcpyDeviceToHost, c->s_comp));
+            if (tr[i].tra_advhoriz) CU(cudaMemcpyAsync(tr[i].tra_advhoriz, p.dgh[i], nLN * 8, cudaMemcpyDeviceToHost, c->s_comp));
+            if (tr[i].tra_advvert) CU(cudaMemcpyAsync(tr[i].tra_advvert, p.dgv[i], nLN * 8, cudaMemcpyDeviceToHost, c->s_comp));
         }
     }
     if (blocking) CU(cudaStreamSynchronize(c->s_comp));

@@ -135,6 +135,8 @@ struct Chunk {
     const double* gmean[TB];
     double* dttf_h[TB];
     double* dttf_v[TB];
+    double* dgh[TB];          // tra_advhoriz / tra_advvert (nl-1, Nh) of tracers with ltra_diag (oce_adv_tra_driver.F90:221-229,
+    double* dgv[TB];          //   :307-318, :464-488), owned nodes; nullptr = off
     double ph[TB], pv[TB];
     double *lo, *adf_h, *adf_v, *pm;
     int nolo;                 // 1: tra_adv_lim /= 'FCT' -- the edge kernel stores the high-order flux itself (o_init_zero = .true.,
@@ -919,6 +921,9 @@ __global__ void ADV_N1_BOUNDS k_node_lo(MeshDev m, Chunk<TB> b, NodePart r, doub
         const double fv = flo_top[t] - flo_bot;                                          // fv(nz)-fv(nz+1)
         const double num = tn[t] * hn + div_rcp((losum[t] + fv) * dt, av, r_av);
         lo_out[t] = div_rcp(num, hnn, r_hnn);                                            // driver :249
+        // ltra_diag: the low-order parts of tra_advhoriz / tra_advvert (driver :221-229, :307-318); plain IEEE divisions
+        if (b.dgh[t]) b.dgh[t][oL] = losum[t] * dt / av / hnn;
+        if (b.dgv[t]) b.dgv[t][oL] = fv * dt / av / hnn;
     }
     stv<TB>(b.lo + (size_t)oL * TB, lo_out);
 }
@@ -1387,6 +1392,7 @@ __global__ void ADV_K2_BOUNDS k_fct_bounds(MeshDev m, Chunk<TB> b, NodePart r, d
         d = d - tn_t * hn + lo_n[t] * hnn;                            // driver :535
         d = d + div_rcp((fv_top - fv_bot) * dt, av, r_av);            // driver :556
         b.dttf_v[t][oL] = d;
+        if (b.dgv[t]) b.dgv[t][oL] = b.dgv[t][oL] + d / hnn;          // ltra_diag, driver :473
     }
 }
 
@@ -1476,7 +1482,10 @@ __global__ void ADV_K3_BOUNDS k_fct_update(MeshDev m, Chunk<TB> b, NodePart r, d
         }
     }
 #pragma unroll
-    for (int t = 0; t < TB; ++t) b.dttf_h[t][oL] = dh[t];
+    for (int t = 0; t < TB; ++t) {
+        b.dttf_h[t][oL] = dh[t];
+        if (b.dgh[t] && n < m.N) b.dgh[t][oL] = b.dgh[t][oL] + dh[t] / __ldg(&m.hnode_new[oL]);   // ltra_diag, driver :472
+    }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1562,7 +1571,14 @@ __global__ void __launch_bounds__(kBlock) k_nofct_update(MeshDev m, Chunk<TB> b,
         }
     }
 #pragma unroll
-    for (int t = 0; t < TB; ++t) b.dttf_h[t][oL] = dh[t];
+    for (int t = 0; t < TB; ++t) {
+        b.dttf_h[t][oL] = dh[t];
+        if (owned && (b.dgh[t] || b.dgv[t])) {                        // ltra_diag without FCT, driver :482-483
+            const double hnn = __ldg(&m.hnode_new[oL]);
+            if (b.dgh[t]) b.dgh[t][oL] = dh[t] / hnn;
+            if (b.dgv[t]) b.dgv[t][oL] = b.dttf_v[t][oL] / hnn;
+        }
+    }
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -79,6 +79,7 @@ module oce_adv_tra_b200
      type(c_ptr) :: values, valuesAB, edge_up_dn_grad, del_ttf_advhoriz, del_ttf_advvert
      type(c_ptr) :: tra_adv_hor, tra_adv_ver, tra_adv_lim
      real(c_double) :: tra_adv_ph, tra_adv_pv
+     type(c_ptr) :: tra_advhoriz, tra_advvert
   end type adv_tracer_desc_t
 
   ! adv_gradient_mesh_desc_t
@@ -367,7 +368,7 @@ contains
     type(adv_tracer_desc_t), allocatable :: td(:)
     character(kind=c_char, len=21), allocatable, target :: hs(:), vs(:), ls(:)
     real(kind=WP), pointer :: helem(:,:), hnode(:,:), hnode_new(:,:), zbar_3d_n(:,:), Z_3d_n(:,:), zbar_n_bot(:)
-    real(kind=WP), pointer :: values(:,:), valuesAB(:,:), grad1(:,:,:), dh1(:,:), dv1(:,:)
+    real(kind=WP), pointer :: values(:,:), valuesAB(:,:), grad1(:,:,:), dh1(:,:), dv1(:,:), dgh1(:,:), dgv1(:,:)
     integer :: i, k, n, rc
 
     n = tr_last - tr_first + 1
@@ -409,6 +410,13 @@ contains
        td(k)%tra_adv_hor = c_loc(hs(k)); td(k)%tra_adv_ver = c_loc(vs(k)); td(k)%tra_adv_lim = c_loc(ls(k))
        td(k)%tra_adv_ph = tracers%data(i)%tra_adv_ph
        td(k)%tra_adv_pv = tracers%data(i)%tra_adv_pv
+       ! ltra_diag (default .true., src/MOD_TRACER.F90:25): the tracer's slices of tracers%work%tra_advhoriz / tra_advvert
+       ! (src/oce_adv_tra_driver.F90:221-229, :307-318, :464-488); the tracer index is the last one, so a slice is contiguous
+       td(k)%tra_advhoriz = c_null_ptr; td(k)%tra_advvert = c_null_ptr
+       if (tracers%data(i)%ltra_diag) then
+          dgh1 => tracers%work%tra_advhoriz(:,:,i); dgv1 => tracers%work%tra_advvert(:,:,i)
+          td(k)%tra_advhoriz = ADV_ADDR(dgh1); td(k)%tra_advvert = ADV_ADDR(dgv1)
+       end if
     end do
 #ifdef ENABLE_OPENACC
     ! the operands may still be in flight on the OpenACC queues: order the library's stream behind them

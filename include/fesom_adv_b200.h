@@ -96,6 +96,12 @@ typedef struct {
     const char *tra_adv_ver;       /* "QR4C" | "CDIFF" | "PPM" | "UPW1"  */
     const char *tra_adv_lim;       /* "FCT" or anything else = no limiter */
     double tra_adv_ph, tra_adv_pv; /* num_ord of the horizontal / vertical scheme */
+    /* tracers%data(tr_num)%ltra_diag (default .true., src/MOD_TRACER.F90:25): the tracer's slices of
+     * tracers%work%tra_advhoriz / tra_advvert, (nl-1, Nh) each, or NULL for ltra_diag = .false.  On return the wet layers of
+     * the OWNED nodes hold what src/oce_adv_tra_driver.F90:221-229, :307-318 and :464-488 leave there -- with FCT the
+     * low-order tendency plus (del_ttf_advhoriz | del_ttf_advvert after the call) / hnode_new, otherwise that quotient alone; everything else
+     * (halo nodes, where the reference stores partial edge sums nobody reads, and dry layers) is left untouched. */
+    double *tra_advhoriz, *tra_advvert;
 } adv_tracer_desc_t;
 
 /* --- life cycle ------------------------------------------------------------------------------ */

@@ -600,6 +600,12 @@ int ora_do_oce_adv_tra(const ora_mesh_t *m, ora_work_t *wk, double dt,
                 fct_LO[IX2(L, nz, en2)] = fct_LO[IX2(L, nz, en2)] - adv_flux_hor[IX2(L, nz, e)];
             }
         }
+        if (wk->tra_advhoriz)                                                        /* :221-229 ltra_diag: LO, horizontal part */
+            for (int n = 1; n <= Nh; ++n) {
+                const int nu1 = m->ulevels_nod2D[n - 1], nl1 = m->nlevels_nod2D[n - 1];
+                for (int nz = nu1; nz <= nl1 - 1; ++nz)
+                    wk->tra_advhoriz[IX2(L, nz, n)] = fct_LO[IX2(L, nz, n)] * dt / AVOL(nz, n) / HNN(nz, n);
+            }
         ora_adv_tra_ver_upw1(m, we, ttf, adv_flux_ver, 1);                           /* :235 */
         for (int n = 1; n <= N; ++n) {                                               /* :243-252 */
             const int nu1 = m->ulevels_nod2D[n - 1], nl1 = m->nlevels_nod2D[n - 1];
@@ -610,6 +616,19 @@ int ora_do_oce_adv_tra(const ora_mesh_t *m, ora_work_t *wk, double dt,
                          dt / AVOL(nz, n)) /
                     HNN(nz, n);
         }
+        if (wk->dvd_trflx_hor)                                                       /* :263-281 ldiag_DVD: LO fluxes */
+            for (int e = 1; e <= E; ++e)
+                for (int nz = 1; nz <= L; ++nz) wk->dvd_trflx_hor[IX2(L, nz, e)] = adv_flux_hor[IX2(L, nz, e)];
+        if (wk->dvd_trflx_ver)                                                       /* :283-296 */
+            for (int n = 1; n <= N; ++n)
+                for (int nz = 1; nz <= nl; ++nz) wk->dvd_trflx_ver[IX2(nl, nz, n)] = adv_flux_ver[IX2(nl, nz, n)];
+        if (wk->tra_advvert)                                                         /* :307-318 ltra_diag: LO, vertical part */
+            for (int n = 1; n <= N; ++n) {
+                const int nu1 = m->ulevels_nod2D[n - 1], nl1 = m->nlevels_nod2D[n - 1];
+                for (int nz = nu1; nz <= nl1 - 1; ++nz)
+                    wk->tra_advvert[IX2(L, nz, n)] =
+                        (adv_flux_ver[IX2(nl, nz, n)] - adv_flux_ver[IX2(nl, nz + 1, n)]) * dt / AVOL(nz, n) / HNN(nz, n);
+            }
         if (use_wsplit) {                                                            /* :323-334 */
             ora_adv_tra_vert_impl(m, dt, wi, fct_LO);
             ora_adv_tra_ver_upw1(m, w, ttf, adv_flux_ver, 1);
@@ -646,6 +665,28 @@ int ora_do_oce_adv_tra(const ora_mesh_t *m, ora_work_t *wk, double dt,
     } else {
         ora_oce_tra_adv_flux2dtracer(m, dt, dttf_h, dttf_v, adv_flux_hor, adv_flux_ver, 0, NULL, NULL);
     }
+    if (wk->dvd_trflx_hor)                                                           /* :395-458: + the (limited) antidiffusive flux, or the HO flux itself */
+        for (int e = 1; e <= E; ++e)
+            for (int nz = 1; nz <= L; ++nz)
+                wk->dvd_trflx_hor[IX2(L, nz, e)] = fct ? wk->dvd_trflx_hor[IX2(L, nz, e)] + adv_flux_hor[IX2(L, nz, e)] : adv_flux_hor[IX2(L, nz, e)];
+    if (wk->dvd_trflx_ver)
+        for (int n = 1; n <= N; ++n)
+            for (int nz = 1; nz <= nl; ++nz)
+                wk->dvd_trflx_ver[IX2(nl, nz, n)] = fct ? wk->dvd_trflx_ver[IX2(nl, nz, n)] + adv_flux_ver[IX2(nl, nz, n)] : adv_flux_ver[IX2(nl, nz, n)];
+    if (wk->tra_advhoriz || wk->tra_advvert)                                         /* :464-488 ltra_diag */
+        for (int n = 1; n <= Nh; ++n) {
+            const int nu1 = m->ulevels_nod2D[n - 1], nl1 = m->nlevels_nod2D[n - 1];
+            for (int nz = nu1; nz <= nl1 - 1; ++nz) {
+                if (wk->tra_advhoriz) {
+                    if (fct) wk->tra_advhoriz[IX2(L, nz, n)] = wk->tra_advhoriz[IX2(L, nz, n)] + dttf_h[IX2(L, nz, n)] / HNN(nz, n);   /* :472 */
+                    else wk->tra_advhoriz[IX2(L, nz, n)] = dttf_h[IX2(L, nz, n)] / HNN(nz, n);                                         /* :482 */
+                }
+                if (wk->tra_advvert) {
+                    if (fct) wk->tra_advvert[IX2(L, nz, n)] = wk->tra_advvert[IX2(L, nz, n)] + dttf_v[IX2(L, nz, n)] / HNN(nz, n);     /* :473 */
+                    else wk->tra_advvert[IX2(L, nz, n)] = dttf_v[IX2(L, nz, n)] / HNN(nz, n);                                          /* :483 */
+                }
+            }
+        }
     return 0;
 }
 
@@ -706,6 +747,10 @@ static void *ora_thread_main(void *arg)
                 memset(rk->dttf_h[t], 0, sizeof(double) * (size_t)L * (size_t)Nh);
                 memset(rk->dttf_v[t], 0, sizeof(double) * (size_t)L * (size_t)Nh);
             }
+            rk->work.tra_advhoriz = rk->tra_advhoriz ? rk->tra_advhoriz[t] : NULL;
+            rk->work.tra_advvert = rk->tra_advvert ? rk->tra_advvert[t] : NULL;
+            rk->work.dvd_trflx_hor = rk->dvd_trflx_hor ? rk->dvd_trflx_hor[t] : NULL;
+            rk->work.dvd_trflx_ver = rk->dvd_trflx_ver ? rk->dvd_trflx_ver[t] : NULL;
             ora_do_oce_adv_tra(m, &rk->work, th->dt, rk->vel, rk->w, rk->wi, rk->we, rk->use_wsplit,
                                rk->values[t], rk->valuesAB[t], rk->edge_up_dn_grad[t],
                                rk->hor[t], rk->ver[t], rk->lim[t], rk->opth[t], rk->optv[t],

@@ -63,6 +63,9 @@ typedef struct {
     double *tvert_max, *tvert_min;     /* (L,Nh) automatic arrays of oce_tra_adv_fct */
     double *AUX;             /* (4,L,E) FCT scratch; the reference aliases edge_up_dn_grad */
     const int *nboundary_lay;/* (Nh) */
+    /* optional diagnostics of the CURRENT tracer (NULL = off), oce_adv_tra_driver.F90:221-229,:263-296,:307-318,:395-458,:464-488 */
+    double *tra_advhoriz, *tra_advvert;     /* (L,Nh) tracers%data(tr_num)%ltra_diag (default .true., MOD_TRACER.F90:25) */
+    double *dvd_trflx_hor, *dvd_trflx_ver;  /* (L,E), (nl,N) ldiag_DVD .and. tr_num <= 2 */
 } ora_work_t;
 
 typedef void (*ora_exchange_fn)(void *user, double *field, int nlev); /* exchange_nod3D */
@@ -153,6 +156,8 @@ typedef struct {
     /* halo description: for halo node k (0-based, k < eDim_nod2D): owner rank and the owner's
      * 1-based local node index */
     const int *halo_owner, *halo_owner_idx;
+    /* optional per-tracer diagnostics, each NULL or [ntr] pointers (entries may be NULL) */
+    double **tra_advhoriz, **tra_advvert, **dvd_trflx_hor, **dvd_trflx_ver;
 } ora_rank_t;
 
 /* returns wall seconds of the timed region (all ranks, barrier to barrier). mode: 0 = only

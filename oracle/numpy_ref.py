@@ -331,8 +331,10 @@ class NumpyAdv:
         return np.where(self.scat, ae * adf_h, adf_h)
 
     # ------------------------------------------------------------------ driver
-    def do_oce_adv_tra(self, dt, tr, dttf_h, dttf_v):
-        """one tracer; accumulates into dttf_h / dttf_v (Nh, L) like the reference"""
+    def do_oce_adv_tra(self, dt, tr, dttf_h, dttf_v, diag=None):
+        """one tracer; accumulates into dttf_h / dttf_v (Nh, L) like the reference.  ``diag``: a dict that receives the
+        optional diagnostics of the call -- tra_advhoriz, tra_advvert (Nh, L) for ltra_diag (driver :221-229, :307-318,
+        :464-488) and dvd_trflx_hor (E, L), dvd_trflx_ver (N, nl) for ldiag_DVD (:263-296, :395-458)"""
         m, N, L, nl = self.m, self.N, self.L, self.nl
         f = lambda t: np.asarray(t.detach().cpu().numpy() if hasattr(t, "detach") else t, dtype=np.float64)
         ttf, ttfAB, grad = f(tr.values), f(tr.valuesAB), f(tr.edge_up_dn_grad)
@@ -346,6 +348,14 @@ class NumpyAdv:
             lo = np.zeros((self.Nh, L))
             self.scatter_edges(lo, flo_h)
             flo_v = self.ver_upw1(self.we, ttf, zV)
+            if diag is not None:
+                hnn_all = self.hnode_new
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    diag["tra_advhoriz"] = np.where(self.nvalid, lo * dt / m.areasvol[:, :L] / hnn_all, 0.0)
+                    tv = np.zeros((self.Nh, L))
+                    tv[:N] = np.where(valid, (flo_v[:, :L] - flo_v[:, 1:L + 1]) * dt / av / hnn_all[:N], 0.0)
+                diag["tra_advvert"] = tv
+                diag["dvd_trflx_hor"], diag["dvd_trflx_ver"] = flo_h.copy(), flo_v.copy()
             with np.errstate(divide="ignore", invalid="ignore"):
                 lo_new = (ttf[:N] * self.hnode[:N] + (lo[:N] + (flo_v[:, :L] - flo_v[:, 1:L + 1])) * dt / av) / self.hnode_new[:N]
             lo = np.where(self.nvalid, 0.0, 0.0)
@@ -373,6 +383,18 @@ class NumpyAdv:
         with np.errstate(divide="ignore", invalid="ignore"):
             val = np.stack([np.where(self.scat, c / a1, 0.0), np.where(self.scat, -(c / a2), 0.0)], 1).reshape(-1, L)
         np.add.at(dttf_h, idx, val)
+        if diag is not None:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                th = np.where(self.nvalid, dttf_h / self.hnode_new, 0.0)
+                tv = np.where(self.nvalid, dttf_v / self.hnode_new, 0.0)
+            if fct:                                                       # LO part + (antidiffusive part incl. what was there)
+                diag["tra_advhoriz"] = np.where(self.nvalid, diag["tra_advhoriz"] + th, 0.0)
+                diag["tra_advvert"] = np.where(self.nvalid, diag["tra_advvert"] + tv, 0.0)
+                diag["dvd_trflx_hor"] = diag["dvd_trflx_hor"] + adf_h
+                diag["dvd_trflx_ver"] = diag["dvd_trflx_ver"] + adf_v
+            else:
+                diag["tra_advhoriz"], diag["tra_advvert"] = th, tv
+                diag["dvd_trflx_hor"], diag["dvd_trflx_ver"] = adf_h.copy(), adf_v.copy()
         return dttf_h, dttf_v
 
 

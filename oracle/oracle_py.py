@@ -38,7 +38,8 @@ class OraMesh(C.Structure):
 class OraWork(C.Structure):
     _fields_ = [("fct_LO", c_dp), ("adv_flux_hor", c_dp), ("adv_flux_ver", c_dp),
                 ("fct_ttf_min", c_dp), ("fct_ttf_max", c_dp), ("fct_plus", c_dp), ("fct_minus", c_dp),
-                ("tvert_max", c_dp), ("tvert_min", c_dp), ("AUX", c_dp), ("nboundary_lay", c_ip)]
+                ("tvert_max", c_dp), ("tvert_min", c_dp), ("AUX", c_dp), ("nboundary_lay", c_ip),
+                ("tra_advhoriz", c_dp), ("tra_advvert", c_dp), ("dvd_trflx_hor", c_dp), ("dvd_trflx_ver", c_dp)]
 
 
 class OraRank(C.Structure):
@@ -48,7 +49,9 @@ class OraRank(C.Structure):
                 ("values", C.POINTER(c_dp)), ("valuesAB", C.POINTER(c_dp)),
                 ("edge_up_dn_grad", C.POINTER(c_dp)), ("dttf_h", C.POINTER(c_dp)), ("dttf_v", C.POINTER(c_dp)),
                 ("hor", c_ip), ("ver", c_ip), ("lim", c_ip), ("opth", c_dp), ("optv", c_dp),
-                ("halo_owner", c_ip), ("halo_owner_idx", c_ip)]
+                ("halo_owner", c_ip), ("halo_owner_idx", c_ip),
+                ("tra_advhoriz", C.POINTER(c_dp)), ("tra_advvert", C.POINTER(c_dp)),
+                ("dvd_trflx_hor", C.POINTER(c_dp)), ("dvd_trflx_ver", C.POINTER(c_dp))]
 
 
 def build(fast: bool = False, force: bool = False) -> str:
@@ -94,7 +97,9 @@ def _np(t) -> np.ndarray:
 class OracleRank:
     """All arrays of one rank, kept alive on the Python side, plus the C structs pointing at them."""
 
-    def __init__(self, mesh, state, tracers, nboundary_lay, alias_aux: bool = False):
+    def __init__(self, mesh, state, tracers, nboundary_lay, alias_aux: bool = False, tra_diag: bool = False, dvd: bool = False):
+        """tra_diag: tracers%data(:)%ltra_diag = .true. (tra_advhoriz / tra_advvert per tracer); dvd: ldiag_DVD (the first
+        two tracers get dvd_trflx_hor / dvd_trflx_ver, oce_adv_tra_driver.F90:263,:395)"""
         m = mesh
         self.mesh_py = m
         L, nl, Nh, N, T, E = m.L, m.nl, m.Nh, m.N, m.T, m.E
@@ -127,6 +132,10 @@ class OracleRank:
         self.grad = [_np(t.edge_up_dn_grad).copy() for t in tracers]
         self.dttf_h = [np.zeros((Nh, L)) for _ in tracers]
         self.dttf_v = [np.zeros((Nh, L)) for _ in tracers]
+        self.tra_advhoriz = [np.zeros((Nh, L)) for _ in tracers] if tra_diag else None
+        self.tra_advvert = [np.zeros((Nh, L)) for _ in tracers] if tra_diag else None
+        self.dvd_trflx_hor = [np.zeros((E, L)) if i < 2 else None for i in range(len(tracers))] if dvd else None
+        self.dvd_trflx_ver = [np.zeros((N, nl)) if i < 2 else None for i in range(len(tracers))] if dvd else None
         self.hor = np.array([HOR[t.tra_adv_hor] for t in tracers], np.int32)
         self.ver = np.array([VER[t.tra_adv_ver] for t in tracers], np.int32)
         self.lim = np.array([LIM[t.tra_adv_lim] for t in tracers], np.int32)
@@ -157,6 +166,13 @@ class OracleRank:
         rk.hor, rk.ver, rk.lim = _ip(self.hor), _ip(self.ver), _ip(self.lim)
         rk.opth, rk.optv = _dp(self.opth), _dp(self.optv)
         rk.halo_owner, rk.halo_owner_idx = _ip(self.halo_owner), _ip(self.halo_owner_idx)
+        self._pd = []
+        for name in ("tra_advhoriz", "tra_advvert", "dvd_trflx_hor", "dvd_trflx_ver"):
+            lst = getattr(self, name)
+            if lst is not None:
+                pa = PA(*[(_dp(a) if a is not None else c_dp()) for a in lst])
+                self._pd.append(pa)
+                setattr(rk, name, C.cast(pa, C.POINTER(c_dp)))
 
 
 def link_halos(ranks: Sequence[OracleRank]):

@@ -17,8 +17,9 @@ from fesom2_b200 import mesh as M
 
 
 def run_local_ranks(g, part, st, trs, dt, nsteps: int = 1, null_grad: bool = False, tri: Optional[np.ndarray] = None,
-                    exchange_inputs: bool = False):
-    """Returns one dict per rank: dh, dv, values (numpy), owned / all_nodes (global ids, 1-based), launches."""
+                    exchange_inputs: bool = False, tra_diag: bool = False):
+    """Returns one dict per rank: dh, dv, values (numpy), owned / all_nodes (global ids, 1-based), launches; with
+    tra_diag also tah, tav = the ltra_diag arrays tra_advhoriz / tra_advvert (pre-filled with 7.0)."""
     from fesom2_b200.driver import AdvB200, comm_init_local
     world = int(np.asarray(part).max()) + 1
     ndev = torch.cuda.device_count()
@@ -42,7 +43,9 @@ def run_local_ranks(g, part, st, trs, dt, nsteps: int = 1, null_grad: bool = Fal
                 t.valuesAB[loc.N:] = -1.0e30
         dh = [torch.zeros((loc.Nh, loc.L), dtype=torch.float64, device=dev) for _ in ltr]
         dv = [torch.zeros((loc.Nh, loc.L), dtype=torch.float64, device=dev) for _ in ltr]
-        ranks.append(dict(loc=loc, ctx=ctx, st=st_d, trs=trs_d, dh=dh, dv=dv, err=None))
+        tah = [torch.full((loc.Nh, loc.L), 7.0, dtype=torch.float64, device=dev) for _ in ltr] if tra_diag else None
+        tav = [torch.full((loc.Nh, loc.L), 7.0, dtype=torch.float64, device=dev) for _ in ltr] if tra_diag else None
+        ranks.append(dict(loc=loc, ctx=ctx, st=st_d, trs=trs_d, dh=dh, dv=dv, tah=tah, tav=tav, err=None))
     comm_init_local([rk["ctx"] for rk in ranks])
 
     def work(rk):
@@ -57,7 +60,7 @@ def run_local_ranks(g, part, st, trs, dt, nsteps: int = 1, null_grad: bool = Fal
                     for x in dh + dv:
                         x.zero_()
                     torch.cuda.current_stream().synchronize()
-                ctx.do_oce_adv_tra(dt, trs_d, dh, dv)
+                ctx.do_oce_adv_tra(dt, trs_d, dh, dv, tra_advhoriz=rk["tah"], tra_advvert=rk["tav"])
                 if nsteps > 1:
                     ctx.update_values([t.values for t in trs_d], dh, dv)     # + exchange_nod(values)
                     ctx.synchronize()
@@ -79,7 +82,10 @@ def run_local_ranks(g, part, st, trs, dt, nsteps: int = 1, null_grad: bool = Fal
         res = dict(dh=[x.cpu().numpy() for x in rk["dh"]], dv=[x.cpu().numpy() for x in rk["dv"]],
                    values=[t.values.cpu().numpy() for t in rk["trs"]], owned=loc.myList_nod2D[:loc.N],
                    all_nodes=loc.myList_nod2D, launches=ctx.launch_count, N=loc.N)
-        if world > 1:
+        if tra_diag:
+            res["tah"] = [x.cpu().numpy() for x in rk["tah"]]
+            res["tav"] = [x.cpu().numpy() for x in rk["tav"]]
+        if world > 1 and any(t.tra_adv_lim.strip() == "FCT" for t in rk["trs"]):   # a call without limiter exchanges nothing
             res["halo_stats"] = ctx.halo_stats()
         out.append(res)
     for rk in ranks:

@@ -272,3 +272,26 @@ def test_vert_vel_ale_zlevel_two_restatements(pi_mesh):
         dsum = (a[1][:g.N, :lz] - st.hnode.numpy()[:g.N, :lz]).sum(axis=1)
         ok = top & (np.abs(dsum - (hbar - hbar_old)[:g.N]) < 1e-10)
         assert ok.sum() > 0.5 * top.sum()
+
+
+@pytest.mark.parametrize("hor,ver,lim,wsplit", [("MFCT", "QR4C", "FCT", False), ("MUSCL", "PPM", "FCT", True),
+                                                ("MFCT", "QR4C", "NON", False), ("UPW1", "UPW1", "FCT", False)])
+def test_diagnostics_two_restatements(pi_mesh, hor, ver, lim, wsplit):
+    """ltra_diag (tra_advhoriz / tra_advvert, src/oce_adv_tra_driver.F90:221-229, :307-318, :464-488) and ldiag_DVD
+    (dvd_trflx_hor / dvd_trflx_ver, :263-296, :395-458): the C loops and the whole-array NumPy restatement agree bit
+    for bit, and switching the diagnostics on does not change the tendencies"""
+    from oracle import numpy_ref as R, oracle_py as O
+    g = pi_mesh
+    st, trs, nb, dt = make_case(g, 2, hor, ver, lim, ph=0.25, pv=0.75, use_wsplit=wsplit)
+    a = O.OracleRank(g, st, trs, nb)
+    O.run([a], dt)
+    b = O.OracleRank(g, st, trs, nb, tra_diag=True, dvd=True)
+    O.run([b], dt)
+    na = R.NumpyAdv(g, st, nb)
+    for k in range(2):
+        assert np.array_equal(a.dttf_h[k], b.dttf_h[k]) and np.array_equal(a.dttf_v[k], b.dttf_v[k])
+        d = {}
+        na.do_oce_adv_tra(dt, trs[k], np.zeros((g.Nh, g.L)), np.zeros((g.Nh, g.L)), diag=d)
+        for name in ("tra_advhoriz", "tra_advvert", "dvd_trflx_hor", "dvd_trflx_ver"):
+            x = getattr(b, name)[k]
+            assert np.isfinite(x).all() and np.abs(x).max() > 0 and np.array_equal(x, d[name]), (name, k)

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--tracers", type=int, default=2)
     ap.add_argument("--null-grad", action="store_true", help="edge_up_dn_grad = NULL: the library computes the gradients inside the step")
+    ap.add_argument("--tra-diag", action="store_true", help="ltra_diag = .true.: tra_advhoriz / tra_advvert are produced as well")
     ap.add_argument("variants", nargs="*")
     a = ap.parse_args()
     import torch
@@ -44,6 +45,7 @@ def main():
         trs += F.make_tracers_kind(g, k, dev, tri, hor="MFCT", ver="QR4C", lim="FCT")
     dh = [torch.zeros((g.Nh, g.L), dtype=torch.float64, device=dev) for _ in trs]
     dv = [torch.zeros((g.Nh, g.L), dtype=torch.float64, device=dev) for _ in trs]
+    dg = dict(tra_advhoriz=[torch.zeros_like(x) for x in dh], tra_advvert=[torch.zeros_like(x) for x in dv]) if a.tra_diag else {}
     knobs = set()
     for v in a.variants:
         for kv in v.split():
@@ -63,20 +65,20 @@ def main():
             for x in dh + dv:
                 x.zero_()
             ctx.set_state(st)
-            ctx.do_oce_adv_tra(dt, trs, dh, dv)             # one checked step from zero tendencies
+            ctx.do_oce_adv_tra(dt, trs, dh, dv, **dg)       # one checked step from zero tendencies
             h = hashlib.sha1()
             for x in dh + dv:
                 h.update(x.cpu().numpy().tobytes())
             for _ in range(3):
                 ctx.set_state(st)
-                ctx.do_oce_adv_tra(dt, trs, dh, dv, sync=False)
+                ctx.do_oce_adv_tra(dt, trs, dh, dv, sync=False, **dg)
             ctx.synchronize()
             ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record(ext)
             for _ in range(a.steps):
                 ctx.set_state(st)
-                ctx.do_oce_adv_tra(dt, trs, dh, dv, sync=False)
+                ctx.do_oce_adv_tra(dt, trs, dh, dv, sync=False, **dg)
             ev1.record(ext)
             ctx.synchronize()
             torch.cuda.synchronize()
@@ -86,7 +88,7 @@ def main():
             try:
                 for _ in range(5):
                     ctx.set_state(st)
-                    ctx.do_oce_adv_tra(dt, trs, dh, dv, sync=False)
+                    ctx.do_oce_adv_tra(dt, trs, dh, dv, sync=False, **dg)
                     ctx.synchronize()
                     ph += np.array(ctx.phase_ms()[:4])
                 ph /= 5
