@@ -267,6 +267,15 @@ def derive_geometry(m: Mesh, need_nod_in_elem_for_all: bool = True) -> Mesh:
     lev = np.arange(1, nl + 1)[None, :]
     valid = (lev >= m.ulevels_nod2D[:, None]) & (lev <= m.nlevels_nod2D[:, None] - 1)
     m.areasvol[valid] = area[valid]
+    if not (m.ulevels == 1).all():
+        # use_cavity (oce_mesh.F90:2299-2321): where a cavity element sits on the upper face of the scalar cell
+        # (some element around the node starts below layer nz) the "mid" area is the area of the LOWER face
+        contrib = np.zeros((Nh, nl), np.int64)
+        for nz in range(1, nl):
+            contrib[:, nz - 1] = np.bincount(flat_nodes, weights=np.repeat((m.ulevels - 1 >= nz).astype(np.float64), 3), minlength=Nh)
+        nzmax = (m.nlevels_nod2D.astype(np.int64) - 1)[:, None]
+        below = np.take_along_axis(area, np.clip(np.minimum(lev + 1, nzmax) - 1, 0, nl - 1) * np.ones((Nh, 1), np.int64), axis=1)
+        m.areasvol = np.where(valid & (contrib > 0), below, m.areasvol)
 
     # --- edge vectors: oce_mesh.F90:2559-2598 -------------------------------------------------
     ed = m.edges.astype(np.int64) - 1
@@ -360,10 +369,14 @@ def read_fesom_mesh(path: str, cyclic_length_deg: float = 360.0, cartesian: bool
     etri = np.loadtxt(p("edge_tri.out"), dtype=np.int64).astype(np.int32)
     etri[etri < 0] = 0                                      # oce_mesh.F90:1900
     N, T, E = coord.shape[0], elem.shape[0], edges.shape[0]
+    ulv_e, ulv_n = np.ones(T, np.int32), np.ones(N, np.int32)
+    if os.path.exists(p("cavity_elvls.out")):               # use_cavity: oce_mesh.F90:1139-1350
+        ulv_e = np.loadtxt(p("cavity_elvls.out"), dtype=np.int64).astype(np.int32)
+        ulv_n = np.loadtxt(p("cavity_nlvls.out"), dtype=np.int64).astype(np.int32)
     m = Mesh(nl=nl, myDim_nod2D=N, eDim_nod2D=0, myDim_elem2D=T, eDim_elem2D=0, myDim_edge2D=E,
              cyclic_length=cyclic_length_deg * RAD, cartesian=cartesian, coord_nod2D=coord,
              elem2D_nodes=elem, edges=edges, edge_tri=etri, nlevels=nlv_e,
-             ulevels=np.ones(T, np.int32), nlevels_nod2D=nlv_n, ulevels_nod2D=np.ones(N, np.int32),
+             ulevels=ulv_e, nlevels_nod2D=nlv_n, ulevels_nod2D=ulv_n,
              zbar=zbar)
     m.myList_nod2D = np.arange(1, N + 1, dtype=np.int32)
     m.myList_elem2D = np.arange(1, T + 1, dtype=np.int32)
@@ -749,8 +762,10 @@ def load_npz_mesh(path: str) -> Mesh:
              cyclic_length=float(z["cyclic_length_deg"]) * RAD, cartesian=False, coord_nod2D=coord,
              elem2D_nodes=z["elem2D_nodes"].astype(np.int32), edges=z["edges"].astype(np.int32),
              edge_tri=z["edge_tri"].astype(np.int32), nlevels=z["nlevels"].astype(np.int32),
-             ulevels=np.ones(T, np.int32), nlevels_nod2D=z["nlevels_nod2D"].astype(np.int32),
-             ulevels_nod2D=np.ones(N, np.int32), zbar=z["zbar"].astype(np.float64))
+             ulevels=z["ulevels"].astype(np.int32) if "ulevels" in z.files else np.ones(T, np.int32),
+             nlevels_nod2D=z["nlevels_nod2D"].astype(np.int32),
+             ulevels_nod2D=z["ulevels_nod2D"].astype(np.int32) if "ulevels_nod2D" in z.files else np.ones(N, np.int32),
+             zbar=z["zbar"].astype(np.float64))
     m.myList_nod2D = np.arange(1, N + 1, dtype=np.int32)
     m.myList_elem2D = np.arange(1, T + 1, dtype=np.int32)
     m.myList_edge2D = np.arange(1, E + 1, dtype=np.int32)

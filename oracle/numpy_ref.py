@@ -462,7 +462,9 @@ def fill_up_dn_grad(mesh, tr_xy, edge_up_dn_tri):
     up, dn = np.maximum(tri[:, 0] - 1, 0), np.maximum(tri[:, 1] - 1, 0)
     for node, t_el, cx, cy in ((n1, up, 0, 2), (n2, dn, 1, 3)):
         col = (lev >= uln[node][:, None]) & (lev <= nln[node][:, None] - 1)
-        mean = col & (~both | (lev <= nzmin - 1) | (lev >= nzmax))
+        # :388-430 run from ulevels_nod2D(node) to nzmin-1, but :445-485 start at nzmax WITHOUT the node's upper bound: under
+        # a cavity (nzmax < ulevels_nod2D(node)) the reference divides 0/0 there and stores the NaN (nobody reads it)
+        mean = np.where(both, (col & (lev <= nzmin - 1)) | ((lev >= nzmax) & (lev <= nln[node][:, None] - 1)), col)
         out[:, :, cx] = np.where(shared, tr[t_el, :, 0], np.where(mean, gx[node], 0.0))
         out[:, :, cy] = np.where(shared, tr[t_el, :, 1], np.where(mean, gy[node], 0.0))
     return out

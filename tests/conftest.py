@@ -21,6 +21,13 @@ def pi_mesh():
 
 
 @pytest.fixture(scope="session")
+def cav_mesh():
+    """the reference's test/meshes/pi_cavity: 170 elements / 95 nodes start below layer 1 (use_cavity)"""
+    from fesom2_b200 import mesh as M
+    return M.load_npz_mesh(os.path.join(GOLDEN, "mesh_pi_cavity.npz"))
+
+
+@pytest.fixture(scope="session")
 def souf_mesh():
     from fesom2_b200 import mesh as M
     return M.load_npz_mesh(os.path.join(GOLDEN, "mesh_soufflet.npz"))

@@ -295,3 +295,89 @@ def test_diagnostics_two_restatements(pi_mesh, hor, ver, lim, wsplit):
         for name in ("tra_advhoriz", "tra_advvert", "dvd_trflx_hor", "dvd_trflx_ver"):
             x = getattr(b, name)[k]
             assert np.isfinite(x).all() and np.abs(x).max() > 0 and np.array_equal(x, d[name]), (name, k)
+
+
+@pytest.mark.parametrize("hor,ver,lim,wsplit", [("MFCT", "QR4C", "FCT", False), ("MUSCL", "PPM", "FCT", True),
+                                                ("MFCT", "QR4C", "NON", False), ("UPW1", "UPW1", "FCT", False),
+                                                ("MUSCL", "CDIFF", "FCT", False)])
+def test_cavity_mesh_two_restatements(cav_mesh, hor, ver, lim, wsplit):
+    """the reference's cavity mesh (test/meshes/pi_cavity, use_cavity): nzmin > 1 in the vertical stencils, one-sided edge
+    ranges A / B, padded FCT clusters, areasvol = lower face under the ice -- C loops vs whole-array NumPy, bit for bit,
+    tendencies and all four diagnostics"""
+    from oracle import numpy_ref as R, oracle_py as O
+    g = cav_mesh
+    assert (g.ulevels > 1).sum() == 170 and (g.ulevels_nod2D > 1).sum() == 95
+    under = (np.arange(1, g.nl + 1)[None, :] < np.asarray(g.ulevels_nod2D_max)[:, None]) & (g.areasvol > 0)
+    assert under.any() and (g.areasvol[under] != g.area[under]).any()      # the lower-face rule is in effect
+    st, trs, nb, dt = make_case(g, 2, hor, ver, lim, ph=0.25, pv=0.75, use_wsplit=wsplit)
+    b = O.OracleRank(g, st, trs, nb, tra_diag=True, dvd=True)
+    O.run([b], dt)
+    na = R.NumpyAdv(g, st, nb)
+    cav = np.asarray(g.ulevels_nod2D) > 1
+    for k in range(2):
+        d = {}
+        dh, dv = np.zeros((g.Nh, g.L)), np.zeros((g.Nh, g.L))
+        with np.errstate(invalid="ignore"):
+            na.do_oce_adv_tra(dt, trs[k], dh, dv, diag=d)
+        assert np.isfinite(dh).all() and np.isfinite(dv).all() and np.abs(dh[cav]).max() > 0
+        assert np.array_equal(dh, b.dttf_h[k]) and np.array_equal(dv, b.dttf_v[k])
+        for name in ("tra_advhoriz", "tra_advvert", "dvd_trflx_hor", "dvd_trflx_ver"):
+            assert np.array_equal(getattr(b, name)[k], d[name]), (name, k)
+
+
+def test_cavity_mesh_1rank_vs_2ranks(cav_mesh):
+    """the reference's dist_2 partition of pi_cavity: owned nodes identical on 1 and 2 ranks (three dwarf iterations)"""
+    from oracle import oracle_py as O
+    g = cav_mesh
+    st, trs, nbg, dt = make_case(g, 2, "MFCT", "QR4C", "FCT")
+    one = O.OracleRank(g, st, trs, nbg)
+    O.run([one], dt, 3, 1)
+    ranks = []
+    for r in range(2):
+        loc = M.localize(g, g.parts[2], r)
+        lst, ltr = F.scatter_to_local(g, loc, st, trs)
+        ranks.append(O.OracleRank(loc, lst, ltr, nbg[loc.myList_nod2D - 1]))
+    O.run(ranks, dt, 3, 1)
+    for rk in ranks:
+        loc = rk.mesh_py
+        own, alln = loc.myList_nod2D[:loc.N] - 1, loc.myList_nod2D - 1
+        for k in range(2):
+            assert np.array_equal(rk.dttf_v[k][:loc.N], one.dttf_v[k][own])
+            assert np.array_equal(rk.dttf_h[k][:loc.N], one.dttf_h[k][own])
+            assert np.array_equal(rk.values[k], one.values[k][alln])
+
+
+def test_cavity_mesh_side_rows_two_restatements(cav_mesh):
+    """rows f-1 and f-3 on the cavity mesh: tracer_gradient_elements, fill_up_dn_grad, the continuity part of
+    vert_vel_ale, compute_CFLz / compute_Wvel_split and the zstar / zlevel corrections (which skip the cavity columns,
+    src/oce_ale.F90:2354, :2550) -- C loops vs whole-array NumPy, bit for bit"""
+    from common import zlevel_case
+    from oracle import numpy_ref as R, oracle_py as O
+    g = cav_mesh
+    st, trs, nb, dt = make_case(g, 1)
+    v = trs[0].values.numpy()
+    tri = F.find_up_downwind_triangles(g)
+    assert np.array_equal(tri, O.find_up_downwind_triangles(g))
+    a, b = O.tracer_gradient_elements(g, v), R.tracer_gradient_elements(g, v)
+    assert np.array_equal(a[:g.T], b)
+    ga, gb = O.fill_up_dn_grad(g, a, tri), R.fill_up_dn_grad(g, b, tri)
+    # under the ice the reference's last two loops (src/oce_muscl_adv.F90:445-485) start at nzmax, above the node's own top:
+    # 0/0 there, a NaN nobody reads -- both restatements keep it
+    assert np.isnan(ga).sum() == 4 and np.array_equal(np.isnan(ga), np.isnan(gb)) and np.array_equal(np.nan_to_num(ga), np.nan_to_num(gb))
+    hbar, hbar_old, wflux, cfl_old = zlevel_case(g, st, 4, 0.5)
+    rk = O.OracleRank(g, st, trs, nb)
+    W = O.vert_vel_ale_core(rk)
+    assert np.isfinite(W).all() and np.array_equal(W, R.vert_vel_ale_core(g, st.uv.numpy(), st.helem.numpy()))
+    dtc = 40.0 * dt
+    for x, y in zip(O.compute_cflz_and_split(rk, dtc, W, True, 0.5), R.compute_cflz_and_split(g, st.hnode_new.numpy(), dtc, W, True, 0.5)):
+        assert np.isfinite(x).all() and np.array_equal(x, y)
+    za = O.vert_vel_ale_zstar(rk, dtc, W, hbar, hbar_old, wflux)
+    zb = R.vert_vel_ale_zstar(g, st.zbar_3d_n.numpy(), st.hnode.numpy(), st.hnode_new.numpy(), dtc, W, hbar, hbar_old, wflux)
+    la = O.vert_vel_ale_zlevel(rk, dtc, W, hbar, hbar_old, wflux, g.zbar, cfl_old, 0.5, 4)
+    lb = R.vert_vel_ale_zlevel(g, g.zbar, st.hnode.numpy(), st.hnode_new.numpy(), cfl_old, dtc, W, hbar, hbar_old, wflux, 0.5, 4)
+    cav = np.asarray(g.ulevels_nod2D)[:g.N] > 1
+    for (x, y) in (za, zb), (la, lb):
+        for p, q in zip(x, y):
+            assert np.isfinite(p).all() and np.array_equal(p, q)
+        assert np.array_equal(x[0][:g.N][cav], W[:g.N][cav]) and np.array_equal(x[1][:g.N][cav], st.hnode_new.numpy()[:g.N][cav])
+        assert not np.array_equal(x[0], W)
