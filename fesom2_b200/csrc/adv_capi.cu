@@ -110,7 +110,7 @@ struct DevBuf {
 };
 
 struct Slot {  // per-tracer staging: host pointers, unaligned device pointers, library-computed gradients
-    DevBuf<double> ttf, ttfAB, grad, dh, dv, tr_xy, gmean, dgh, dgv;
+    DevBuf<double> ttf, ttfAB, grad, dh, dv, tr_xy, gmean, dgh, dgv, dvdh, dvdv;
 };
 
 // work arrays of one chunk of <= 2 tracers (t_tracer_work, allocated by oce_adv_tra_fct_init in the
@@ -660,6 +660,7 @@ struct TrPtrs {   // device pointers of the call's tracers
     std::vector<const double*> ttf, ttfAB, grad, txy, gmean;   // grad == nullptr && txy != nullptr: fused gradients
     std::vector<double*> dh, dv;
     std::vector<double*> dgh, dgv;                             // ltra_diag outputs (nullptr = off)
+    std::vector<double*> dvdh, dvdv;                           // ldiag_DVD outputs (nullptr = off)
 };
 
 template <int TB>
@@ -1026,6 +1027,22 @@ static int run_batch(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr
             for (auto& ch : chunks) if (ch.fct) run(PH_K3, ch, rAll);
         }
     } else { mark(2); mark(3); }
+    // ---- ldiag_DVD (driver :263-296, :395-458): two optional sweeps over the edges / the owned nodes of the chunks that asked
+    for (auto& ch : chunks) {
+        bool any = false;
+        for (int t = 0; t < ch.tb; ++t) any = any || p.dvdh[ch.idx[t]] || p.dvdv[ch.idx[t]];
+        if (!any) continue;
+        const NodeRange rn = node_range(c, rAll, cpb);
+        auto go = [&](auto chunk) {
+            constexpr int TBc = sizeof(chunk.ttf) / sizeof(chunk.ttf[0]);
+            DvdPtrs<TBc> d;
+            for (int t = 0; t < TBc; ++t) { d.hor[t] = p.dvdh[ch.idx[t]]; d.ver[t] = p.dvdv[ch.idx[t]]; }
+            k_dvd_hor<TBc><<<nblocks(m.E, cpb), cpb * m.L, 0, sc>>>(m, chunk, d, cpb, ch.fct);
+            k_dvd_ver<TBc><<<nblocks(rn.count, rn.cpb), rn.cpb * m.L, 0, sc>>>(m, chunk, d, rn, ch.fct);
+            c->launches += 2;
+        };
+        if (ch.tb == 2) go(make_chunk<2>(c, p, tr, ch)); else go(make_chunk<1>(c, p, tr, ch));
+    }
     mark(4);
     c->ph_valid = prof;
     if (launch_rc) { cudaGetLastError(); return fail(launch_rc, launch_msg); }
@@ -1043,7 +1060,7 @@ static int do_adv(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr, i
     const size_t nLN = (size_t)m.L * m.Nh, nLE = (size_t)m.L * m.E;
     TrPtrs p;
     p.ttf.resize(ntr); p.ttfAB.resize(ntr); p.grad.resize(ntr); p.txy.assign(ntr, nullptr); p.gmean.assign(ntr, nullptr); p.dh.resize(ntr); p.dv.resize(ntr);
-    p.dgh.assign(ntr, nullptr); p.dgv.assign(ntr, nullptr);
+    p.dgh.assign(ntr, nullptr); p.dgv.assign(ntr, nullptr); p.dvdh.assign(ntr, nullptr); p.dvdv.assign(ntr, nullptr);
     for (int i = 0; i < ntr; ++i) {
         if (!tr[i].values || !tr[i].valuesAB || !tr[i].del_ttf_advhoriz || !tr[i].del_ttf_advvert)
             return fail(ADV_EINVAL, "tracer " + std::to_string(i + 1) + ": null field");
@@ -1051,6 +1068,7 @@ static int do_adv(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr, i
             p.ttf[i] = tr[i].values; p.ttfAB[i] = tr[i].valuesAB; p.grad[i] = tr[i].edge_up_dn_grad;
             p.dh[i] = tr[i].del_ttf_advhoriz; p.dv[i] = tr[i].del_ttf_advvert;
             p.dgh[i] = tr[i].tra_advhoriz; p.dgv[i] = tr[i].tra_advvert;
+            p.dvdh[i] = tr[i].dvd_trflx_hor; p.dvdv[i] = tr[i].dvd_trflx_ver;
             if (tr[i].edge_up_dn_grad && ((uintptr_t)tr[i].edge_up_dn_grad & 15u)) {
                 // edge_up_dn_grad(1:4,nz,e) is read as 16-byte words / bulk copies: stage an aligned copy
                 Slot& s = c->slots[i];
@@ -1084,6 +1102,12 @@ static int do_adv(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr, i
                 if (sd[k]->n != nLN) CU(sd[k]->alloc(nLN, false));
                 CU(cudaMemcpyAsync(sd[k]->p, hd[k], nLN * 8, cudaMemcpyHostToDevice, c->s_comp));
                 (k == 0 ? p.dgh[i] : p.dgv[i]) = sd[k]->p;
+            }
+            // ldiag_DVD arrays: every entry is written by the library, so they are only copied back
+            if (tr[i].dvd_trflx_hor) { host_register(c, tr[i].dvd_trflx_hor, nLE * 8); if (s.dvdh.n != nLE) CU(s.dvdh.alloc(nLE, false)); p.dvdh[i] = s.dvdh.p; }
+            if (tr[i].dvd_trflx_ver) {
+                const size_t nNN = (size_t)m.nl * m.N;
+                host_register(c, tr[i].dvd_trflx_ver, nNN * 8); if (s.dvdv.n != nNN) CU(s.dvdv.alloc(nNN, false)); p.dvdv[i] = s.dvdv.p;
             }
         }
     }
@@ -1159,6 +1183,8 @@ static int do_adv(adv_ctx* c, double dt, int ntr, const adv_tracer_desc_t* tr, i
             CU(cudaMemcpyAsync(tr[i].del_ttf_advvert, p.dv[i], nLN * 8, cudaMemcpyDeviceToHost, c->s_comp));
             if (tr[i].tra_advhoriz) CU(cudaMemcpyAsync(tr[i].tra_advhoriz, p.dgh[i], nLN * 8, cudaMemcpyDeviceToHost, c->s_comp));
             if (tr[i].tra_advvert) CU(cudaMemcpyAsync(tr[i].tra_advvert, p.dgv[i], nLN * 8, cudaMemcpyDeviceToHost, c->s_comp));
+            if (tr[i].dvd_trflx_hor) CU(cudaMemcpyAsync(tr[i].dvd_trflx_hor, p.dvdh[i], nLE * 8, cudaMemcpyDeviceToHost, c->s_comp));
+            if (tr[i].dvd_trflx_ver) CU(cudaMemcpyAsync(tr[i].dvd_trflx_ver, p.dvdv[i], (size_t)m.nl * m.N * 8, cudaMemcpyDeviceToHost, c->s_comp));
         }
     }
     if (blocking) CU(cudaStreamSynchronize(c->s_comp));

@@ -1582,6 +1582,100 @@ __global__ void __launch_bounds__(kBlock) k_nofct_update(MeshDev m, Chunk<TB> b,
 }
 
 // ----------------------------------------------------------------------------------------------
+// ldiag_DVD (oce_adv_tra_driver.F90:263-296, :395-458): the total tracer fluxes through the mid-edge faces and through the
+// upper / lower faces of the scalar cells, for the discrete-variance-decay diagnostic.  With FCT the reference stores the
+// low-order flux first and adds the LIMITED antidiffusive flux at the end; neither is materialised by the four passes
+// (the low-order flux is recomputed from Q, the limiter is applied on the fly), so two optional sweeps rebuild them from
+// what is at hand after the last pass: Q, ttf, the unlimited antidiffusive fluxes and R+/R- (owned and halo nodes).
+// Without FCT the stored high-order fluxes are the answer.  Every entry of the outputs is written (zeros outside the
+// wet range, like the reference's zeroed flux arrays); the layers a boundary edge has above a cavity top, where the
+// reference keeps fluxes of cells nobody uses, are written as zero.
+// ----------------------------------------------------------------------------------------------
+template <int TB> struct DvdPtrs { double* hor[TB]; double* ver[TB]; };
+
+template <int TB>
+__global__ void __launch_bounds__(kBlock) k_dvd_hor(MeshDev m, Chunk<TB> b, DvdPtrs<TB> d, int epb, int fct)
+{
+    const ColThread c = col_thread(m);
+    const int L = m.L;
+    const int e = blockIdx.x * epb + c.g;
+    if (e >= m.E) return;
+    const int nz0 = c.nz0, nz = nz0 + 1;
+    const int4 em = __ldg(&m.edge_meta[e]);
+    const uchar4 lv = __ldg(&m.edge_lev[e]);
+    const int lo = lv.z > 0 ? min((int)lv.x, (int)lv.z) : (int)lv.x;      // scatter range, oce_adv_tra_driver.F90:154-156
+    const int hi = max((int)lv.y, (int)lv.w);
+    const size_t oe = (size_t)e * L + nz0;
+    double out[TB];
+#pragma unroll
+    for (int t = 0; t < TB; ++t) out[t] = 0.0;
+    if (nz >= lo && nz <= hi) {
+        double f[TB];
+        ldv<TB>(b.adf_h + oe * TB, f);
+        if (fct) {
+            const size_t o1 = (size_t)em.x * L + nz0, o2 = (size_t)em.y * L + nz0;
+            const double q = __ldg(&m.Q[oe]), aq = fabs(q), qp = q + aq, qm = q - aq;
+            double p1[TB], m1[TB], p2[TB], m2[TB];
+            ldpm<TB>(b.pm + o1 * TB * 2, p1, m1);
+            ldpm<TB>(b.pm + o2 * TB * 2, p2, m2);
+#pragma unroll
+            for (int t = 0; t < TB; ++t) {
+                const double flo = hor_lo(__ldg(&b.ttf[t][o1]), __ldg(&b.ttf[t][o2]), qp, qm);   // driver :115, :273
+                double ae = 1.0;                                                                 // fct :489-494
+                if (f[t] >= 0.0) { ae = dmin(ae, p1[t]); ae = dmin(ae, m2[t]); }
+                else { ae = dmin(ae, m1[t]); ae = dmin(ae, p2[t]); }
+                out[t] = flo + ae * f[t];                                                        // driver :404
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < TB; ++t) out[t] = f[t];                                          // driver :437
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < TB; ++t) if (d.hor[t]) d.hor[t][oe] = out[t];
+}
+
+template <int TB>
+__global__ void __launch_bounds__(kBlock) k_dvd_ver(MeshDev m, Chunk<TB> b, DvdPtrs<TB> d, NodeRange r, int fct)
+{
+    const NodeThread th = node_thread(m, r);
+    if (!th.active) return;
+    const int L = m.L, nl = m.nl, n = th.n, nzmin = th.nzmin, nzmax = th.nzmax;
+    const size_t cN = (size_t)n * nl;
+    ColV c;
+    c.w = m.we + cN; c.area = m.area + cN; c.nzmin = nzmin; c.nzmax = nzmax; c.dt = 0.0; c.num_ord = 0.0;
+    c.Z = nullptr; c.zbar = nullptr; c.hnode = nullptr; c.hnode_new = nullptr;
+    // thread nz0 owns interface nz0 + 1; the thread of the last layer also owns interface nl
+    for (int k = th.nz0 + 1; k <= (th.nz0 == L - 1 ? nl : th.nz0 + 1); ++k) {
+        double out[TB];
+#pragma unroll
+        for (int t = 0; t < TB; ++t) out[t] = 0.0;
+        if (k >= nzmin && k <= nzmax) {
+            double f[TB];
+            ldv<TB>(b.adf_v + (cN + k - 1) * TB, f);
+            if (fct) {
+                double pa[TB], ma[TB], pk[TB], mk[TB];
+#pragma unroll
+                for (int t = 0; t < TB; ++t) { pa[t] = ma[t] = pk[t] = mk[t] = 1.0; }
+                if (k - 1 >= nzmin) ldpm<TB>(b.pm + ((size_t)n * L + k - 2) * TB * 2, pa, ma);      // R+/R- of layer k-1
+                if (k <= nzmax - 1) ldpm<TB>(b.pm + ((size_t)n * L + k - 1) * TB * 2, pk, mk);      // of layer k
+#pragma unroll
+                for (int t = 0; t < TB; ++t) {
+                    c.ttf = b.ttf[t] + (size_t)n * L;
+                    const double flo = ver_upw1(c, k, 0.0);                                          // driver :235, :288
+                    out[t] = flo + limit_v(f[t], k, nzmin, nzmax, pa[t], ma[t], pk[t], mk[t]);       // driver :418
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < TB; ++t) out[t] = f[t];                                          // driver :449
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < TB; ++t) if (d.ver[t]) d.ver[t][cN + k - 1] = out[t];
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
 // halo pack (replaces the MPI_TYPE_INDEXED send types, gen_modules_partitioning.F90:462-473):
 // one CTA per send column, out[i*nlev + k] = field[slist[i]*nlev + k]
 // ----------------------------------------------------------------------------------------------

@@ -58,7 +58,7 @@ class TracerDesc(C.Structure):
                 ("del_ttf_advhoriz", c_dp), ("del_ttf_advvert", c_dp),
                 ("tra_adv_hor", C.c_char_p), ("tra_adv_ver", C.c_char_p), ("tra_adv_lim", C.c_char_p),
                 ("tra_adv_ph", C.c_double), ("tra_adv_pv", C.c_double),
-                ("tra_advhoriz", c_dp), ("tra_advvert", c_dp)]
+                ("tra_advhoriz", c_dp), ("tra_advvert", c_dp), ("dvd_trflx_hor", c_dp), ("dvd_trflx_ver", c_dp)]
 
 
 class ZstarDesc(C.Structure):
@@ -263,7 +263,7 @@ class AdvB200:
         else:
             _check(self.lib.adv_ctx_set_state_step(self.h, C.byref(sd), _where(st.uv), int(step)))
 
-    def _descs(self, tracers, dttf_h, dttf_v, tra_advhoriz=None, tra_advvert=None):
+    def _descs(self, tracers, dttf_h, dttf_v, tra_advhoriz=None, tra_advvert=None, dvd_trflx_hor=None, dvd_trflx_ver=None):
         n = len(tracers)
         arr = (TracerDesc * n)()
         keep = []
@@ -275,16 +275,20 @@ class AdvB200:
                                 tra_adv_hor=hs, tra_adv_ver=vs, tra_adv_lim=ls,
                                 tra_adv_ph=float(t.tra_adv_ph), tra_adv_pv=float(t.tra_adv_pv),
                                 tra_advhoriz=_ptr(tra_advhoriz[i]) if tra_advhoriz else c_dp(),
-                                tra_advvert=_ptr(tra_advvert[i]) if tra_advvert else c_dp())
+                                tra_advvert=_ptr(tra_advvert[i]) if tra_advvert else c_dp(),
+                                dvd_trflx_hor=_ptr(dvd_trflx_hor[i]) if dvd_trflx_hor else c_dp(),
+                                dvd_trflx_ver=_ptr(dvd_trflx_ver[i]) if dvd_trflx_ver else c_dp())
         return arr, keep
 
     def do_oce_adv_tra(self, dt: float, tracers: Sequence, dttf_h: Sequence, dttf_v: Sequence, sync: bool = True,
-                       tra_advhoriz: Optional[Sequence] = None, tra_advvert: Optional[Sequence] = None):
+                       tra_advhoriz: Optional[Sequence] = None, tra_advvert: Optional[Sequence] = None,
+                       dvd_trflx_hor: Optional[Sequence] = None, dvd_trflx_ver: Optional[Sequence] = None):
         """Batched ``do_oce_adv_tra``.  Tensors on cuda are used in place; cpu tensors / numpy arrays
         are copied to the device and the tendencies copied back (blocking).  ``tra_advhoriz`` / ``tra_advvert``: per-tracer
         (Nh, L) arrays (entries may be None) that receive the ltra_diag diagnostics of the reference
-        (src/oce_adv_tra_driver.F90:221-229, :307-318, :464-488)."""
-        arr, keep = self._descs(tracers, dttf_h, dttf_v, tra_advhoriz, tra_advvert)
+        (src/oce_adv_tra_driver.F90:221-229, :307-318, :464-488); ``dvd_trflx_hor`` (E, L) / ``dvd_trflx_ver`` (N, nl) the
+        ldiag_DVD fluxes (:263-296, :395-458)."""
+        arr, keep = self._descs(tracers, dttf_h, dttf_v, tra_advhoriz, tra_advvert, dvd_trflx_hor, dvd_trflx_ver)
         where = _where(tracers[0].values)
         if where == ADV_DEVICE:
             self._after_torch()

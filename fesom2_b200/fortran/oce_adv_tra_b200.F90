@@ -80,6 +80,7 @@ module oce_adv_tra_b200
      type(c_ptr) :: tra_adv_hor, tra_adv_ver, tra_adv_lim
      real(c_double) :: tra_adv_ph, tra_adv_pv
      type(c_ptr) :: tra_advhoriz, tra_advvert
+     type(c_ptr) :: dvd_trflx_hor, dvd_trflx_ver
   end type adv_tracer_desc_t
 
   ! adv_gradient_mesh_desc_t
@@ -349,6 +350,7 @@ contains
     use MOD_PARSUP
     use MOD_DYN
     use o_PARAM, only: mstep
+    use diagnostics, only: ldiag_DVD
 #ifdef ENABLE_OPENACC
     use openacc
 #endif
@@ -416,6 +418,12 @@ contains
        if (tracers%data(i)%ltra_diag) then
           dgh1 => tracers%work%tra_advhoriz(:,:,i); dgv1 => tracers%work%tra_advvert(:,:,i)
           td(k)%tra_advhoriz = ADV_ADDR(dgh1); td(k)%tra_advvert = ADV_ADDR(dgv1)
+       end if
+       ! ldiag_DVD: temperature and salinity only (src/oce_adv_tra_driver.F90:263, :395)
+       td(k)%dvd_trflx_hor = c_null_ptr; td(k)%dvd_trflx_ver = c_null_ptr
+       if (ldiag_DVD .and. i <= 2) then
+          dgh1 => tracers%work%dvd_trflx_hor(:,:,i); dgv1 => tracers%work%dvd_trflx_ver(:,:,i)
+          td(k)%dvd_trflx_hor = ADV_ADDR(dgh1); td(k)%dvd_trflx_ver = ADV_ADDR(dgv1)
        end if
     end do
 #ifdef ENABLE_OPENACC

@@ -102,6 +102,13 @@ typedef struct {
      * low-order tendency plus (del_ttf_advhoriz | del_ttf_advvert after the call) / hnode_new, otherwise that quotient alone; everything else
      * (halo nodes, where the reference stores partial edge sums nobody reads, and dry layers) is left untouched. */
     double *tra_advhoriz, *tra_advvert;
+    /* ldiag_DVD (src/gen_modules_diag.F90:101, default .false.; the reference does it for tr_num <= 2 only): the tracer's
+     * slices of tracers%work%dvd_trflx_hor (nl-1, myDim_edge2D) and dvd_trflx_ver (nl, myDim_nod2D), or NULL.  On return
+     * they hold the total flux through every mid-edge face / scalar-cell face: with FCT the low-order flux plus the limited
+     * antidiffusive flux, otherwise the high-order flux (src/oce_adv_tra_driver.F90:263-296, :395-458).  Every entry is
+     * written; the layers a boundary edge has above a cavity top are written as zero (the reference keeps fluxes of
+     * cells it never uses there). */
+    double *dvd_trflx_hor, *dvd_trflx_ver;
 } adv_tracer_desc_t;
 
 /* --- life cycle ------------------------------------------------------------------------------ */

@@ -28,6 +28,13 @@ def cav_mesh():
 
 
 @pytest.fixture(scope="session")
+def nw2_mesh():
+    """the reference's test/meshes/neverworld2: a 60-degree periodic sector, 8578 nodes, 15 layers (many short columns per CTA)"""
+    from fesom2_b200 import mesh as M
+    return M.load_npz_mesh(os.path.join(GOLDEN, "mesh_neverworld2.npz"))
+
+
+@pytest.fixture(scope="session")
 def souf_mesh():
     from fesom2_b200 import mesh as M
     return M.load_npz_mesh(os.path.join(GOLDEN, "mesh_soufflet.npz"))

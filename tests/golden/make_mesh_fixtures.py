@@ -1,4 +1,4 @@
-"""Convert the reference's ASCII test meshes (test/meshes/pi, test/meshes/soufflet, test/meshes/pi_cavity, with their
+"""Convert the reference's ASCII test meshes (test/meshes/pi, test/meshes/soufflet, test/meshes/pi_cavity, test/meshes/neverworld2, with their
 checked-in dist_2 / dist_8 partitions) into compact .npz fixtures, so that the GPU box -- which
 has no /root/reference -- can run the config-1/2 parity tests.  Run here:
 
@@ -18,7 +18,8 @@ from fesom2_b200 import mesh as M  # noqa: E402
 REF = "/root/reference/test/meshes"
 OUT = os.path.dirname(os.path.abspath(__file__))
 
-for name, cyc, dists in (("pi", 360.0, (2, 8)), ("soufflet", 4.5, (2, 8)), ("pi_cavity", 360.0, (2,))):
+for name, cyc, dists in (("pi", 360.0, (2, 8)), ("soufflet", 4.5, (2, 8)), ("pi_cavity", 360.0, (2,)),
+                         ("neverworld2", 60.0, (2, 8))):      # setups/test_neverworld2/setup.yml:23 cyclic_length: 60.0
     g = M.read_fesom_mesh(os.path.join(REF, name), cyclic_length_deg=cyc)
     parts = {f"part{n}": M.read_dist(os.path.join(REF, name), n)["part"].astype(np.int8) for n in dists}
     extra = {}

@@ -1,6 +1,7 @@
 """-m gpu: the optional diagnostics of do_oce_adv_tra -- tracers%data(tr_num)%ltra_diag (the reference's default,
 src/MOD_TRACER.F90:25): tra_advhoriz / tra_advvert (src/oce_adv_tra_driver.F90:221-229, :307-318, :464-488) -- through
-the C ABI against the C restatement, bit for bit on the wet layers of the owned nodes; everything else untouched."""
+the C ABI against the C restatement, bit for bit on the wet layers of the owned nodes; everything else untouched.
+And ldiag_DVD: dvd_trflx_hor / dvd_trflx_ver (:263-296, :395-458), every entry."""
 import numpy as np
 import pytest
 import torch
@@ -86,3 +87,51 @@ def test_ltra_diag_on_two_local_ranks(pi_mesh, lim):
             for got, ref in ((r["tah"][k], rk.tra_advhoriz[k]), (r["tav"][k], rk.tra_advvert[k])):
                 assert np.array_equal(got[:n][wet], ref[own][wet])
                 assert (got[:n][~wet] == FILL).all() and (got[n:] == FILL).all()
+
+
+def _scatter_range(g):
+    """(E, L) mask of the layers an edge's flux is scattered on (oce_adv_tra_driver.F90:154-156)"""
+    lev = np.arange(1, g.L + 1)[None, :]
+    el1 = g.edge_tri[:, 0].astype(np.int64) - 1
+    has2 = g.edge_tri[:, 1] > 0
+    el2 = np.where(has2, g.edge_tri[:, 1].astype(np.int64) - 1, 0)
+    nu1, nl1 = g.ulevels[el1][:, None], (g.nlevels[el1] - 1)[:, None]
+    nu2 = np.where(has2, g.ulevels[el2], 0)[:, None]
+    nl2 = np.where(has2, g.nlevels[el2] - 1, 0)[:, None]
+    lo = np.where(nu2 > 0, np.minimum(nu1, nu2), nu1)
+    return (lev >= lo) & (lev <= np.maximum(nl1, nl2))
+
+
+@pytest.mark.parametrize("which", ["pi", "cavity"])
+@pytest.mark.parametrize("hor,ver,lim,wsplit", [("MFCT", "QR4C", "FCT", False), ("MUSCL", "PPM", "FCT", True), ("MFCT", "QR4C", "NON", False)])
+@pytest.mark.parametrize("host", [False, True])
+def test_ldiag_dvd_matches_the_oracle(pi_mesh, cav_mesh, which, hor, ver, lim, wsplit, host):
+    """three tracers, the last one without DVD arrays (the reference does it for temperature and salinity only)"""
+    from oracle import oracle_py as O
+    from fesom2_b200.driver import AdvB200
+    g = {"pi": pi_mesh, "cavity": cav_mesh}[which]
+    st, trs, nb, dt = make_case(g, 3, hor, ver, lim, ph=0.25, pv=0.75, use_wsplit=wsplit)
+    rk = O.OracleRank(g, st, trs, nb, dvd=True)
+    O.run([rk], dt)
+    dev = "cpu" if host else torch.device("cuda:0")
+    ctx = AdvB200(g, nb, device=0, max_tracers=3)
+    st_d, trs_d = (st, trs) if host else to_device(st, trs, dev)
+    z = lambda shape, v=0.0: [torch.full(shape, v, dtype=torch.float64, device=dev) for _ in trs]   # noqa: E731
+    dh, dv = z((g.Nh, g.L)), z((g.Nh, g.L))
+    fh, fv = z((g.E, g.L), FILL), z((g.N, g.nl), FILL)
+    fh[2] = None
+    fv[2] = None
+    ctx.set_state(st_d)
+    ctx.do_oce_adv_tra(dt, trs_d, dh, dv, dvd_trflx_hor=fh, dvd_trflx_ver=fv)
+    scat = _scatter_range(g)
+    for k in range(2):
+        assert np.array_equal(dh[k].cpu().numpy(), rk.dttf_h[k]) and np.array_equal(dv[k].cpu().numpy(), rk.dttf_v[k])
+        gh, gv = fh[k].cpu().numpy(), fv[k].cpu().numpy()
+        assert np.isfinite(gh).all() and np.isfinite(gv).all()
+        assert np.array_equal(gh[scat], rk.dvd_trflx_hor[k][scat]), np.abs(gh[scat] - rk.dvd_trflx_hor[k][scat]).max()
+        assert (gh[~scat] == 0.0).all()            # incl. the layers of boundary edges above a cavity top (header)
+        if which == "pi":
+            assert np.array_equal(gh, rk.dvd_trflx_hor[k])
+        assert np.array_equal(gv, rk.dvd_trflx_ver[k]), np.abs(gv - rk.dvd_trflx_ver[k]).max()
+        assert np.abs(gh).max() > 0 and np.abs(gv).max() > 0
+    ctx.close()

@@ -42,7 +42,7 @@ def _check_owned(res, one, ntr=2):
 
 
 # ------------------------------------------------------------------------------- in-process ranks (any GPU count)
-@pytest.mark.parametrize("mesh_name,world", [("pi", 2), ("synth", 2), ("pi", 8), ("soufflet", 8), ("synth", 5)])
+@pytest.mark.parametrize("mesh_name,world", [("pi", 2), ("synth", 2), ("pi", 8), ("soufflet", 8), ("synth", 5), ("neverworld2", 8), ("pi_cavity", 2)])
 def test_local_ranks_match_single_rank_oracle(mesh_name, world):
     import mgpu_worker
     from local_ranks import run_local_ranks

@@ -62,6 +62,18 @@ def test_config2_soufflet_mfct_qr4c_fct(souf_mesh):
     ctx.close()
 
 
+@pytest.mark.parametrize("hor,ver,lim,wsplit", [("MFCT", "QR4C", "FCT", False), ("MUSCL", "PPM", "FCT", True), ("MFCT", "CDIFF", "NON", False)])
+def test_neverworld2_mesh(nw2_mesh, hor, ver, lim, wsplit):
+    """the reference's fourth test mesh (test/meshes/neverworld2: 60-degree periodic sector, 15 layers, columns of 4 to 15
+    layers): up to kMaxCols short columns share a CTA of the compacted node kernels"""
+    g = nw2_mesh
+    st, trs, nb, dt = make_case(g, 3, hor, ver, lim, ph=0.25, pv=0.75, use_wsplit=wsplit)
+    ora = run_oracle(g, st, trs, nb, dt)
+    ctx, dh, dv = run_cuda(g, st, trs, nb, dt)
+    _compare(g, ctx, dh, dv, ora, 3, fct=(lim == "FCT"), exact=True)
+    ctx.close()
+
+
 @pytest.mark.parametrize("hor,ver,lim", list(itertools.product(("UPW1", "MUSCL", "MFCT"),
                                                                ("UPW1", "QR4C", "PPM", "CDIFF"), ("FCT", "NON"))))
 def test_all_scheme_combinations(small_mesh, hor, ver, lim):

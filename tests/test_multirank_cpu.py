@@ -31,10 +31,10 @@ def test_gloo_world2_halo_exchange(mesh_name):
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_MESHES), reason="reference fixtures not mounted")
-@pytest.mark.parametrize("name,npes", [("pi", 2), ("pi", 8), ("soufflet", 2), ("soufflet", 8), ("pi_cavity", 2)])
+@pytest.mark.parametrize("name,npes", [("pi", 2), ("pi", 8), ("soufflet", 2), ("soufflet", 8), ("pi_cavity", 2), ("neverworld2", 2), ("neverworld2", 8)])
 def test_localize_reproduces_reference_dist_files(name, npes):
     """mesh.localize == the reference's own partition bookkeeping (test/meshes/*/dist_N)"""
-    g = M.read_fesom_mesh(os.path.join(REF_MESHES, name), cyclic_length_deg=4.5 if name == "soufflet" else 360.0)
+    g = M.read_fesom_mesh(os.path.join(REF_MESHES, name), cyclic_length_deg={"soufflet": 4.5, "neverworld2": 60.0}.get(name, 360.0))
     d = M.read_dist(os.path.join(REF_MESHES, name), npes)
     for r in range(npes):
         m = M.localize(g, d["part"], r)
@@ -88,11 +88,11 @@ def test_oracle_1rank_vs_nrank_identical_on_owned_nodes(pi_mesh, npes):
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_MESHES), reason="reference fixtures not mounted")
-@pytest.mark.parametrize("name,npes", [("pi", 2), ("pi", 8), ("soufflet", 2), ("soufflet", 8), ("pi_cavity", 2)])
+@pytest.mark.parametrize("name,npes", [("pi", 2), ("pi", 8), ("soufflet", 2), ("soufflet", 8), ("pi_cavity", 2), ("neverworld2", 2), ("neverworld2", 8)])
 def test_element_halo_reproduces_reference_dist_files(name, npes):
     """mesh.element_halo == communication_elemn + com_global2local of the reference: myList_elem2D with its
     eDim / eXDim tails and both element communicators, against test/meshes/*/dist_N"""
-    g = M.read_fesom_mesh(os.path.join(REF_MESHES, name), cyclic_length_deg=4.5 if name == "soufflet" else 360.0)
+    g = M.read_fesom_mesh(os.path.join(REF_MESHES, name), cyclic_length_deg={"soufflet": 4.5, "neverworld2": 60.0}.get(name, 360.0))
     d = M.read_dist(os.path.join(REF_MESHES, name), npes)
     for r in range(npes):
         h, info = M.element_halo(g, d["part"], r), d["ranks"][r]

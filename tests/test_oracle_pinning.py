@@ -381,3 +381,22 @@ def test_cavity_mesh_side_rows_two_restatements(cav_mesh):
             assert np.isfinite(p).all() and np.array_equal(p, q)
         assert np.array_equal(x[0][:g.N][cav], W[:g.N][cav]) and np.array_equal(x[1][:g.N][cav], st.hnode_new.numpy()[:g.N][cav])
         assert not np.array_equal(x[0], W)
+
+
+@pytest.mark.parametrize("hor,ver,lim,wsplit", [("MFCT", "QR4C", "FCT", False), ("MUSCL", "PPM", "FCT", True), ("MFCT", "QR4C", "NON", False)])
+def test_neverworld2_mesh_two_restatements(nw2_mesh, hor, ver, lim, wsplit):
+    """the reference's test/meshes/neverworld2 (periodic 60-degree sector, columns of 4 to 15 layers)"""
+    from oracle import numpy_ref as R, oracle_py as O
+    g = nw2_mesh
+    st, trs, nb, dt = make_case(g, 2, hor, ver, lim, ph=0.25, pv=0.75, use_wsplit=wsplit)
+    b = O.OracleRank(g, st, trs, nb, tra_diag=True)
+    O.run([b], dt)
+    na = R.NumpyAdv(g, st, nb)
+    for k in range(2):
+        d = {}
+        dh, dv = np.zeros((g.Nh, g.L)), np.zeros((g.Nh, g.L))
+        with np.errstate(invalid="ignore"):
+            na.do_oce_adv_tra(dt, trs[k], dh, dv, diag=d)
+        assert np.isfinite(dh).all() and np.abs(dh).max() > 0
+        assert np.array_equal(dh, b.dttf_h[k]) and np.array_equal(dv, b.dttf_v[k])
+        assert np.array_equal(b.tra_advhoriz[k], d["tra_advhoriz"]) and np.array_equal(b.tra_advvert[k], d["tra_advvert"])
