@@ -1,0 +1,125 @@
+// dwarf_tracer.cpp -- the reference's tracer-advection dwarf (dwarf/dwarf_tracer/dwarf_ini/fesom.F90:85-128) as a compiled
+// host program above the C++ mirror of the reference interface (fesom_host.hpp): no Python, no torch -- pageable host arrays
+// in, host arrays out, the call sequence of the model (state refreshed once per step, do_oce_adv_tra once per tracer).
+//
+//     dwarf_tracer_b200 <case.bin> <result.bin>
+//
+// case.bin (little endian, written by tests/test_gpu_host_cpp.py): 'FADV', int32 {nl, myDim_nod2D, eDim_nod2D, myDim_elem2D,
+// eDim_elem2D, myDim_edge2D, nod_in_elem2D_ld, num_tracers, nsteps, use_wsplit, ldiag_DVD}, double dt, then the arrays of
+// t_mesh / t_dyn / t_tracer in the order read below, reference layouts.  One rank (the reference's restart reader and
+// MPI are outside the path; the N-rank launch sequence is covered through the C ABI by tests/test_gpu_multirank.py).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include <numeric>
+
+#include "fesom_host.hpp"
+
+using namespace fesom;
+
+template <class T>
+static void rd(FILE* f, std::vector<T>& v, size_t n)
+{
+    v.resize(n);
+    if (n && std::fread(v.data(), sizeof(T), n, f) != n) { std::fprintf(stderr, "dwarf_tracer: short read\n"); std::exit(2); }
+}
+template <class T>
+static void wr(FILE* f, const std::vector<T>& v)
+{
+    if (!v.empty() && std::fwrite(v.data(), sizeof(T), v.size(), f) != v.size()) { std::fprintf(stderr, "dwarf_tracer: short write\n"); std::exit(2); }
+}
+
+int main(int argc, char** argv)
+{
+    if (argc != 3) { std::fprintf(stderr, "usage: %s case.bin result.bin\n", argv[0]); return 2; }
+    FILE* f = std::fopen(argv[1], "rb");
+    if (!f) { std::perror(argv[1]); return 2; }
+    char magic[4];
+    int32_t h[11];
+    double dt;
+    if (std::fread(magic, 1, 4, f) != 4 || std::memcmp(magic, "FADV", 4) != 0 || std::fread(h, 4, 11, f) != 11 || std::fread(&dt, 8, 1, f) != 1) {
+        std::fprintf(stderr, "dwarf_tracer: bad header\n");
+        return 2;
+    }
+    t_mesh mesh;
+    t_partit partit;
+    t_dyn dyn;
+    t_tracer tracers;
+    mesh.nl = h[0];
+    partit.myDim_nod2D = h[1]; partit.eDim_nod2D = h[2]; partit.myDim_elem2D = h[3]; partit.eDim_elem2D = h[4]; partit.myDim_edge2D = h[5];
+    mesh.nod_in_elem2D_ld = h[6];
+    tracers.num_tracers = h[7];
+    const int nsteps = h[8];
+    dyn.use_wsplit = h[9] != 0;
+    ldiag_DVD = h[10] != 0;
+    const size_t nl = mesh.nl, L = nl - 1, N = partit.myDim_nod2D, Nh = N + partit.eDim_nod2D, T = partit.myDim_elem2D + partit.eDim_elem2D, E = partit.myDim_edge2D;
+    const size_t ntr = tracers.num_tracers;
+    rd(f, mesh.edges, 2 * E); rd(f, mesh.edge_tri, 2 * E); rd(f, mesh.elem2D_nodes, 3 * T);
+    rd(f, mesh.nod_in_elem2D, (size_t)mesh.nod_in_elem2D_ld * Nh); rd(f, mesh.nod_in_elem2D_num, Nh);
+    rd(f, mesh.nlevels, T); rd(f, mesh.ulevels, T); rd(f, mesh.nlevels_nod2D, Nh); rd(f, mesh.ulevels_nod2D, Nh);
+    rd(f, tracers.work.nboundary_lay, Nh);
+    rd(f, mesh.edge_cross_dxdy, 4 * E); rd(f, mesh.edge_dxdy, 2 * E); rd(f, mesh.elem_cos, T);
+    rd(f, mesh.area, nl * Nh); rd(f, mesh.areasvol, nl * Nh);
+    rd(f, dyn.uv, 2 * L * T); rd(f, dyn.w, nl * Nh); rd(f, dyn.w_e, nl * Nh); rd(f, dyn.w_i, nl * Nh);
+    rd(f, mesh.helem, L * T); rd(f, mesh.hnode, L * Nh); rd(f, mesh.hnode_new, L * Nh);
+    rd(f, mesh.zbar_3d_n, nl * Nh); rd(f, mesh.Z_3d_n, L * Nh); rd(f, mesh.zbar_n_bot, Nh);
+    tracers.data.resize(ntr);
+    std::vector<std::vector<WP>> grad(ntr);               // what the caller's fill_up_dn_grad produced for each tracer
+    for (size_t k = 0; k < ntr; ++k) {
+        t_tracer_data& td = tracers.data[k];
+        char s[24];
+        int32_t diag;
+        double pp[2];
+        if (std::fread(s, 1, 24, f) != 24 || std::fread(pp, 8, 2, f) != 2 || std::fread(&diag, 4, 1, f) != 1) { std::fprintf(stderr, "dwarf_tracer: bad tracer header\n"); return 2; }
+        auto str = [&](int o) { std::string x(s + o, 8); x.erase(x.find_last_not_of(' ') + 1); return x; };
+        td.tra_adv_hor = str(0); td.tra_adv_ver = str(8); td.tra_adv_lim = str(16);
+        td.tra_adv_ph = pp[0]; td.tra_adv_pv = pp[1];
+        td.ltra_diag = diag != 0;
+        td.ID = (int)k + 1;
+        rd(f, td.values, L * Nh); rd(f, td.valuesAB, L * Nh); rd(f, grad[k], 4 * L * E);
+    }
+    std::fclose(f);
+
+    t_tracer_work& wk = tracers.work;
+    wk.del_ttf.assign(L * Nh, 0.0); wk.del_ttf_advhoriz.assign(L * Nh, 0.0); wk.del_ttf_advvert.assign(L * Nh, 0.0);
+    wk.edge_up_dn_grad.assign(4 * L * E, 0.0);
+    wk.tra_advhoriz.assign(L * Nh * ntr, 0.0); wk.tra_advvert.assign(L * Nh * ntr, 0.0);      // src/oce_setup_step.F90:505-507
+    if (ldiag_DVD) { wk.dvd_trflx_hor.assign(L * E * 2, 0.0); wk.dvd_trflx_ver.assign(nl * N * 2, 0.0); }
+    oce_adv_tra_fct_init(wk, partit, mesh, 0, 1);
+
+    std::vector<std::vector<WP>> last_h(ntr), last_v(ntr);
+    for (int i = 1; i <= nsteps; ++i) {                    // fesom.F90:85
+        mstep = i;
+        for (int tr = 1; tr <= (int)ntr; ++tr) {           // src/oce_ale_tracer.F90:280-312
+            std::fill(wk.del_ttf_advhoriz.begin(), wk.del_ttf_advhoriz.end(), 0.0);           // fesom.F90:88-95
+            std::fill(wk.del_ttf_advvert.begin(), wk.del_ttf_advvert.end(), 0.0);
+            wk.edge_up_dn_grad = grad[(size_t)tr - 1];     // the gradient calls of init_tracers_AB, src/oce_tracer_mod.F90:125-141
+            do_oce_adv_tra(dt, dyn.uv.data(), dyn.w.data(), dyn.w_i.data(), dyn.w_e.data(), tr, dyn, tracers, partit, mesh);   // :97
+            std::vector<WP>& val = tracers.data[(size_t)tr - 1].values;
+            if (partit.mype == 0) {                        // :99
+                const auto mm = std::minmax_element(val.begin(), val.end());
+                std::printf("%d %d %.17g %.17g %.17g\n", i, tr, *mm.first, *mm.second, std::accumulate(val.begin(), val.end(), 0.0));
+            }
+            // :105-125 with del_ttf reset per step as in the model (src/oce_tracer_mod.F90:28-34)
+            for (size_t n = 0; n < N; ++n) {
+                const int nzmax = mesh.nlevels_nod2D[n] - 1, nzmin = mesh.ulevels_nod2D[n];
+                for (int nz = nzmin; nz <= nzmax; ++nz) {
+                    const size_t o = n * L + (size_t)(nz - 1);
+                    wk.del_ttf[o] = 0.0 + wk.del_ttf_advhoriz[o] + wk.del_ttf_advvert[o];
+                    val[o] = val[o] + wk.del_ttf[o] / mesh.hnode_new[o];
+                }
+            }
+            // exchange_nod(values): one rank, nothing to do (:127)
+            if (i == nsteps) { last_h[(size_t)tr - 1] = wk.del_ttf_advhoriz; last_v[(size_t)tr - 1] = wk.del_ttf_advvert; }
+        }
+    }
+    oce_adv_tra_fct_final(wk);
+
+    FILE* g = std::fopen(argv[2], "wb");
+    if (!g) { std::perror(argv[2]); return 2; }
+    for (size_t k = 0; k < ntr; ++k) { wr(g, tracers.data[k].values); wr(g, last_h[k]); wr(g, last_v[k]); }
+    wr(g, wk.tra_advhoriz); wr(g, wk.tra_advvert); wr(g, wk.dvd_trflx_hor); wr(g, wk.dvd_trflx_ver);
+    std::fclose(g);
+    return 0;
+}

@@ -65,3 +65,14 @@ def test_product_package_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".c", ".F90")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|#include\s+.*oracle", txt, flags=re.M), os.path.join(dirpath, f)
+
+
+def test_compiled_host_side_builds_and_links():
+    """fesom2_b200/host (C++ mirror of the reference interface + the tracer dwarf) compiles against include/*.h and links
+    the in-tree library; without arguments the dwarf prints its usage (no GPU call is made here)"""
+    import subprocess
+    from fesom2_b200 import build as B
+    B.build_library()
+    exe = B.build_host(force=True)
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 2 and "usage" in p.stderr
