@@ -28,13 +28,13 @@ def build_library(force: bool = False, verbose: bool = False, out: str = OUT, de
 
 HOST_DIR = os.path.join(_HERE, "host")
 HOST_BIN = os.path.join(_HERE, "dwarf_tracer_b200")
-HOST_SRC = [os.path.join(HOST_DIR, "fesom_host.cpp"), os.path.join(HOST_DIR, "dwarf_tracer.cpp")]
+HOST_SRC = [os.path.join(HOST_DIR, "fesom_host.cpp"), os.path.join(HOST_DIR, "fesom_restart.cpp"), os.path.join(HOST_DIR, "dwarf_tracer.cpp")]
 
 
 def build_host(force: bool = False) -> str:
     """The compiled host side above the C ABI (fesom2_b200/host: C++ mirror of the reference interface + the tracer dwarf),
     linked against the in-tree library (rpath $ORIGIN, so the binary travels with the snapshot)."""
-    deps = HOST_SRC + [os.path.join(HOST_DIR, "fesom_host.hpp"), DEPS[-1], OUT]
+    deps = HOST_SRC + [os.path.join(HOST_DIR, "fesom_host.hpp"), os.path.join(HOST_DIR, "fesom_restart.hpp"), DEPS[-1], OUT]
     newest = max(os.path.getmtime(p) for p in deps)
     if force or not os.path.exists(HOST_BIN) or os.path.getmtime(HOST_BIN) < newest:
         cxx = os.environ.get("CXX", "g++")

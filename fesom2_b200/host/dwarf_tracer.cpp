@@ -3,6 +3,11 @@
 // in, host arrays out, the call sequence of the model (state refreshed once per step, do_oce_adv_tra once per tracer).
 //
 //     dwarf_tracer_b200 <case.bin> <result.bin>
+//     dwarf_tracer_b200 --restart <npepath> <result.bin> [nsteps [dt]]
+//
+// The second form is the dwarf as the reference ships it: it reads the derived-type binary restarts of rank 0 of 1 from
+// <npepath> (read_all_bin_restarts, fesom.F90:64), advects tracer 1 ten times with dt = 1.e-3, accumulates del_ttf over the
+// iterations exactly as fesom.F90:105-125 does, and writes values / del_ttf / del_ttf_advhoriz / del_ttf_advvert.
 //
 // case.bin (little endian, written by tests/test_gpu_host_cpp.py): 'FADV', int32 {nl, myDim_nod2D, eDim_nod2D, myDim_elem2D,
 // eDim_elem2D, myDim_edge2D, nod_in_elem2D_ld, num_tracers, nsteps, use_wsplit, ldiag_DVD}, double dt, then the arrays of
@@ -15,6 +20,9 @@
 #include <numeric>
 
 #include "fesom_host.hpp"
+#include "fesom_restart.hpp"
+
+#include <stdexcept>
 
 using namespace fesom;
 
@@ -30,9 +38,87 @@ static void wr(FILE* f, const std::vector<T>& v)
     if (!v.empty() && std::fwrite(v.data(), sizeof(T), v.size(), f) != v.size()) { std::fprintf(stderr, "dwarf_tracer: short write\n"); std::exit(2); }
 }
 
+// dwarf/dwarf_tracer/dwarf_ini/fesom.F90:64-128, literally (tracer 1, del_ttf carried over the iterations)
+static int dwarf_from_restarts(const char* npepath, const char* result, int nsteps, double dt)
+{
+    t_mesh mesh;
+    t_partit partit;
+    t_dyn dyn;
+    t_tracer tracers;
+    try {
+        read_all_bin_restarts(npepath, 0, 1, partit, mesh, dyn, tracers);                     // :64
+    } catch (const std::exception& ex) {
+        std::fprintf(stderr, " -ERROR-> %s\n", ex.what());
+        par_ex(0, 1);
+    }
+    t_tracer_work& wk = tracers.work;
+    const size_t L = (size_t)mesh.nl - 1, N = (size_t)partit.myDim_nod2D, Nh = N + (size_t)partit.eDim_nod2D;
+    oce_adv_tra_fct_init(wk, partit, mesh, 0, 1);
+    std::vector<WP>& val = tracers.data[0].values;
+    for (int i = 1; i <= nsteps; ++i) {                                                       // :85
+        mstep = i;
+        std::fill(wk.del_ttf_advhoriz.begin(), wk.del_ttf_advhoriz.end(), 0.0);               // :88-95
+        std::fill(wk.del_ttf_advvert.begin(), wk.del_ttf_advvert.end(), 0.0);
+        do_oce_adv_tra(dt, dyn.uv.data(), dyn.w.data(), dyn.w_i.data(), dyn.w_e.data(), 1, dyn, tracers, partit, mesh);   // :97
+        const auto mm = std::minmax_element(val.begin(), val.end());
+        std::printf("%.17g %.17g %.17g\n", *mm.first, *mm.second, std::accumulate(val.begin(), val.end(), 0.0));          // :99
+        for (size_t n = 0; n < Nh; ++n)                                                       // :105-113
+            for (int nz = mesh.ulevels_nod2D[n]; nz <= mesh.nlevels_nod2D[n] - 1; ++nz) {
+                const size_t o = n * L + (size_t)(nz - 1);
+                wk.del_ttf[o] = wk.del_ttf[o] + wk.del_ttf_advhoriz[o] + wk.del_ttf_advvert[o];
+            }
+        for (size_t n = 0; n < N; ++n)                                                        // :116-124
+            for (int nz = mesh.ulevels_nod2D[n]; nz <= mesh.nlevels_nod2D[n] - 1; ++nz) {
+                const size_t o = n * L + (size_t)(nz - 1);
+                val[o] = val[o] + wk.del_ttf[o] / mesh.hnode_new[o];
+            }
+        // exchange_nod(values): one rank (:127)
+    }
+    oce_adv_tra_fct_final(wk);
+    FILE* g = std::fopen(result, "wb");
+    if (!g) { std::perror(result); return 2; }
+    wr(g, val); wr(g, wk.del_ttf); wr(g, wk.del_ttf_advhoriz); wr(g, wk.del_ttf_advvert);
+    std::fclose(g);
+    return 0;
+}
+
+// what read_all_bin_restarts delivered, as text (no GPU call): dimensions, scheme strings, sums of the arrays
+static int dump_restart(const char* npepath)
+{
+    t_mesh mesh;
+    t_partit partit;
+    t_dyn dyn;
+    t_tracer tracers;
+    try {
+        read_all_bin_restarts(npepath, 0, 1, partit, mesh, dyn, tracers);
+    } catch (const std::exception& ex) {
+        std::fprintf(stderr, " -ERROR-> %s\n", ex.what());
+        return 1;
+    }
+    auto sumd = [](const std::vector<WP>& a) { return std::accumulate(a.begin(), a.end(), 0.0); };
+    auto sumi = [](const std::vector<int32_t>& a) { return (long long)std::accumulate(a.begin(), a.end(), 0LL); };
+    std::printf("dims %d %d %d %d %d %d %d %d %d\n", mesh.nl, partit.myDim_nod2D, partit.eDim_nod2D, partit.myDim_elem2D, partit.eDim_elem2D,
+                partit.myDim_edge2D, mesh.nod_in_elem2D_ld, tracers.num_tracers, dyn.use_wsplit ? 1 : 0);
+    std::printf("ints %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld\n", sumi(mesh.edges), sumi(mesh.edge_tri), sumi(mesh.elem2D_nodes),
+                sumi(mesh.nod_in_elem2D), sumi(mesh.nod_in_elem2D_num), sumi(mesh.nlevels), sumi(mesh.ulevels), sumi(mesh.nlevels_nod2D),
+                sumi(mesh.ulevels_nod2D), sumi(tracers.work.nboundary_lay));
+    std::printf("reals %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", sumd(mesh.edge_cross_dxdy),
+                sumd(mesh.edge_dxdy), sumd(mesh.elem_cos), sumd(mesh.area), sumd(mesh.areasvol), sumd(mesh.helem), sumd(mesh.hnode),
+                sumd(mesh.hnode_new), sumd(mesh.zbar_3d_n), sumd(mesh.Z_3d_n), sumd(mesh.zbar_n_bot), sumd(dyn.uv), sumd(dyn.w), sumd(dyn.w_e),
+                sumd(dyn.w_i));
+    for (const t_tracer_data& t : tracers.data)
+        std::printf("tracer %d %s %s %s %.17g %.17g %.17g %.17g\n", t.ID, t.tra_adv_hor.c_str(), t.tra_adv_ver.c_str(), t.tra_adv_lim.c_str(),
+                    t.tra_adv_ph, t.tra_adv_pv, sumd(t.values), sumd(t.valuesAB));
+    std::printf("work %.17g %zu\n", sumd(tracers.work.edge_up_dn_grad), tracers.work.del_ttf.size());
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
-    if (argc != 3) { std::fprintf(stderr, "usage: %s case.bin result.bin\n", argv[0]); return 2; }
+    if (argc == 3 && std::strcmp(argv[1], "--dump-restart") == 0) return dump_restart(argv[2]);
+    if (argc >= 4 && std::strcmp(argv[1], "--restart") == 0)
+        return dwarf_from_restarts(argv[2], argv[3], argc > 4 ? std::atoi(argv[4]) : 10, argc > 5 ? std::atof(argv[5]) : 1.e-3);
+    if (argc != 3) { std::fprintf(stderr, "usage: %s case.bin result.bin | --restart npepath result.bin [nsteps [dt]]\n", argv[0]); return 2; }
     FILE* f = std::fopen(argv[1], "rb");
     if (!f) { std::perror(argv[1]); return 2; }
     char magic[4];

@@ -100,3 +100,38 @@ def test_cpp_dwarf_unknown_scheme_ends_in_par_ex(pi_mesh):
     p, _ = run_dwarf(g, st, trs, nb, dt, 1)
     assert p.returncode == 1
     assert "Unknown vertical advection type QR5C" in p.stderr and "par_ex" in p.stderr
+
+
+def test_cpp_dwarf_from_reference_format_restarts(pi_mesh, tmp_path):
+    """`dwarf_tracer_b200 --restart <npepath>`: the dwarf as the reference ships it -- derived-type binary restarts in
+    (read_all_bin_restarts), tracer 1, dt = 1.e-3, ten iterations with del_ttf carried over (fesom.F90:85-128, literally) --
+    against the same loop around the C restatement"""
+    from fesom2_b200 import restart as R
+    from oracle import oracle_py as O
+    g = pi_mesh
+    nsteps, dt = 10, 1.0e-3
+    st, trs, nb, _ = make_case(g, 1, "MUSCL", "QR4C", "FCT")
+    npepath = str(tmp_path / "np1")
+    R.dump_dwarf(npepath, g, st, trs, nb)
+    res = str(tmp_path / "result.bin")
+    p = subprocess.run([B.build_host(), "--restart", npepath, res], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr
+    assert len(p.stdout.strip().splitlines()) == nsteps
+    rk = O.OracleRank(g, st, trs, nb)
+    lev = np.arange(1, g.L + 1)[None, :]
+    wet = (lev >= np.asarray(g.ulevels_nod2D)[:, None]) & (lev <= np.asarray(g.nlevels_nod2D)[:, None] - 1)
+    del_ttf = np.zeros((g.Nh, g.L))
+    hnn = st.hnode_new.numpy()
+    for _ in range(nsteps):
+        rk.dttf_h[0][...] = 0.0
+        rk.dttf_v[0][...] = 0.0
+        O.run([rk], dt, 1, 0)
+        del_ttf[wet] = (del_ttf + rk.dttf_h[0] + rk.dttf_v[0])[wet]
+        own = wet.copy()
+        own[g.N:] = False
+        rk.values[0][own] = (rk.values[0] + del_ttf / np.where(wet, hnn, 1.0))[own]
+    out = np.fromfile(res, dtype=np.float64).reshape(4, g.Nh, g.L)
+    assert np.array_equal(out[0], rk.values[0]) and np.array_equal(out[1], del_ttf)
+    assert np.array_equal(out[2], rk.dttf_h[0]) and np.array_equal(out[3], rk.dttf_v[0])
+    vals = [float(x) for x in p.stdout.strip().splitlines()[-1].split()]
+    assert len(vals) == 3 and vals[0] <= vals[1]

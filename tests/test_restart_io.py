@@ -168,3 +168,53 @@ def test_step_from_dwarf_files_equals_step_from_memory(tmp_path, pi_mesh):
     ctx2, dh2, dv2 = run_cuda(m, st2, trs2, ex["nboundary_lay"], dt)
     assert np.array_equal(dh[0], dh2[0]) and np.array_equal(dv[0], dv2[0])
     ctx.close(); ctx2.close()
+
+
+def test_cpp_reader_agrees_with_the_python_reader(tmp_path):
+    """fesom2_b200/host/fesom_restart.cpp (read_all_bin_restarts of the compiled host side) on files written in the
+    reference's format: every dimension, scheme string and array sum equals what the Python reader delivers"""
+    import subprocess
+    import numpy as np
+    from fesom2_b200 import build as B, fields as F, mesh as M, restart as R
+    g = M.synth_mesh(23, 19, nl=14, min_layers=4)
+    st = F.make_state(g, "cpu", use_wsplit=True)
+    trs = F.make_tracers(g, 3, "cpu", hor="MUSCL", ver="PPM", lim="FCT", ph=0.25, pv=0.75)
+    nb = M.nboundary_lay(g)
+    d = str(tmp_path / "np1")
+    R.dump_dwarf(d, g, st, trs, nb, wsplit_maxcfl=0.9)
+    B.build_library()
+    p = subprocess.run([B.build_host(), "--dump-restart", d], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 0, p.stderr
+    out = {ln.split()[0] + (ln.split()[1] if ln.startswith("tracer") else ""): ln.split()[1:] for ln in p.stdout.strip().splitlines()}
+    m2, st2, trs2, ex = R.load_dwarf(d)
+    assert [int(x) for x in out["dims"]] == [g.nl, g.N, g.eDim_nod2D, g.T, g.eDim_elem2D, g.E, g.nod_in_elem2D.shape[1], 3, 1]
+    ints = [m2.edges, m2.edge_tri, m2.elem2D_nodes, m2.nod_in_elem2D, m2.nod_in_elem2D_num, m2.nlevels, m2.ulevels, m2.nlevels_nod2D,
+            m2.ulevels_nod2D, ex["nboundary_lay"]]
+    assert [int(x) for x in out["ints"]] == [int(np.asarray(a, np.int64).sum()) for a in ints]
+    reals = [m2.edge_cross_dxdy, m2.edge_dxdy, m2.elem_cos, m2.area, m2.areasvol, st2.helem, st2.hnode, st2.hnode_new, st2.zbar_3d_n,
+             st2.Z_3d_n, st2.zbar_n_bot, st2.uv, st2.w, st2.w_e, st2.w_i]
+    for got, a in zip(out["reals"], reals):
+        a = np.asarray(a, np.float64).ravel()
+        ref = 0.0
+        for x in a:                                   # the C++ side sums left to right
+            ref += x
+        assert float(got) == ref
+    for k, t in enumerate(trs2):
+        f = out[f"tracer{k + 1}"]
+        assert f[1:4] == [t.tra_adv_hor, t.tra_adv_ver, t.tra_adv_lim] and float(f[4]) == t.tra_adv_ph and float(f[5]) == t.tra_adv_pv
+        assert abs(float(f[6]) - float(t.values.sum())) <= 1e-9 * abs(float(t.values.sum()))
+
+
+def test_cpp_reader_rejects_a_truncated_file(tmp_path):
+    import subprocess
+    from fesom2_b200 import build as B, fields as F, mesh as M, restart as R
+    g = M.synth_mesh(11, 9, nl=8, min_layers=4)
+    st = F.make_state(g, "cpu")
+    trs = F.make_tracers(g, 1, "cpu")
+    d = str(tmp_path / "np1")
+    R.dump_dwarf(d, g, st, trs, M.nboundary_lay(g))
+    path = os.path.join(d, "t_mesh.0")
+    raw = open(path, "rb").read()
+    open(path, "wb").write(raw[:len(raw) // 2])
+    p = subprocess.run([B.build_host(), "--dump-restart", d], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 1 and "t_mesh.0" in p.stderr
