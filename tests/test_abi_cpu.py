@@ -76,3 +76,12 @@ def test_compiled_host_side_builds_and_links():
     exe = B.build_host(force=True)
     p = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert p.returncode == 2 and "usage" in p.stderr
+
+
+def test_header_is_plain_c():
+    """include/fesom_adv_b200.h must compile as C99 on its own (what a cgo / ISO_C_BINDING / ctypes generator sees);
+    also catches a comment that closes itself early"""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "fesom_adv_b200.h")
+    p = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
