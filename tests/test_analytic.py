@@ -170,3 +170,29 @@ def test_fct_does_not_touch_a_linear_field(hor, ver):
         err = np.abs(dh + dv - exact)[inner].max() / np.abs(exact).max()
         assert err <= 1e-9, (hor, ver, err)
         assert np.abs(dv).max() > 0                               # with FCT the low-order part sits in del_ttf_advvert
+
+
+def test_continuity_of_a_uniform_flow_and_zstar_conservation():
+    """vert_vel_ale (src/oce_ale.F90:2164-2310): the transports of a constant velocity through the closed boundary of a
+    median-dual cell sum to zero, so W vanishes at every interior node of an irregular mesh (to round-off of the
+    individual transports) -- a sign or metric slip in edge_cross_dxdy would leave O(u h / dx) there.  The zstar correction
+    (:2539-2603) must hand the whole elevation change to the layers: sum_k (hnode_new - hnode) = hbar - hbar_old."""
+    from oracle import numpy_ref as R, oracle_py as O
+    g, st, trs, nb, dt = linear_case()
+    rk = O.OracleRank(g, st, trs, nb)
+    h = st.hnode.numpy()[0, 0]
+    scale = np.hypot(U0, V0) * h / (4.0 / 16 * M.RAD * R_EARTH)            # u h / dx: what an unbalanced cell would show
+    inner = interior_nodes(g)
+    for W in (O.vert_vel_ale_core(rk), R.vert_vel_ale_core(g, st.uv.numpy(), st.helem.numpy())):
+        assert np.abs(W[inner]).max() <= 1e-12 * scale * g.L
+        assert np.abs(W[~inner]).max() > 1e-3 * scale                      # open cells at the wall are NOT balanced
+    ids = np.arange(g.Nh, dtype=np.float64)
+    hbar_old = 0.05 * np.sin(0.37 * ids)
+    hbar = hbar_old + 0.2 * np.cos(0.11 * ids)
+    W0_ = np.zeros((g.Nh, g.nl))
+    for Wz, hn in (O.vert_vel_ale_zstar(rk, dt, W0_, hbar, hbar_old, np.zeros(g.Nh)),
+                   R.vert_vel_ale_zstar(g, st.zbar_3d_n.numpy(), st.hnode.numpy(), st.hnode_new.numpy(), dt, W0_, hbar, hbar_old, np.zeros(g.Nh))):
+        dsum = (hn - st.hnode.numpy())[:g.N].sum(axis=1)
+        assert np.abs(dsum - (hbar - hbar_old)[:g.N]).max() <= 1e-12
+        # and the surface velocity is the rate of that change: W(1) = -(hbar - hbar_old) / dt
+        assert np.abs(Wz[:g.N, 0] + (hbar - hbar_old)[:g.N] / dt).max() <= 1e-12 * np.abs(hbar - hbar_old).max() / dt * 10
