@@ -60,7 +60,7 @@ constexpr int kBlock = 256;
 #define ADV_N1_REGS 56
 #endif
 #ifndef ADV_K2_REGS
-#define ADV_K2_REGS 72
+#define ADV_K2_REGS 64   // with 256-thread CTAs and one slot per gather batch: 4 x 8 = 32 resident warps (72 registers: 28), 8 bytes spilled
 #endif
 #ifndef ADV_K3_REGS
 #define ADV_K3_REGS 56   // since the vertical part of the update moved into k_fct_bounds: no spills at 56, 5 CTAs per SM (0.84 -> 0.77 ms)

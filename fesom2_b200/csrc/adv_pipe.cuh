@@ -111,8 +111,16 @@ __host__ __device__ inline size_t e1b_smem_bytes(int nge, int nthr, int D)
     return align128(e1p_meta_bytes(nge)) + (size_t)D * e1b_stage_bytes<TB, QMODE, GS>(nthr) + 16 * D;
 }
 
+#ifndef ADV_E1P_REGS
+#define ADV_E1P_REGS 0      // > 0: explicit register budget instead of the __launch_bounds__ cap (experiments)
+#endif
+#if ADV_E1P_REGS > 0
+#define ADV_E1P_BOUNDS __maxnreg__(ADV_E1P_REGS)
+#else
+#define ADV_E1P_BOUNDS __launch_bounds__(kBlock, ADV_E1P_MINB)
+#endif
 template <int HOR, int TB, int QMODE, int D, int GS>
-__global__ void __launch_bounds__(kBlock, ADV_E1P_MINB) k_edge_flux_b(MeshDev m, Chunk<TB> b, int epb, int ng, int il, int pf)
+__global__ void ADV_E1P_BOUNDS k_edge_flux_b(MeshDev m, Chunk<TB> b, int epb, int ng, int il, int pf)
 {
     static_assert(HOR != HOR_UPW1, "the bulk variant stages edge_up_dn_grad");
     using C = E1bCells<TB, QMODE>;
