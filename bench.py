@@ -474,6 +474,30 @@ def sub_bench(name, ntr, steps, peak, peak_src, dist):
 
 
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(local_rank: int):
+    """What `srun --cpu-bind` / `numactl` do for the one-rank-per-GPU launch of an MPI host (the reference's
+    work/job_gpu_levante binds ranks next to their GPUs): pin this rank to the CPUs of its GPU's NUMA node, so that the
+    first-touch pages of its host arrays sit behind the GPU's own PCIe root (the e2e leg copies 9.5 GB per rank and step).
+    Returns the number of CPUs bound to, or 0 when the affinity is unknown (then nothing changes)."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode() if hasattr(bus, "encode") else bus)
+        words = (max(os.cpu_count() or 64, 64) + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if len(cpus) >= 2:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -531,6 +555,8 @@ def main():
     dev = torch.device(f"cuda:{local_rank}")
     gloo_group = None
     if world > 1:
+        ncpu = bind_to_gpu_numa(local_rank)
+        config["cpu_bind"] = f"each rank pinned to the CPUs of its GPU's NUMA node ({ncpu} on rank 0)" if ncpu else "none (GPU affinity unknown)"
         dist.init_process_group("nccl", device_id=dev)
         if not args.no_parity:
             gloo_group = dist.new_group(backend="gloo")
