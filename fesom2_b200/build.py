@@ -39,5 +39,5 @@ def build_host(force: bool = False) -> str:
     if force or not os.path.exists(HOST_BIN) or os.path.getmtime(HOST_BIN) < newest:
         cxx = os.environ.get("CXX", "g++")
         subprocess.check_call([cxx, "-O2", "-std=c++17", "-Wall", "-ffp-contract=off", "-I", os.path.join(_HERE, "..", "include"), "-I", HOST_DIR]
-                              + HOST_SRC + ["-L", _HERE, "-lfesom_adv_b200", "-Wl,-rpath,$ORIGIN", "-o", HOST_BIN])
+                              + HOST_SRC + ["-L", _HERE, "-lfesom_adv_b200", "-pthread", "-Wl,-rpath,$ORIGIN", "-o", HOST_BIN])
     return HOST_BIN

@@ -6,8 +6,8 @@
 
 namespace fesom {
 
-int mstep = 0;
-bool ldiag_DVD = false;
+thread_local int mstep = 0;
+thread_local bool ldiag_DVD = false;
 
 [[noreturn]] void par_ex(int mype, int abort_code)
 {
@@ -44,6 +44,13 @@ void oce_adv_tra_fct_init(t_tracer_work& twork, t_partit& partit, const t_mesh& 
     d.rPEnum = c.rPEnum; d.rPE = c.rPE.data(); d.rptr = c.rptr.data(); d.rlist = c.rlist.data();
     d.sPEnum = c.sPEnum; d.sPE = c.sPE.data(); d.sptr = c.sptr.data(); d.slist = c.slist.data();
     check(adv_ctx_create(&twork.b200, &d, device, max_tracers), partit);
+}
+
+void par_init_local(std::vector<t_tracer_work*>& tworks, t_partit& partit0)
+{
+    std::vector<adv_ctx_t*> ctxs;
+    for (t_tracer_work* w : tworks) ctxs.push_back(w->b200);
+    check(adv_ctx_comm_init_local(ctxs.data(), (int)ctxs.size()), partit0);
 }
 
 void oce_adv_tra_fct_final(t_tracer_work& twork)

@@ -73,8 +73,11 @@ struct t_dyn {                                            // src/MOD_DYN.F90:65-
     bool use_wsplit = false;
 };
 
-extern int mstep;                                         // o_PARAM mstep (src/oce_modules.F90:23): the model's step counter
-extern bool ldiag_DVD;                                    // diagnostics ldiag_DVD (src/gen_modules_diag.F90:101)
+// o_PARAM mstep (src/oce_modules.F90:23), the model's step counter, and diagnostics ldiag_DVD (src/gen_modules_diag.F90:101).
+// thread_local: a host that runs several ranks as threads of one process (one context each, adv_ctx_comm_init_local)
+// gives every rank its own copy, like the module variables of separate MPI processes.
+extern thread_local int mstep;
+extern thread_local bool ldiag_DVD;
 
 // par_ex(comm, mype, abort) (src/gen_modules_partitioning.F90:87-123): the reference's way out of an unrecoverable error
 [[noreturn]] void par_ex(int mype, int abort_code);
@@ -83,6 +86,10 @@ extern bool ldiag_DVD;                                    // diagnostics ldiag_D
 // here; this one creates the device context (mesh upload, gather lists, work arrays for `max_tracers` per call)
 void oce_adv_tra_fct_init(t_tracer_work& twork, t_partit& partit, const t_mesh& mesh, int device = 0, int max_tracers = 2);
 void oce_adv_tra_fct_final(t_tracer_work& twork);
+// N ranks inside one process (one host thread per rank, every twork initialised with its own partit): links their contexts
+// so that the halo exchanges inside do_oce_adv_tra run as device-to-device copies (adv_ctx_comm_init_local); with MPI ranks
+// in separate processes the host broadcasts adv_comm_unique_id and calls adv_ctx_comm_init instead
+void par_init_local(std::vector<t_tracer_work*>& tworks, t_partit& partit0);
 
 // do_oce_adv_tra(dt, vel, w, wi, we, tr_num, dynamics, tracers, partit, mesh) (src/oce_adv_tra_driver.F90:46-490): one tracer
 // per call, tr_num 1-based, accumulating into tracers%work%del_ttf_advhoriz / del_ttf_advvert; the state arrays are uploaded

@@ -18,14 +18,20 @@ from fesom2_b200 import build as B
 pytestmark = pytest.mark.gpu
 
 
-def write_case(path, g, st, trs, nb, dt, nsteps, ltra_diag=True, dvd=False):
+def write_case(path, g, st, trs, nb, dt, nsteps, ltra_diag=True, dvd=False, partitioned=False):
+    """partitioned: 'FADW' = a rank's local mesh with mype / npes and the com_nod2D lists after the header"""
     i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32).tobytes()       # noqa: E731
     f64 = lambda a: np.ascontiguousarray(np.asarray(a), dtype=np.float64).tobytes()   # noqa: E731
     with open(path, "wb") as f:
-        f.write(b"FADV")
+        f.write(b"FADW" if partitioned else b"FADV")
         f.write(struct.pack("<11i", g.nl, g.N, g.eDim_nod2D, g.T, g.eDim_elem2D, g.E, g.nod_in_elem2D.shape[1], len(trs), nsteps,
                             int(bool(st.use_wsplit)), int(dvd)))
         f.write(struct.pack("<d", dt))
+        if partitioned:
+            c = g.com_nod2D
+            f.write(struct.pack("<6i", g.mype, g.npes, c.rPEnum, c.sPEnum, len(c.rlist), len(c.slist)))
+            for a in (c.rPE, c.rptr, c.rlist, c.sPE, c.sptr, c.slist):
+                f.write(i32(a))
         for name in ("edges", "edge_tri", "elem2D_nodes", "nod_in_elem2D", "nod_in_elem2D_num", "nlevels", "ulevels",
                      "nlevels_nod2D", "ulevels_nod2D"):
             f.write(i32(getattr(g, name)))
@@ -135,3 +141,37 @@ def test_cpp_dwarf_from_reference_format_restarts(pi_mesh, tmp_path):
     assert np.array_equal(out[2], rk.dttf_h[0]) and np.array_equal(out[3], rk.dttf_v[0])
     vals = [float(x) for x in p.stdout.strip().splitlines()[-1].split()]
     assert len(vals) == 3 and vals[0] <= vals[1]
+
+
+@pytest.mark.parametrize("which,world", [("pi", 2), ("pi", 8), ("cavity", 2)])
+def test_cpp_dwarf_ranks_as_threads(pi_mesh, cav_mesh, which, world, tmp_path):
+    """`dwarf_tracer_b200 --ranks N`: the reference's dist_N partition, one context and one host thread per rank, the halo
+    exchanges of do_oce_adv_tra inside the library (in-process communicator), exchange_nod(values) between the ranks' host
+    arrays -- three dwarf iterations of two tracers; every rank's nodes (owned and halo) equal the one-rank C restatement"""
+    from fesom2_b200 import fields as F, mesh as M
+    from oracle import oracle_py as O
+    g = {"pi": pi_mesh, "cavity": cav_mesh}[which]
+    nsteps = 3
+    st, trs, nb, dt = make_case(g, 2, "MFCT", "QR4C", "FCT")
+    one = O.OracleRank(g, st, trs, nb)
+    O.run([one], dt, nsteps, 1)
+    part = g.parts[world]
+    locs = []
+    for r in range(world):
+        loc = M.localize(g, part, r)
+        lst, ltr = F.scatter_to_local(g, loc, st, trs)
+        write_case(str(tmp_path / f"case.{r}"), loc, lst, ltr, nb[loc.myList_nod2D - 1], dt, nsteps, partitioned=True)
+        locs.append(loc)
+    p = subprocess.run([B.build_host(), "--ranks", str(world), str(tmp_path / "case"), str(tmp_path / "result")],
+                       capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr
+    assert len(p.stdout.strip().splitlines()) == nsteps * 2          # rank 0 prints
+    for r, loc in enumerate(locs):
+        out = np.fromfile(str(tmp_path / f"result.{r}"), dtype=np.float64)
+        n = loc.Nh * loc.L
+        alln = loc.myList_nod2D.astype(np.int64) - 1
+        own = alln[:loc.N]
+        for k in range(2):
+            vals, dh, dv = (out[(3 * k + j) * n:(3 * k + j + 1) * n].reshape(loc.Nh, loc.L) for j in range(3))
+            assert np.array_equal(vals, one.values[k][alln]), (r, k, "values incl. halo")
+            assert np.array_equal(dh[:loc.N], one.dttf_h[k][own]) and np.array_equal(dv[:loc.N], one.dttf_v[k][own]), (r, k)
