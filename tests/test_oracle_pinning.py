@@ -400,3 +400,31 @@ def test_neverworld2_mesh_two_restatements(nw2_mesh, hor, ver, lim, wsplit):
         assert np.isfinite(dh).all() and np.abs(dh).max() > 0
         assert np.array_equal(dh, b.dttf_h[k]) and np.array_equal(dv, b.dttf_v[k])
         assert np.array_equal(b.tra_advhoriz[k], d["tra_advhoriz"]) and np.array_equal(b.tra_advvert[k], d["tra_advvert"])
+
+
+@pytest.mark.parametrize("which", ["cavity", "nw2"])
+@pytest.mark.parametrize("hor,ver,lim", [("MFCT", "QR4C", "FCT"), ("MUSCL", "PPM", "NON"), ("UPW1", "CDIFF", "FCT")])
+def test_invariants_on_the_cavity_and_neverworld2_meshes(cav_mesh, nw2_mesh, which, hor, ver, lim):
+    """(ii) and (iii) of SURVEY 8c on the reference's other two meshes: a constant tracer keeps a zero tendency under the
+    ice (nzmin > 1, areasvol = lower face) and in 4-layer columns, and the area-weighted sum of the tendencies equals the
+    flux through the top interface of every column (which is the cavity base where there is one)"""
+    g = {"cavity": cav_mesh, "nw2": nw2_mesh}[which]
+    _, nmask = F.layer_masks(g, "cpu")
+    N, L = g.N, g.L
+    mask = nmask.numpy()[:N]
+    st, trs, nb, dt = make_case(g, 1, hor, ver, lim, ph=0.25, pv=0.75)
+    real = run_oracle(g, st, trs, nb, dt)                                    # a real field first: conservation
+    tend = np.where(mask, (real.dttf_h[0][:N] + real.dttf_v[0][:N]) * g.areasvol[:N, :L], 0.0)
+    top, rows = g.ulevels_nod2D[:N] - 1, np.arange(N)
+    surf = real.keep["adv_flux_ver"][rows, top].copy()
+    if lim == "FCT":
+        surf += -st.w_e.numpy()[rows, top] * trs[0].values.numpy()[rows, top] * g.area[rows, top]
+    assert abs(tend.sum() - dt * surf.sum()) <= 1e-10 * np.abs(tend).sum()
+    c0 = 7.25                                                                # then T = const
+    trs[0].values = torch.where(nmask, torch.full_like(trs[0].values, c0), torch.zeros_like(trs[0].values))
+    trs[0].valuesAB = trs[0].values.clone()
+    trs[0].edge_up_dn_grad = torch.zeros_like(trs[0].edge_up_dn_grad)
+    ora = run_oracle(g, st, trs, nb, dt)
+    hn = st.hnode_new.numpy()[:N]
+    dval = np.where(mask, (ora.dttf_h[0][:N] + ora.dttf_v[0][:N]) / np.where(mask, hn, 1.0), 0.0)
+    assert np.abs(dval).max() <= 1e-11 * c0
