@@ -25,11 +25,14 @@ U0, V0, W0 = 0.31, -0.17, 2.0e-5
 GA, GB, GC = 3.0e-6, -2.0e-6, 4.0e-3          # dT/dx, dT/dy per metre; dT/dz per metre
 
 
-def linear_case(hor="MFCT", ver="QR4C", ph=0.0, pv=1.0, vertical=False, nx=17, ny=13, nl=14):
-    """flat-bottom cartesian patch with uniform layers; returns (mesh, state, [tracer], nboundary_lay, dt)"""
+def linear_case(hor="MFCT", ver="QR4C", ph=0.0, pv=1.0, vertical=False, nx=17, ny=13, nl=14, uniform_z=True):
+    """flat-bottom cartesian patch with uniform (or stretched) layers; returns (mesh, state, [tracer], nboundary_lay, dt)"""
     g = M.synth_mesh(nx, ny, nl=nl, lon0=-2.0, lon1=2.0, lat0=-1.5, lat1=1.5, staircase=False, derive=False)
     g.cartesian = True
-    g.zbar = -np.linspace(0.0, 50.0 * (nl - 1), nl)            # uniform 50 m layers
+    if uniform_z:
+        g.zbar = -np.linspace(0.0, 50.0 * (nl - 1), nl)        # uniform 50 m layers
+    else:
+        g.zbar = -np.cumsum(np.concatenate([[0.0], 10.0 * 1.35 ** np.arange(nl - 1)]))   # 10 m at the top, growing by 35 % per layer
     if not vertical:
         # an IRREGULAR triangulation: every interior node moved by up to 30 % of the grid spacing (on a uniform grid even
         # first-order upwind is exact for a linear field, by symmetry, and the test could not fail)
@@ -196,3 +199,18 @@ def test_continuity_of_a_uniform_flow_and_zstar_conservation():
         assert np.abs(dsum - (hbar - hbar_old)[:g.N]).max() <= 1e-12
         # and the surface velocity is the rate of that change: W(1) = -(hbar - hbar_old) / dt
         assert np.abs(Wz[:g.N, 0] + (hbar - hbar_old)[:g.N] / dt).max() <= 1e-12 * np.abs(hbar - hbar_old).max() / dt * 10
+
+
+@pytest.mark.parametrize("ver,pv", [("QR4C", 1.0), ("QR4C", 0.0), ("PPM", 1.0)])
+def test_vertical_schemes_on_stretched_layers(ver, pv):
+    """the same on layers that grow by 35 % each: QR4C's slopes over the layer-centre distances Z(k-1) - Z(k) and its
+    extrapolation to zbar(k), and PPM's non-uniform interface weights, are exact for a profile linear in depth"""
+    g, st, trs, nb, dt = linear_case(hor="UPW1", ver=ver, pv=pv, vertical=True, uniform_z=False)
+    h = st.hnode.numpy()
+    assert h[0, 5] > 3.0 * h[0, 1]
+    exact = -dt * h * W0 * GC
+    lev = np.arange(1, g.L + 1)
+    ok = (lev >= 4) & (lev <= g.L - 4)
+    for dh, dv in _both(g, st, trs, nb, dt):
+        err = (np.abs(dv - exact)[:, ok] / np.abs(exact)[:, ok]).max()
+        assert err <= 1e-9, (ver, pv, err)
