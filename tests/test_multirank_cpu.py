@@ -170,3 +170,33 @@ def test_gradient_producer_is_rank_local_with_the_element_halo(mesh_name, npes, 
                              elem_area=g.elem_area[elist], nl=g.nl, L=g.L, E=loc.E)
         got = O.fill_up_dn_grad(lm, xy, tri_l)
         assert np.array_equal(got, grad_glob[edges]), (mesh_name, npes, r)
+
+
+@pytest.mark.parametrize("lim", ["FCT", "NON"])
+def test_oracle_diagnostics_1rank_vs_nrank(pi_mesh, lim):
+    """ltra_diag / ldiag_DVD on the reference's dist_2 partition: tra_advhoriz / tra_advvert of the owned nodes and
+    dvd_trflx_ver of the owned nodes are identical on 1 and 2 ranks; dvd_trflx_hor of every local edge equals the global
+    edge's value (an edge's flux needs its two end nodes only, and both are local)"""
+    from oracle import oracle_py as O
+    g = pi_mesh
+    st = F.make_state(g, "cpu")
+    dt = F.cfl_dt(g, st, 0.3)
+    trs = F.make_tracers(g, 2, "cpu", hor="MFCT", ver="QR4C", lim=lim)
+    nbg = M.nboundary_lay(g)
+    one = O.OracleRank(g, st, trs, nbg, tra_diag=True, dvd=True)
+    O.run([one], dt)
+    ranks = []
+    for r in range(2):
+        loc = M.localize(g, g.parts[2], r)
+        lst, ltr = F.scatter_to_local(g, loc, st, trs)
+        ranks.append(O.OracleRank(loc, lst, ltr, nbg[loc.myList_nod2D - 1], tra_diag=True, dvd=True))
+    O.run(ranks, dt)
+    for rk in ranks:
+        loc = rk.mesh_py
+        own = loc.myList_nod2D[:loc.N] - 1
+        edges = loc.myList_edge2D[:loc.E] - 1
+        for k in range(2):
+            assert np.array_equal(rk.tra_advhoriz[k][:loc.N], one.tra_advhoriz[k][own])
+            assert np.array_equal(rk.tra_advvert[k][:loc.N], one.tra_advvert[k][own])
+            assert np.array_equal(rk.dvd_trflx_ver[k], one.dvd_trflx_ver[k][own])
+            assert np.array_equal(rk.dvd_trflx_hor[k], one.dvd_trflx_hor[k][edges])
