@@ -192,8 +192,8 @@ struct adv_ctx {
     int force_tb1 = 0;                        // experiments: one tracer per chunk (ADV_TB1)
     // wet-level compaction: CTA partitions of the node ranges and edge groups (built in adv_ctx_create)
     int cta_threads = 224;                    // threads per CTA of the FCT node kernels (ADV_CTA_THREADS) ...
-    int cta_n1 = 288, cta_k2 = 256, cta_k3 = 0; // ... per kernel (ADV_CTA_N1 / _K2 / _K3; 0 = cta_threads): the size at which the register
-                                              //     file holds most warps -- N1 (56 registers) 4 x 9 = 36, K2 (64) 4 x 8 = 32, K3 (56) 5 x 7 = 35
+    int cta_n1 = 288, cta_k2 = 256, cta_k3 = 288; // ... per kernel (ADV_CTA_N1 / _K2 / _K3; 0 = cta_threads): the size at which the register
+                                              //     file holds most warps -- N1 (56 registers) 4 x 9 = 36, K2 (64) 4 x 8 = 32, K3 (56) 4 x 9 = 36
     struct Part { DevBuf<int> first; int ncta = 0; };
     struct PartSet { int threads = 0; Part all, inner, s, sh; };   // the CTA partitions of the four node ranges for one CTA size
     PartSet parts[3];                         // one per distinct CTA size in use (at most three kernels)
@@ -379,7 +379,7 @@ int adv_ctx_create(adv_ctx_t** out, const adv_mesh_desc_t* d, int device, int ma
     if (const char* v = getenv("ADV_TB1")) c->force_tb1 = atoi(v);
     if (const char* v = getenv("ADV_I_IDENTITY")) c->i_identity = atoi(v) ? 1 : 0;
     if (const char* v = getenv("ADV_E1_PF")) c->e1_pf = std::max(0, atoi(v));
-    if (const char* v = getenv("ADV_CTA_THREADS")) { c->cta_threads = atoi(v); c->cta_n1 = 0; c->cta_k2 = 0; }
+    if (const char* v = getenv("ADV_CTA_THREADS")) { c->cta_threads = atoi(v); c->cta_n1 = 0; c->cta_k2 = 0; c->cta_k3 = 0; }
     if (const char* v = getenv("ADV_CTA_N1")) c->cta_n1 = atoi(v);
     if (const char* v = getenv("ADV_CTA_K2")) c->cta_k2 = atoi(v);
     if (const char* v = getenv("ADV_CTA_K3")) c->cta_k3 = atoi(v);

@@ -48,7 +48,8 @@ constexpr int kBlock = 256;
 #define ADV_QR4C_RCP 1   // k_node_lo: one reciprocal per thread shared through smem instead of six IEEE divisions
 #endif
 #ifndef ADV_PF_OWN
-#define ADV_PF_OWN 5     // bit mask N1|K2|K3: also pull the next CTAs' own columns into L2 (K3: 1.37 -> 1.26 ms, N1: -1 %, K2: nothing)
+#define ADV_PF_OWN 0     // bit mask N1|K2|K3: also pull the next CTAs' own columns into L2.  Round 1 / early round 2: 5 (K3 1.37 -> 1.26 ms,
+                         // N1 -1 %); with the per-kernel CTA sizes of DESIGN decision 17 it costs N1 6 % and K3 1.5 % (profiles/r8p_*): off
 #endif
 // minimum resident CTAs per SM (register caps): measured on B200, see DESIGN.md section 4 --
 // occupancy beats register-resident batching: 4-5 CTAs of 7 warps with a few spilled words run
