@@ -123,11 +123,12 @@ def test_global_conservation(small_mesh, lim):
     assert abs(tend.sum() - dt * surf.sum()) <= 1e-10 * scale
 
 
-def test_fct_no_new_extrema(pi_mesh):
+@pytest.mark.parametrize("which,hor,ver", [("pi", "MFCT", "QR4C"), ("cavity", "MFCT", "QR4C"), ("nw2", "MUSCL", "PPM"), ("souf", "MFCT", "CDIFF")])
+def test_fct_no_new_extrema(pi_mesh, cav_mesh, nw2_mesh, souf_mesh, which, hor, ver):
     """(iv) / Appendix C: values_new within the 3-D cluster bounds of oce_adv_tra_fct.F90:124-248
-    recomputed here from the oracle's ttf and fct_LO"""
-    g = pi_mesh
-    st, trs, nb, dt = make_case(g, 1, "MFCT", "QR4C", "FCT")
+    recomputed here from the oracle's ttf and fct_LO -- on all four meshes of the reference"""
+    g = {"pi": pi_mesh, "cavity": cav_mesh, "nw2": nw2_mesh, "souf": souf_mesh}[which]
+    st, trs, nb, dt = make_case(g, 1, hor, ver, "FCT")
     ora = run_oracle(g, st, trs, nb, dt)
     N, L = g.N, g.L
     ttf = trs[0].values.numpy()
