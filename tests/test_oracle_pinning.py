@@ -429,3 +429,23 @@ def test_invariants_on_the_cavity_and_neverworld2_meshes(cav_mesh, nw2_mesh, whi
     hn = st.hnode_new.numpy()[:N]
     dval = np.where(mask, (ora.dttf_h[0][:N] + ora.dttf_v[0][:N]) / np.where(mask, hn, 1.0), 0.0)
     assert np.abs(dval).max() <= 1e-11 * c0
+
+
+@pytest.mark.parametrize("hor,ver", [("MFCT", "QR4C"), ("MUSCL", "PPM")])
+def test_constant_tracer_with_wsplit(small_mesh, hor, ver):
+    """(ii) with dynamics%use_wsplit: the explicit upwind flux on w_e plus the implicit sweep adv_tra_vert_impl on w_i
+    (src/oce_adv_tra_ver.F90:90-240, src/oce_adv_tra_driver.F90:320-334) together still advect nothing when T = const --
+    which pins the tridiagonal coefficients of the implicit part against the explicit one"""
+    g = small_mesh
+    st, trs, nb, dt = make_case(g, 1, hor, ver, "FCT", ph=0.25, pv=0.75, use_wsplit=True)
+    assert (st.w_i.numpy() != 0).sum() > 10
+    c0 = 7.25
+    _, nmask = F.layer_masks(g, "cpu")
+    trs[0].values = torch.where(nmask, torch.full_like(trs[0].values, c0), torch.zeros_like(trs[0].values))
+    trs[0].valuesAB = trs[0].values.clone()
+    trs[0].edge_up_dn_grad = torch.zeros_like(trs[0].edge_up_dn_grad)
+    ora = run_oracle(g, st, trs, nb, dt)
+    N = g.N
+    mask = nmask.numpy()[:N]
+    dval = np.where(mask, (ora.dttf_h[0][:N] + ora.dttf_v[0][:N]) / np.where(mask, st.hnode_new.numpy()[:N], 1.0), 0.0)
+    assert np.abs(dval).max() <= 1e-11 * c0
